@@ -1,0 +1,1167 @@
+// sb_api.cu -- the C ABI of libsuma_b200 (include/suma_b200.h): context, frames, the operator-level entry points
+// (Preprocessing::process, SurfelMap::render*/update, Frame2Model::jacobianProducts, LieGaussNewton::minimize) and the
+// per-scan orchestration of SurfelMapping::processScan (core/SurfelMapping.cpp:175-210, 323-358, 372-476, 797-804).
+// There is no CPU fallback: without a CUDA device sb_create fails with SB_ERR_NOGPU.
+#include <chrono>
+#include <cmath>
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "sb_gn.cuh"
+#include "sb_internal.cuh"
+
+using namespace sb;
+
+struct sb_frame {
+  sb_ctx* ctx;
+  FrameDev d;
+  float4* base;
+};
+
+struct HostTile {  // SubmapCache, SurfelMap.h:179-181 (kept as SoA lanes in host memory)
+  std::vector<float4> p0, p1, p2, p3;
+};
+
+struct sb_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  sb_params p;
+  KParams kp;
+  std::string err;
+  uint64_t launches = 0;
+
+  // ---- preprocessing scratch
+  unsigned long long* keys_data = nullptr;  // P_data
+  float4* sem_raw = nullptr;
+  float4* eroded = nullptr;
+  float4* d_pts = nullptr;
+  float* d_labels = nullptr;
+  float* d_probs = nullptr;
+  size_t pts_cap = 0;
+
+  // ---- ICP
+  GnState* gn = nullptr;
+  long long* acc32 = nullptr;
+  unsigned int* ticket = nullptr;
+  void* h_pinned = nullptr;  // pinned staging for small read-backs (64 KiB)
+  int icp_blocks = 296;
+
+  // ---- map
+  SurfelPlanes A{}, T{}, G{}, X{};  // current surfels, updated (same index), generated (per pixel), extraction buffer
+  uint8_t* keep = nullptr;
+  uint32_t* block_counts = nullptr;
+  uint32_t* block_offsets = nullptr;
+  uint32_t* d_counts = nullptr;  // [0] n surfels, [1] n after update (base for new), [2] kept updated, [3] kept new, [4] extracted
+  float* poses = nullptr;        // device pose table, kMaxPoses x 16
+  float* poses_inv = nullptr;
+  std::vector<float> h_poses, h_poses_inv;
+  float* Mtab_old = nullptr;
+  float* Mtab_new = nullptr;
+  unsigned long long* key_old = nullptr;  // three model-size key images, contiguous
+  unsigned long long* key_new = nullptr;
+  unsigned long long* key_comp = nullptr;
+  unsigned long long* key_index = nullptr;
+  float4* radius_map = nullptr;
+  uint8_t* integrated = nullptr;
+  sb_frame* f_old = nullptr;
+  sb_frame* f_new = nullptr;
+  sb_frame* f_comp = nullptr;
+  uint32_t n_host = 0;   // surfel count (exact; refreshed after every update)
+  uint32_t n_updated = 0, n_new = 0;
+  uint32_t map_timestamp = 0;
+  int32_t origin_i = 0, origin_j = 0;
+  std::vector<std::pair<int32_t, int32_t>> extraction;
+  std::map<std::pair<int32_t, int32_t>, HostTile> tiles;
+
+  // ---- SurfelMapping state
+  sb_frame* cur = nullptr;
+  sb_frame* last = nullptr;
+  sb_frame* cur_model = nullptr;
+  sb_frame* last_model = nullptr;
+  uint32_t timestamp = 0;
+  double currentPose[16], lastPose[16], currentPose_old[16], currentPose_new[16], lastIncrement[16];
+  float confidence_threshold = 0.f, log_unstable_slam = 0.f;
+  double stats[16];
+  uint32_t trackLoss = 0;
+  bool cur_has_semantics = false, last_has_semantics = false;
+
+  // ---- multi-GPU
+  long long* mailbox = nullptr;
+  unsigned int* comm_epoch = nullptr;
+  CommDev comm{};
+  bool comm_on = false;
+  int row_begin = 0, row_end = 0;
+  std::vector<void*> peer_ptrs;
+};
+
+namespace {
+
+int fail(sb_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+#define SB_CUDA(ctx, call)                                                                              \
+  do {                                                                                                  \
+    cudaError_t e__ = (call);                                                                           \
+    if (e__ != cudaSuccess)                                                                             \
+      return fail(ctx, SB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));               \
+  } while (0)
+
+Launch L_(sb_ctx* c) { return Launch{c->stream, &c->launches}; }
+
+void ident_d(double* M) {
+  for (int i = 0; i < 16; ++i) M[i] = (i % 5 == 0) ? 1.0 : 0.0;
+}
+Mat4 mat4_from(const float* m) {
+  Mat4 r;
+  memcpy(r.m, m, 64);
+  return r;
+}
+void cast_f(const double* M, float* F) {
+  for (int i = 0; i < 16; ++i) F[i] = (float)M[i];
+}
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+float deg2rad_f(float d) { return d * (float)(3.14159265358979323846 / 180.0); }
+
+// host-side derived constants: SurfelMap.cpp:336-457, Preprocessing.cpp:76-117, Frame2Model.cpp:65-110
+void derive(sb_ctx* c) {
+  const sb_params& p = c->p;
+  KParams& k = c->kp;
+  memset(&k, 0, sizeof(k));
+  k.W = p.data_width; k.H = p.data_height; k.Wm = p.model_width; k.Hm = p.model_height;
+  k.fov_up = fabsf(p.data_fov_up); k.fov = fabsf(p.data_fov_up) + fabsf(p.data_fov_down);
+  k.min_depth = p.min_depth; k.max_depth = p.max_depth;
+  k.m_fov_up = fabsf(p.model_fov_up); k.m_fov = fabsf(p.model_fov_up) + fabsf(p.model_fov_down);
+  k.m_min_depth = p.model_min_depth; k.m_max_depth = p.model_max_depth;
+  k.weighting = p.weighting; k.bilinear = p.bilinear_sampling; k.factor = p.factor;
+  k.use_stability = p.use_stability; k.unstable_age = p.unstable_age; k.confidence_mode = p.confidence_mode;
+  k.active_timestamps = p.active_timestamps; k.weighting_scheme = p.weighting_scheme;
+  k.averaging_scheme = p.averaging_scheme; k.update_always = p.update_always;
+  k.confidence_threshold = p.confidence_threshold; k.p_stable = p.p_stable;
+  k.p_unstable = 1.0f - p.p_stable;                                   // SurfelMap.cpp:347
+  k.log_prior = (float)log(p.p_prior / (1.0 - p.p_prior));            // :349
+  k.log_unstable = (float)log(k.p_unstable / (1.0 - k.p_unstable));   // :350
+  k.sigma_angle = p.sigma_angle; k.sigma_distance = p.sigma_distance; k.max_weight = p.max_weight;
+  float vfov = fabsf(p.data_fov_up) + fabsf(p.data_fov_down);         // :339-344
+  float vpix = (float)tan(0.5f * ((double)vfov * 3.14159265358979323846 / 180.0) / (uint32_t)p.data_height);
+  float hpix = (float)tan(0.5f * ((double)360.0f * 3.14159265358979323846 / 180.0) / (uint32_t)p.data_width);
+  k.pixel_size = vpix > hpix ? vpix : hpix;
+  k.min_radius = p.min_radius; k.max_radius = p.max_radius;
+  k.radconf_angle_thresh = (float)cos((double)deg2rad_f(p.max_angle));     // :395
+  k.update_angle_thresh = (float)sin((double)deg2rad_f(p.map_max_angle));  // :407
+  k.map_max_distance = p.map_max_distance;
+  k.max_loop_closure_distance = p.max_loop_closure_distance;
+  k.label_offset_quirk = p.label_offset_quirk;
+  c->confidence_threshold = p.confidence_threshold;  // SurfelMapping.cpp:111-113
+  float pu = 0.1f;
+  c->log_unstable_slam = logf(pu / (1.0f - pu));     // SurfelMapping.cpp:108-109
+}
+
+int alloc_planes(sb_ctx* c, SurfelPlanes* s, size_t n) {
+  float4* base = nullptr;
+  SB_CUDA(c, cudaMalloc(&base, n * 4 * sizeof(float4)));
+  s->p0 = base; s->p1 = base + n; s->p2 = base + 2 * n; s->p3 = base + 3 * n;
+  return SB_OK;
+}
+void free_planes(SurfelPlanes* s) {
+  if (s->p0) cudaFree(s->p0);
+  s->p0 = s->p1 = s->p2 = s->p3 = nullptr;
+}
+
+int frame_create(sb_ctx* c, int w, int h, sb_frame** out) {
+  if (!c || w <= 0 || h <= 0 || !out) return fail(c, SB_ERR_INVALID, "frame_create: bad arguments");
+  sb_frame* f = new sb_frame();
+  f->ctx = c;
+  size_t P = (size_t)w * h;
+  cudaError_t e = cudaMalloc(&f->base, P * 3 * sizeof(float4));
+  if (e != cudaSuccess) {
+    delete f;
+    return fail(c, SB_ERR_NOMEM, std::string("frame alloc: ") + cudaGetErrorString(e));
+  }
+  cudaMemsetAsync(f->base, 0, P * 3 * sizeof(float4), c->stream);
+  f->d.W = w; f->d.H = h;
+  f->d.vertex = f->base; f->d.normal = f->base + P; f->d.semantic = f->base + 2 * P;
+  *out = f;
+  return SB_OK;
+}
+
+int release_buffers(sb_ctx* c) {
+  cudaFree(c->keys_data); cudaFree(c->sem_raw); cudaFree(c->eroded);
+  cudaFree(c->d_pts); cudaFree(c->d_labels); cudaFree(c->d_probs);
+  cudaFree(c->gn); cudaFree(c->acc32); cudaFree(c->ticket);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  free_planes(&c->A); free_planes(&c->T); free_planes(&c->G); free_planes(&c->X);
+  cudaFree(c->keep); cudaFree(c->block_counts); cudaFree(c->block_offsets); cudaFree(c->d_counts);
+  cudaFree(c->poses); cudaFree(c->poses_inv); cudaFree(c->Mtab_old); cudaFree(c->Mtab_new);
+  cudaFree(c->key_old); cudaFree(c->key_index); cudaFree(c->radius_map); cudaFree(c->integrated);
+  sb_frame* fr[] = {c->f_old, c->f_new, c->f_comp, c->cur, c->last, c->cur_model, c->last_model};
+  for (sb_frame* f : fr)
+    if (f) {
+      cudaFree(f->base);
+      delete f;
+    }
+  cudaFree(c->mailbox);
+  cudaFree(c->comm_epoch);
+  return SB_OK;
+}
+
+int reset_state(sb_ctx* c) {
+  // SurfelMap::reset (SurfelMap.cpp:473-482) + the SurfelMapping members set up in its constructor
+  c->n_host = 0; c->n_updated = 0; c->n_new = 0; c->map_timestamp = 0;
+  c->origin_i = c->origin_j = 0;
+  c->extraction.clear();
+  c->tiles.clear();
+  c->h_poses.assign((size_t)kMaxPoses * 16, 0.0f);
+  for (uint32_t t = 0; t < kMaxPoses; ++t)
+    for (int i = 0; i < 4; ++i) c->h_poses[16 * (size_t)t + 5 * i] = 1.0f;
+  c->h_poses_inv = c->h_poses;
+  SB_CUDA(c, cudaMemcpyAsync(c->poses, c->h_poses.data(), (size_t)kMaxPoses * 64, cudaMemcpyHostToDevice, c->stream));
+  SB_CUDA(c, cudaMemcpyAsync(c->poses_inv, c->h_poses.data(), (size_t)kMaxPoses * 64, cudaMemcpyHostToDevice, c->stream));
+  SB_CUDA(c, cudaMemsetAsync(c->d_counts, 0, 16 * sizeof(uint32_t), c->stream));
+  c->timestamp = 0;
+  ident_d(c->currentPose); ident_d(c->lastPose); ident_d(c->currentPose_old); ident_d(c->currentPose_new);
+  ident_d(c->lastIncrement);
+  memset(c->stats, 0, sizeof(c->stats));
+  c->trackLoss = 0;
+  c->cur_has_semantics = c->last_has_semantics = false;
+  sb_frame* fr[] = {c->f_old, c->f_new, c->f_comp, c->cur, c->last, c->cur_model, c->last_model};
+  for (sb_frame* f : fr)
+    if (f) SB_CUDA(c, cudaMemsetAsync(f->base, 0, (size_t)f->d.W * f->d.H * 3 * sizeof(float4), c->stream));
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SB_OK;
+}
+
+int alloc_buffers(sb_ctx* c) {
+  const sb_params& p = c->p;
+  size_t Pd = (size_t)p.data_width * p.data_height, Pm = (size_t)p.model_width * p.model_height;
+  SB_CUDA(c, cudaMalloc(&c->keys_data, Pd * 8));
+  SB_CUDA(c, cudaMalloc(&c->sem_raw, Pd * 16));
+  SB_CUDA(c, cudaMalloc(&c->eroded, Pd * 16));
+  c->pts_cap = Pd * 2 + 1024;
+  SB_CUDA(c, cudaMalloc(&c->d_pts, c->pts_cap * 16));
+  SB_CUDA(c, cudaMalloc(&c->d_labels, c->pts_cap * 4));
+  SB_CUDA(c, cudaMalloc(&c->d_probs, c->pts_cap * 4));
+  SB_CUDA(c, cudaMalloc(&c->gn, sizeof(GnState)));
+  SB_CUDA(c, cudaMalloc(&c->acc32, 32 * sizeof(long long)));
+  SB_CUDA(c, cudaMalloc(&c->ticket, 64));
+  SB_CUDA(c, cudaMemsetAsync(c->ticket, 0, 64, c->stream));
+  SB_CUDA(c, cudaMemsetAsync(c->acc32, 0, 32 * sizeof(long long), c->stream));
+  SB_CUDA(c, cudaMallocHost(&c->h_pinned, 65536));
+  int r;
+  if ((r = alloc_planes(c, &c->A, kMaxSurfels))) return r;
+  if ((r = alloc_planes(c, &c->T, kMaxSurfels))) return r;
+  if ((r = alloc_planes(c, &c->G, Pd))) return r;
+  if ((r = alloc_planes(c, &c->X, kExtractCap))) return r;
+  SB_CUDA(c, cudaMalloc(&c->keep, kMaxSurfels));
+  size_t nb = (kMaxSurfels + 255) / 256 + 16;
+  SB_CUDA(c, cudaMalloc(&c->block_counts, nb * 4));
+  SB_CUDA(c, cudaMalloc(&c->block_offsets, nb * 4));
+  SB_CUDA(c, cudaMalloc(&c->d_counts, 16 * sizeof(uint32_t)));
+  SB_CUDA(c, cudaMalloc(&c->poses, (size_t)kMaxPoses * 64));
+  SB_CUDA(c, cudaMalloc(&c->poses_inv, (size_t)kMaxPoses * 64));
+  SB_CUDA(c, cudaMalloc(&c->Mtab_old, (size_t)kMaxPoses * 64));
+  SB_CUDA(c, cudaMalloc(&c->Mtab_new, (size_t)kMaxPoses * 64));
+  SB_CUDA(c, cudaMalloc(&c->key_old, Pm * 8 * 3));
+  c->key_new = c->key_old + Pm;
+  c->key_comp = c->key_old + 2 * Pm;
+  SB_CUDA(c, cudaMalloc(&c->key_index, Pd * 8));
+  SB_CUDA(c, cudaMalloc(&c->radius_map, Pd * 16));
+  SB_CUDA(c, cudaMalloc(&c->integrated, Pd));
+  SB_CUDA(c, cudaMalloc(&c->comm_epoch, 64));
+  SB_CUDA(c, cudaMemsetAsync(c->comm_epoch, 0, 64, c->stream));
+  if ((r = frame_create(c, p.model_width, p.model_height, &c->f_old))) return r;
+  if ((r = frame_create(c, p.model_width, p.model_height, &c->f_new))) return r;
+  if ((r = frame_create(c, p.model_width, p.model_height, &c->f_comp))) return r;
+  if ((r = frame_create(c, p.data_width, p.data_height, &c->cur))) return r;
+  if ((r = frame_create(c, p.data_width, p.data_height, &c->last))) return r;
+  if ((r = frame_create(c, p.model_width, p.model_height, &c->cur_model))) return r;
+  if ((r = frame_create(c, p.model_width, p.model_height, &c->last_model))) return r;
+  return reset_state(c);
+}
+
+int t_threshold(const sb_ctx* c) { return (int)(c->map_timestamp - kComposeAge); }  // SurfelMap.cpp:873 (Q9)
+
+uint32_t pose_table_count(const sb_ctx* c) {
+  uint32_t n = c->map_timestamp + 1;
+  return n < kMaxPoses ? n : kMaxPoses;
+}
+
+int set_pose_entry(sb_ctx* c, uint32_t t, const float* pose) {
+  if (t >= kMaxPoses) return fail(c, SB_ERR_CAPACITY, "pose table full (10000 poses, SurfelMap.h:205)");
+  memcpy(&c->h_poses[16 * (size_t)t], pose, 64);
+  sbg::rigid_inverse_f(pose, &c->h_poses_inv[16 * (size_t)t]);
+  SB_CUDA(c, cudaMemcpyAsync(c->poses + 16 * (size_t)t, &c->h_poses[16 * (size_t)t], 64, cudaMemcpyHostToDevice, c->stream));
+  SB_CUDA(c, cudaMemcpyAsync(c->poses_inv + 16 * (size_t)t, &c->h_poses_inv[16 * (size_t)t], 64, cudaMemcpyHostToDevice,
+                             c->stream));
+  return SB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// rendering
+// ---------------------------------------------------------------------------------------------------------
+FrameDev null_frame() {
+  FrameDev f;
+  f.W = f.H = 0;
+  f.vertex = f.normal = f.semantic = nullptr;
+  return f;
+}
+
+int render_full(sb_ctx* c, const float* pose_old, const float* pose_new, float conf_thr, sb_frame* out) {
+  const KParams& kp = c->kp;
+  Launch L = L_(c);
+  size_t Pm = (size_t)kp.Wm * kp.Hm;
+  float inv_old[16], inv_new[16];
+  sbg::rigid_inverse_f(pose_old, inv_old);
+  sbg::rigid_inverse_f(pose_new, inv_new);
+  const bool same = memcmp(pose_old, pose_new, 64) == 0;
+  uint32_t np = pose_table_count(c);
+  launch_pose_products(L, mat4_from(inv_old), c->poses, c->Mtab_old, np);
+  float* Mnew = c->Mtab_old;
+  if (!same) {
+    launch_pose_products(L, mat4_from(inv_new), c->poses, c->Mtab_new, np);
+    Mnew = c->Mtab_new;
+  }
+  if (c->p.compose_rendering) {
+    launch_fill_u64(L, c->key_old, ~0ull, Pm * 3);
+    RenderTargets t{c->key_old, c->key_new, c->key_comp};
+    int thr = t_threshold(c);
+    if (same) {
+      launch_render_scatter(L, kp, c->A, c->d_counts, c->n_host, c->Mtab_old, conf_thr, thr, 1, 1, 0, t);
+    } else {
+      RenderTargets to{c->key_old, nullptr, c->key_comp}, tn{nullptr, c->key_new, c->key_comp};
+      launch_render_scatter(L, kp, c->A, c->d_counts, c->n_host, c->Mtab_old, conf_thr, thr, 1, 0, 0, to);
+      launch_render_scatter(L, kp, c->A, c->d_counts, c->n_host, Mnew, conf_thr, thr, 0, 1, 0, tn);
+    }
+    launch_render_resolve(L, kp, c->A, c->Mtab_old, Mnew, t, c->f_old->d, c->f_new->d, c->f_comp->d, out->d, 0, 0);
+  } else {
+    // SurfelMap.cpp:977-1017: one view with render_old_surfels = false, timestamp_threshold = 0, copied to old and new
+    launch_fill_u64(L, c->key_new, ~0ull, Pm);
+    RenderTargets t{nullptr, c->key_new, nullptr};
+    launch_render_scatter(L, kp, c->A, c->d_counts, c->n_host, c->Mtab_old, conf_thr, 0, 0, 1, 0, t);
+    launch_render_resolve(L, kp, c->A, c->Mtab_old, c->Mtab_old, t, null_frame(), c->f_new->d, null_frame(), null_frame(),
+                          0, 0);
+    SB_CUDA(c, cudaMemcpyAsync(c->f_old->base, c->f_new->base, Pm * 48, cudaMemcpyDeviceToDevice, c->stream));
+    SB_CUDA(c, cudaMemcpyAsync(out->base, c->f_new->base, Pm * 48, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  return SB_OK;
+}
+
+// which: 1 = active (new surfels into newMapFrame), 0 = inactive (old surfels into oldMapFrame); Q4: semantic map kept
+int render_single(sb_ctx* c, const float* pose, float conf_thr, int which) {
+  const KParams& kp = c->kp;
+  Launch L = L_(c);
+  size_t Pm = (size_t)kp.Wm * kp.Hm;
+  float inv[16];
+  sbg::rigid_inverse_f(pose, inv);
+  launch_pose_products(L, mat4_from(inv), c->poses, c->Mtab_old, pose_table_count(c));
+  unsigned long long* key = which ? c->key_new : c->key_old;
+  launch_fill_u64(L, key, ~0ull, Pm);
+  RenderTargets t{which ? nullptr : key, which ? key : nullptr, nullptr};
+  launch_render_scatter(L, kp, c->A, c->d_counts, c->n_host, c->Mtab_old, conf_thr, t_threshold(c), which ? 0 : 1,
+                        which ? 1 : 0, 0, t);
+  launch_render_resolve(L, kp, c->A, c->Mtab_old, c->Mtab_old, t, c->f_old->d, c->f_new->d, null_frame(), null_frame(), 1,
+                        0);
+  return SB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ICP
+// ---------------------------------------------------------------------------------------------------------
+IcpArgs icp_args(sb_ctx* c, const sb_frame* data, const sb_frame* model, float max_distance, float max_angle_deg,
+                 int row_begin, int row_end, bool semantics) {
+  IcpArgs a;
+  a.data_v = data->d.vertex; a.data_n = data->d.normal; a.data_s = data->d.semantic;
+  a.model_v = model->d.vertex; a.model_n = model->d.normal; a.model_s = model->d.semantic;
+  a.distance_thresh = max_distance;
+  a.angle_thresh = (float)cos((double)max_angle_deg * 3.14159265358979323846 / 180.0);  // Frame2Model.cpp:66
+  a.row_begin = row_begin; a.row_end = row_end;
+  a.has_semantics = semantics ? 1 : 0;
+  return a;
+}
+
+int icp_check(sb_ctx* c, const sb_frame* data, const sb_frame* model) {
+  if (!c || !data || !model) return fail(c, SB_ERR_INVALID, "icp: null argument");
+  if (data->d.W != c->kp.W || data->d.H != c->kp.H || model->d.W != c->kp.Wm || model->d.H != c->kp.Hm)
+    return fail(c, SB_ERR_INVALID, "icp: frame size does not match data_/model_ width/height");
+  return SB_OK;
+}
+
+int icp_jacobian_raw(sb_ctx* c, const sb_frame* data, const sb_frame* model, const double* pose, int iteration,
+                     float max_distance, float max_angle_deg, int r0, int r1, bool semantics, long long* raw) {
+  IcpArgs a = icp_args(c, data, model, max_distance, max_angle_deg, r0, r1, semantics);
+  Mat4 P;
+  for (int i = 0; i < 16; ++i) P.m[i] = (float)pose[i];  // pose_.cast<float>(), Frame2Model.cpp:194
+  launch_icp_jacobian(L_(c), c->kp, a, P, iteration, c->acc32, c->icp_blocks);
+  SB_CUDA(c, cudaMemcpyAsync(c->h_pinned, c->acc32, 32 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  memcpy(raw, c->h_pinned, 32 * sizeof(long long));
+  return SB_OK;
+}
+
+// enqueue the device-resident Gauss-Newton loop; the result stays in c->gn
+int icp_minimize_enqueue(sb_ctx* c, const sb_frame* data, const sb_frame* model, const double* T0, int max_iter,
+                         double eps, double delta, float max_distance, float max_angle_deg, bool semantics) {
+  if (max_iter <= 0 || max_iter > kMaxGnIter) max_iter = kMaxGnIter;
+  int r0 = 0, r1 = c->kp.H;
+  if (c->comm_on) {
+    r0 = c->row_begin;
+    r1 = c->row_end;
+  }
+  IcpArgs a = icp_args(c, data, model, max_distance, max_angle_deg, r0, r1, semantics);
+  Mat4d T;
+  memcpy(T.m, T0, sizeof(T.m));
+  Launch L = L_(c);
+  launch_gn_init(L, c->gn, T, c->acc32, c->ticket);
+  for (int i = 0; i < max_iter; ++i)
+    launch_icp_fused_iteration(L, c->kp, a, c->gn, c->acc32, c->ticket, max_iter, eps, delta,
+                               c->comm_on ? &c->comm : nullptr, c->icp_blocks);
+  return SB_OK;
+}
+
+struct GnHead {  // prefix of GnState copied back
+  double pose[16];
+  double last_error;
+  double out48[48];
+  int k, done, history_len, pad;
+};
+
+int icp_minimize_fetch(sb_ctx* c, double* pose_out, double* out48, int* iters, double* history, int* history_len) {
+  SB_CUDA(c, cudaMemcpyAsync(c->h_pinned, c->gn, sizeof(GnHead), cudaMemcpyDeviceToHost, c->stream));
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  GnHead h;
+  memcpy(&h, c->h_pinned, sizeof(h));
+  if (pose_out) memcpy(pose_out, h.pose, sizeof(h.pose));
+  if (out48) memcpy(out48, h.out48, sizeof(h.out48));
+  if (iters) *iters = h.k;
+  if (history_len) *history_len = h.history_len;
+  if (history && h.history_len > 0) {
+    SB_CUDA(c, cudaMemcpy(history, (const char*)c->gn + offsetof(GnState, history), (size_t)h.history_len * 128,
+                          cudaMemcpyDeviceToHost));
+  }
+  return SB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// map update: SurfelMap::update, SurfelMap.cpp:492-584
+// ---------------------------------------------------------------------------------------------------------
+float2 submap_center(const sb_ctx* c, int32_t i, int32_t j) {  // submapIndex2center, SurfelMap.cpp:704-706
+  return make_float2((float)(2.0 * i * c->p.submap_extent), (float)(2.0 * j * c->p.submap_extent));
+}
+
+int fetch_counts(sb_ctx* c, uint32_t* dst, int n) {
+  SB_CUDA(c, cudaMemcpyAsync(c->h_pinned, c->d_counts, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  memcpy(dst, c->h_pinned, n * sizeof(uint32_t));
+  return SB_OK;
+}
+
+int append_tiles(sb_ctx* c, int32_t i0, int32_t j0, int di, int dj) {  // SurfelMap.cpp:769-780
+  const int dim = c->p.submap_dimension;
+  for (int32_t k = -dim; k <= dim; ++k) {
+    HostTile& t = c->tiles[std::make_pair(i0 + di * k, j0 + dj * k)];
+    uint32_t room = kMaxSurfels - c->n_host;
+    uint32_t n = (uint32_t)t.p0.size();
+    if (n > room) n = room;
+    if (n == 0) continue;
+    SB_CUDA(c, cudaMemcpyAsync(c->A.p0 + c->n_host, t.p0.data(), (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    SB_CUDA(c, cudaMemcpyAsync(c->A.p1 + c->n_host, t.p1.data(), (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    SB_CUDA(c, cudaMemcpyAsync(c->A.p2 + c->n_host, t.p2.data(), (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    SB_CUDA(c, cudaMemcpyAsync(c->A.p3 + c->n_host, t.p3.data(), (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    c->n_host += n;
+  }
+  SB_CUDA(c, cudaMemcpyAsync(c->d_counts, &c->n_host, 4, cudaMemcpyHostToDevice, c->stream));
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));  // n_host is a stack-adjacent member; keep the copy ordered
+  return SB_OK;
+}
+
+int extract_surfels(sb_ctx* c, bool partially) {  // SurfelMap.cpp:708-742 + extract_surfels.vert
+  Launch L = L_(c);
+  while (!c->extraction.empty()) {
+    std::pair<int32_t, int32_t> idx = c->extraction.back();
+    c->extraction.pop_back();
+    float2 ctr = submap_center(c, idx.first, idx.second);
+    launch_extract_flags(L, c->A, c->d_counts, c->n_host, c->poses, ctr, c->p.submap_extent, c->keep, c->block_counts);
+    launch_compact(L, c->A, c->keep, c->block_counts, c->block_offsets, c->d_counts, c->n_host, c->X, nullptr,
+                   kExtractCap, c->d_counts + 4, nullptr);
+    uint32_t cnt[5];
+    int r = fetch_counts(c, cnt, 5);
+    if (r) return r;
+    uint32_t n = cnt[4];
+    HostTile& t = c->tiles[idx];
+    t.p0.resize(n); t.p1.resize(n); t.p2.resize(n); t.p3.resize(n);
+    if (n) {
+      SB_CUDA(c, cudaMemcpy(t.p0.data(), c->X.p0, (size_t)n * 16, cudaMemcpyDeviceToHost));
+      SB_CUDA(c, cudaMemcpy(t.p1.data(), c->X.p1, (size_t)n * 16, cudaMemcpyDeviceToHost));
+      SB_CUDA(c, cudaMemcpy(t.p2.data(), c->X.p2, (size_t)n * 16, cudaMemcpyDeviceToHost));
+      SB_CUDA(c, cudaMemcpy(t.p3.data(), c->X.p3, (size_t)n * 16, cudaMemcpyDeviceToHost));
+    }
+    if (partially) break;
+  }
+  return SB_OK;
+}
+
+int update_active_submaps(sb_ctx* c, const float* pose) {  // SurfelMap.cpp:744-824
+  const int dim = c->p.submap_dimension;
+  const float ext = c->p.submap_extent;
+  float2 ctr = submap_center(c, c->origin_i, c->origin_j);
+  float changex = pose[12] - ctr.x, changey = pose[13] - ctr.y;
+  float factor = 1.1f;
+  int r;
+  if (fabsf(changex) > factor * ext || fabsf(changey) > factor * ext) {
+    if (fabsf(changex) > factor * ext) {
+      int dir = changex < 0 ? -1 : 1;
+      for (int32_t k = -dim; k <= dim; ++k) c->extraction.push_back(std::make_pair(c->origin_i - dir * dim, c->origin_j + k));
+      c->origin_i += dir;
+      if ((r = append_tiles(c, c->origin_i + dir * dim, c->origin_j, 0, 1))) return r;
+    }
+    if (fabsf(changey) > factor * ext) {
+      int dir = changey < 0 ? -1 : 1;
+      for (int32_t k = -dim; k <= dim; ++k) c->extraction.push_back(std::make_pair(c->origin_i + k, c->origin_j - dir * dim));
+      c->origin_j += dir;
+      if ((r = append_tiles(c, c->origin_i, c->origin_j + dir * dim, 1, 0))) return r;
+    }
+  }
+  if (!c->extraction.empty()) return extract_surfels(c, c->p.partial_extraction != 0);
+  return SB_OK;
+}
+
+int map_update(sb_ctx* c, const float* pose, const sb_frame* frame) {
+  const KParams& kp = c->kp;
+  Launch L = L_(c);
+  const size_t Pd = (size_t)kp.W * kp.H;
+  int r;
+  if (c->map_timestamp < kMaxPoses) {
+    if ((r = set_pose_entry(c, c->map_timestamp, pose))) return r;  // SurfelMap.cpp:494-495
+  }
+  float inv_pose[16];
+  sbg::rigid_inverse_f(pose, inv_pose);  // :497
+  // K6a
+  launch_pose_products(L, mat4_from(inv_pose), c->poses, c->Mtab_old, pose_table_count(c));
+  launch_fill_u64(L, c->key_index, ~0ull, Pd);
+  launch_index_scatter(L, kp, c->A, c->d_counts, c->n_host, c->Mtab_old, c->key_index);
+  // K6b
+  launch_radius(L, kp, frame->d, c->radius_map);
+  // K6c + K6e predicate
+  SB_CUDA(c, cudaMemsetAsync(c->integrated, 0, Pd, c->stream));
+  float2 ctr = submap_center(c, c->origin_i, c->origin_j);
+  float extent = 2.0f * c->p.submap_dimension * c->p.submap_extent + c->p.submap_extent;  // :674
+  if (c->p.partial_extraction && !c->extraction.empty()) extent += 2.0f * c->p.submap_extent;  // :677
+  launch_update_surfels(L, kp, c->A, c->T, c->d_counts, c->n_host, mat4_from(pose), mat4_from(inv_pose), c->poses,
+                        c->poses_inv, c->key_index, c->radius_map, frame->d, (int)c->map_timestamp, ctr, extent,
+                        c->integrated, c->keep, c->block_counts);
+  // ordered compaction of the kept updated surfels back into the map: d_counts[1] = S'
+  launch_compact(L, c->T, c->keep, c->block_counts, c->block_offsets, c->d_counts, c->n_host, c->A, nullptr, kMaxSurfels,
+                 c->d_counts + 1, c->d_counts + 2);
+  // K6d + K6e predicate, appended behind the updated surfels
+  launch_gen_surfels(L, kp, frame->d, c->radius_map, c->integrated, c->poses, (int)c->map_timestamp, ctr, extent, c->G,
+                     c->keep, c->block_counts);
+  launch_compact(L, c->G, c->keep, c->block_counts, c->block_offsets, nullptr, (uint32_t)Pd, c->A, c->d_counts + 1,
+                 kMaxSurfels, c->d_counts, c->d_counts + 3);
+  uint32_t cnt[4];
+  if ((r = fetch_counts(c, cnt, 4))) return r;
+  c->n_host = cnt[0];
+  c->n_updated = cnt[2];
+  c->n_new = cnt[3];
+  if ((r = update_active_submaps(c, pose))) return r;  // :547
+  c->map_timestamp += 1;
+  return SB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SurfelMapping
+// ---------------------------------------------------------------------------------------------------------
+float conf_threshold(const sb_ctx* c) {  // SurfelMapping.cpp:333-340, time_init = 10
+  float ct = c->confidence_threshold;
+  if (c->timestamp < 10) {
+    float alpha = (float)c->timestamp / 10.0f;
+    ct = (float)((1.0 - (double)alpha) * (double)c->log_unstable_slam + (double)(alpha * c->confidence_threshold));
+  }
+  return ct;
+}
+
+int upload_scan(sb_ctx* c, const float* pts4, const float* labels, const float* probs, uint32_t n, int on_device,
+                const float4** d_pts, const float** d_labels, const float** d_probs) {
+  if (on_device) {
+    *d_pts = reinterpret_cast<const float4*>(pts4);
+    *d_labels = labels;
+    *d_probs = probs;
+    return SB_OK;
+  }
+  if (n > c->pts_cap) return fail(c, SB_ERR_CAPACITY, "scan larger than 2 * data_width * data_height points");
+  if (n) SB_CUDA(c, cudaMemcpyAsync(c->d_pts, pts4, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+  if (labels && n) SB_CUDA(c, cudaMemcpyAsync(c->d_labels, labels, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  if (probs && n) SB_CUDA(c, cudaMemcpyAsync(c->d_probs, probs, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  *d_pts = c->d_pts;
+  *d_labels = labels ? c->d_labels : nullptr;
+  *d_probs = probs ? c->d_probs : nullptr;
+  return SB_OK;
+}
+
+int update_pose(sb_ctx* c) {  // SurfelMapping::updatePose, SurfelMapping.cpp:372-476
+  const sb_params& p = c->p;
+  double T0[16];
+  if (!p.initialize_identity) memcpy(T0, c->lastIncrement, sizeof(T0)); else ident_d(T0);
+  const bool sem = c->cur_has_semantics;
+  int r;
+  // objective_->setData(currentFrame_, map_->newMapFrame()); gn_->minimize(*objective_, T0)   :384-389
+  if ((r = icp_minimize_enqueue(c, c->cur, c->f_new, T0, p.max_iterations, p.stopping_threshold, p.delta,
+                                p.icp_max_distance, p.icp_max_angle, sem)))
+    return r;
+  double increment[16], o48[48];
+  int iters = 0;
+  if ((r = icp_minimize_fetch(c, increment, o48, &iters, nullptr, nullptr))) return r;
+  c->stats[0] = iters;
+  double inv_last[16], delta[16];
+  sbg::rigid_inverse_d(c->lastIncrement, inv_last);
+  sbm::mat4_mul<double>(inv_last, increment, delta);  // :397
+  // :405-413: render_active at the new pose, copy into lastModelFrame_, statistics pass at identity
+  double Pn[16];
+  float Pf[16];
+  sbm::mat4_mul<double>(c->currentPose_new, increment, Pn);
+  cast_f(Pn, Pf);
+  if ((r = render_single(c, Pf, conf_threshold(c), 1))) return r;
+  size_t Pm = (size_t)c->kp.Wm * c->kp.Hm;
+  SB_CUDA(c, cudaMemcpyAsync(c->last_model->base, c->f_new->base, Pm * 48, cudaMemcpyDeviceToDevice, c->stream));
+  double I[16], r48[48];
+  long long raw[32];
+  ident_d(I);
+  int r0 = 0, r1 = c->kp.H;
+  if ((r = icp_jacobian_raw(c, c->cur, c->f_new, I, 0, p.icp_max_distance, p.icp_max_angle, r0, r1, sem, raw))) return r;
+  sbg::unpack48(raw, r48);
+  c->stats[1] = r48[43];
+  c->stats[3] = r48[44];
+  c->stats[2] = (double)((uint32_t)r48[42] - (uint32_t)r48[44]);  // Frame2Model.cpp:222-226
+  c->stats[4] = r48[46];
+  c->stats[5] = (float)r48[45];
+  // :430-449 track-loss test and frame-to-frame fallback
+  float t_err = (float)sqrt((delta[12] * delta[12] + delta[13] * delta[13]) + delta[14] * delta[14]);
+  float angle = (float)(0.5 * (((delta[0] + delta[5]) + delta[10]) - 1.0));
+  float ca = angle < 1.0f ? angle : 1.0f;
+  ca = ca > -1.0f ? ca : -1.0f;
+  float r_err = acosf(ca);
+  if (c->timestamp > 1 && (t_err > 0.4 || r_err > 0.1) && p.fallback_mode) {
+    c->trackLoss += 1;
+    if ((r = icp_minimize_enqueue(c, c->cur, c->last, T0, p.max_iterations, p.stopping_threshold, p.delta,
+                                  p.fallback_max_distance, p.fallback_max_angle, sem && c->last_has_semantics)))
+      return r;
+    if ((r = icp_minimize_fetch(c, increment, o48, &iters, nullptr, nullptr))) return r;
+  }
+  c->stats[6] = c->trackLoss;
+  memcpy(c->lastPose, c->currentPose, sizeof(c->lastPose));
+  double np[16];
+  sbm::mat4_mul<double>(c->currentPose, increment, np);  // :452
+  memcpy(c->currentPose, np, sizeof(np));
+  memcpy(c->currentPose_old, np, sizeof(np));
+  memcpy(c->currentPose_new, np, sizeof(np));
+  memcpy(c->lastIncrement, increment, sizeof(increment));  // :473
+  return SB_OK;
+}
+
+}  // namespace
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+extern "C" {
+
+int sb_default_params(sb_params* p) {
+  if (!p) return SB_ERR_INVALID;
+  memset(p, 0, sizeof(*p));
+  p->data_width = 900; p->data_height = 64;
+  p->data_fov_up = 3.0f; p->data_fov_down = -25.0f;
+  p->min_depth = 2.0f; p->max_depth = 75.0f;
+  p->model_width = 900; p->model_height = 64;
+  p->model_fov_up = 3.0f; p->model_fov_down = -25.0f;
+  p->model_min_depth = 2.0f; p->model_max_depth = 75.0f;
+  p->max_iterations = 33; p->stopping_threshold = 0.0001f; p->delta = 0.0001f;
+  p->icp_max_distance = 2.0f; p->icp_max_angle = 30.0f;
+  p->weighting = 1; p->factor = 0.5f;
+  p->initialize_identity = 0; p->bilinear_sampling = 1;
+  p->fallback_mode = 1; p->fallback_max_distance = 0.5f; p->fallback_max_angle = 30.0f;
+  p->compose_rendering = 1; p->max_loop_closure_distance = 8.0f;
+  p->min_radius = 0.03f; p->max_radius = 1.0f; p->max_angle = 90.0f;
+  p->map_max_distance = 0.2f; p->map_max_angle = 45.0f;
+  p->unstable_age = 3; p->confidence_mode = 3; p->confidence_threshold = 0.0f;
+  p->p_stable = 0.6f; p->p_prior = 0.5f; p->sigma_angle = 1.0f; p->sigma_distance = 1.0f;
+  p->use_stability = 1; p->active_timestamps = 100; p->max_weight = 20.0f;
+  p->weighting_scheme = 0; p->averaging_scheme = 0; p->update_always = 0;
+  p->submap_dimension = 4; p->submap_extent = 10.0f; p->partial_extraction = 1;
+  p->label_offset_quirk = 1; p->render_after_update = 1;
+  return SB_OK;
+}
+
+int sb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+static int check_params(const sb_params* p) {
+  if (!p) return SB_ERR_INVALID;
+  if (p->data_width <= 0 || p->data_height <= 0 || p->model_width <= 0 || p->model_height <= 0) return SB_ERR_INVALID;
+  if ((size_t)p->data_width * p->data_height > (1u << 24)) return SB_ERR_INVALID;
+  if (!(p->max_depth > p->min_depth) || !(p->model_max_depth > p->model_min_depth)) return SB_ERR_INVALID;
+  return SB_OK;
+}
+
+int sb_create(const sb_params* p, int device, sb_ctx** out) {
+  if (!out || check_params(p)) return SB_ERR_INVALID;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return SB_ERR_NOGPU;  // no CPU fallback
+  if (device < 0 || device >= n) return SB_ERR_INVALID;
+  sb_ctx* c = new sb_ctx();
+  c->device = device;
+  c->p = *p;
+  if (cudaSetDevice(device) != cudaSuccess) {
+    delete c;
+    return SB_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  c->icp_blocks = icp_grid_blocks(c->sm_count);
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return SB_ERR_CUDA;
+  }
+  derive(c);
+  int r = alloc_buffers(c);
+  if (r != SB_OK) {
+    fprintf(stderr, "sb_create: %s\n", c->err.c_str());
+    release_buffers(c);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return r;
+  }
+  *out = c;
+  return SB_OK;
+}
+
+int sb_destroy(sb_ctx* c) {
+  if (!c) return SB_ERR_INVALID;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  sb_comm_shutdown(c);
+  release_buffers(c);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return SB_OK;
+}
+
+int sb_reset(sb_ctx* c) {
+  if (!c) return SB_ERR_INVALID;
+  cudaSetDevice(c->device);
+  return reset_state(c);
+}
+
+int sb_set_params(sb_ctx* c, const sb_params* p) {
+  if (!c || check_params(p)) return fail(c, SB_ERR_INVALID, "set_params: bad parameters");
+  if (p->data_width != c->p.data_width || p->data_height != c->p.data_height || p->model_width != c->p.model_width ||
+      p->model_height != c->p.model_height)
+    return fail(c, SB_ERR_STATE, "set_params: image sizes are fixed at sb_create (as in SurfelMapping's constructor)");
+  c->p = *p;
+  derive(c);
+  return SB_OK;
+}
+
+const char* sb_last_error(const sb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int sb_synchronize(sb_ctx* c) {
+  if (!c) return SB_ERR_INVALID;
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SB_OK;
+}
+
+void* sb_stream(sb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+uint64_t sb_launch_count(const sb_ctx* c) { return c ? c->launches : 0; }
+
+int sb_frame_create(sb_ctx* c, int w, int h, sb_frame** out) {
+  if (!c) return SB_ERR_INVALID;
+  cudaSetDevice(c->device);
+  return frame_create(c, w, h, out);
+}
+int sb_frame_destroy(sb_frame* f) {
+  if (!f) return SB_ERR_INVALID;
+  cudaStreamSynchronize(f->ctx->stream);
+  cudaFree(f->base);
+  delete f;
+  return SB_OK;
+}
+int sb_frame_copy(sb_frame* dst, const sb_frame* src) {
+  if (!dst || !src || dst->d.W != src->d.W || dst->d.H != src->d.H) return SB_ERR_INVALID;
+  sb_ctx* c = dst->ctx;
+  SB_CUDA(c, cudaMemcpyAsync(dst->base, src->base, (size_t)src->d.W * src->d.H * 48, cudaMemcpyDeviceToDevice, c->stream));
+  return SB_OK;
+}
+static float4* frame_plane(const sb_frame* f, int which) {
+  return which == SB_MAP_VERTEX ? f->d.vertex : (which == SB_MAP_NORMAL ? f->d.normal : f->d.semantic);
+}
+int sb_frame_download(const sb_frame* f, int which, float* dst) {
+  if (!f || !dst || which < 0 || which > 2) return SB_ERR_INVALID;
+  sb_ctx* c = f->ctx;
+  SB_CUDA(c, cudaMemcpyAsync(dst, frame_plane(f, which), (size_t)f->d.W * f->d.H * 16, cudaMemcpyDeviceToHost, c->stream));
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SB_OK;
+}
+int sb_frame_upload(sb_frame* f, int which, const float* src) {
+  if (!f || !src || which < 0 || which > 2) return SB_ERR_INVALID;
+  sb_ctx* c = f->ctx;
+  SB_CUDA(c, cudaMemcpyAsync(frame_plane(f, which), src, (size_t)f->d.W * f->d.H * 16, cudaMemcpyHostToDevice, c->stream));
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SB_OK;
+}
+int sb_frame_size(const sb_frame* f, int* w, int* h) {
+  if (!f) return SB_ERR_INVALID;
+  if (w) *w = f->d.W;
+  if (h) *h = f->d.H;
+  return SB_OK;
+}
+
+int sb_preprocess(sb_ctx* c, const float* pts4, const float* labels, const float* probs, uint32_t n, uint32_t timestamp,
+                  int on_device, sb_frame* out) {
+  if (!c || !out || (!pts4 && n)) return fail(c, SB_ERR_INVALID, "preprocess: null argument");
+  if (out->d.W != c->kp.W || out->d.H != c->kp.H) return fail(c, SB_ERR_INVALID, "preprocess: frame size mismatch");
+  cudaSetDevice(c->device);
+  const float4* dp; const float* dl; const float* dq;
+  int r = upload_scan(c, pts4, labels, probs, n, on_device, &dp, &dl, &dq);
+  if (r) return r;
+  launch_preprocess(L_(c), c->kp, dp, dl, dq, n, timestamp, c->keys_data, c->sem_raw, c->eroded, out->d);
+  SB_CUDA(c, cudaGetLastError());
+  return SB_OK;
+}
+
+int sb_map_render(sb_ctx* c, const float pose_old[16], const float pose_new[16], float conf_thr, sb_frame* out) {
+  if (!c || !pose_old || !pose_new || !out) return fail(c, SB_ERR_INVALID, "map_render: null argument");
+  if (out->d.W != c->kp.Wm || out->d.H != c->kp.Hm) return fail(c, SB_ERR_INVALID, "map_render: frame size mismatch");
+  cudaSetDevice(c->device);
+  int r = render_full(c, pose_old, pose_new, conf_thr, out);
+  if (r) return r;
+  SB_CUDA(c, cudaGetLastError());
+  return SB_OK;
+}
+int sb_map_render_active(sb_ctx* c, const float pose[16], float conf_thr) {
+  if (!c || !pose) return fail(c, SB_ERR_INVALID, "map_render_active: null argument");
+  cudaSetDevice(c->device);
+  int r = render_single(c, pose, conf_thr, 1);
+  if (r) return r;
+  SB_CUDA(c, cudaGetLastError());
+  return SB_OK;
+}
+int sb_map_render_inactive(sb_ctx* c, const float pose[16], float conf_thr) {
+  if (!c || !pose) return fail(c, SB_ERR_INVALID, "map_render_inactive: null argument");
+  cudaSetDevice(c->device);
+  int r = render_single(c, pose, conf_thr, 0);
+  if (r) return r;
+  SB_CUDA(c, cudaGetLastError());
+  return SB_OK;
+}
+int sb_map_render_composed(sb_ctx* c, const float pose_old[16], const float pose_new[16], float conf_thr) {
+  if (!c || !pose_old || !pose_new) return fail(c, SB_ERR_INVALID, "map_render_composed: null argument");
+  cudaSetDevice(c->device);
+  const KParams& kp = c->kp;
+  Launch L = L_(c);
+  size_t Pm = (size_t)kp.Wm * kp.Hm;
+  float inv_old[16], inv_new[16];
+  sbg::rigid_inverse_f(pose_old, inv_old);
+  sbg::rigid_inverse_f(pose_new, inv_new);
+  uint32_t np = pose_table_count(c);
+  launch_pose_products(L, mat4_from(inv_old), c->poses, c->Mtab_old, np);
+  launch_pose_products(L, mat4_from(inv_new), c->poses, c->Mtab_new, np);
+  launch_fill_u64(L, c->key_comp, ~0ull, Pm);
+  RenderTargets t{nullptr, nullptr, c->key_comp};
+  int thr = t_threshold(c);
+  // GL_LEQUAL (SurfelMap.cpp:1126), old then new without clearing (:1146-1152); COLOR2 not attached (Q4)
+  launch_render_scatter(L, kp, c->A, c->d_counts, c->n_host, c->Mtab_old, conf_thr, thr, 1, 0, 1, t);
+  launch_render_scatter(L, kp, c->A, c->d_counts, c->n_host, c->Mtab_new, conf_thr, thr, 0, 1, 1, t);
+  launch_render_resolve(L, kp, c->A, c->Mtab_old, c->Mtab_new, t, null_frame(), null_frame(), c->f_comp->d, null_frame(), 1,
+                        1);
+  SB_CUDA(c, cudaGetLastError());
+  return SB_OK;
+}
+int sb_map_frame(sb_ctx* c, int which, sb_frame** out) {
+  if (!c || !out || which < 0 || which > 2) return SB_ERR_INVALID;
+  *out = which == SB_FRAME_OLD ? c->f_old : (which == SB_FRAME_NEW ? c->f_new : c->f_comp);
+  return SB_OK;
+}
+
+void sb_icp_unpack(const int64_t raw32[32], double out48[48]) { sbg::unpack48((const long long*)raw32, out48); }
+
+int sb_icp_jacobian(sb_ctx* c, const sb_frame* data, const sb_frame* model, const double pose[16], int iteration,
+                    float max_distance, float max_angle_deg, int row_begin, int row_end, double out48[48],
+                    int64_t raw32[32]) {
+  int r = icp_check(c, data, model);
+  if (r) return r;
+  if (!pose || row_begin < 0 || row_end > c->kp.H || row_begin > row_end)
+    return fail(c, SB_ERR_INVALID, "icp_jacobian: bad pose / row range");
+  cudaSetDevice(c->device);
+  long long raw[32];
+  if ((r = icp_jacobian_raw(c, data, model, pose, iteration, max_distance, max_angle_deg, row_begin, row_end, true, raw)))
+    return r;
+  if (raw32) memcpy(raw32, raw, sizeof(raw));
+  if (out48) sbg::unpack48(raw, out48);
+  return SB_OK;
+}
+
+int sb_icp_minimize(sb_ctx* c, const sb_frame* data, const sb_frame* model, const double T0[16], int max_iter, double eps,
+                    double delta, float max_distance, float max_angle_deg, double pose_out[16], double out48[48],
+                    int* iters, double* history, int* history_len) {
+  int r = icp_check(c, data, model);
+  if (r) return r;
+  if (!T0) return fail(c, SB_ERR_INVALID, "icp_minimize: null T0");
+  cudaSetDevice(c->device);
+  if ((r = icp_minimize_enqueue(c, data, model, T0, max_iter, eps, delta, max_distance, max_angle_deg, true))) return r;
+  if ((r = icp_minimize_fetch(c, pose_out, out48, iters, history, history_len))) return r;
+  SB_CUDA(c, cudaGetLastError());
+  return SB_OK;
+}
+
+void sb_se3_exp(const double x[6], double T[16]) { sbg::se3_exp(x, T); }
+
+void sb_se3_log(const double M[16], double x[6]) {  // lie_algebra.cpp:36-71 (not on the hot path; libm fp64)
+  for (int i = 0; i < 6; ++i) x[i] = 0.0;
+  double d = 0.5 * (((M[0] + M[5]) + M[10]) - 1.0);
+  double K[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (d < 1 - 1e-10) {
+    double theta = acos(d);
+    double f = theta / (2 * sin(theta));
+    for (int r = 0; r < 3; ++r)
+      for (int cc = 0; cc < 3; ++cc) K[r * 3 + cc] = f * (M[cc * 4 + r] - M[r * 4 + cc]);
+    x[3] = K[2 * 3 + 1]; x[4] = K[0 * 3 + 2]; x[5] = K[1 * 3 + 0];
+  }
+  double theta = sqrt((x[3] * x[3] + x[4] * x[4]) + x[5] * x[5]);
+  x[0] = M[12]; x[1] = M[13]; x[2] = M[14];
+  if (fabs(theta) > 1e-10) {
+    double half = 0.5 * theta;
+    double beta = 1 / (theta * theta) * (1 - theta * cos(half) / (2 * sin(half)));
+    double t[3] = {M[12], M[13], M[14]};
+    for (int r = 0; r < 3; ++r) {
+      double acc = 0;
+      for (int cc = 0; cc < 3; ++cc) {
+        double k2 = (K[r * 3 + 0] * K[0 * 3 + cc] + K[r * 3 + 1] * K[1 * 3 + cc]) + K[r * 3 + 2] * K[2 * 3 + cc];
+        double Vi = ((r == cc ? 1.0 : 0.0) + (-0.5) * K[r * 3 + cc]) + beta * k2;
+        acc += Vi * t[cc];
+      }
+      x[r] = acc;
+    }
+  }
+}
+
+int sb_ldlt_solve6(const double A[36], const double b[6], double x[6]) {
+  sbg::ldlt_solve6(A, b, x);
+  return SB_OK;
+}
+int sb_gn_step(const double out48[48], double last_error, double eps, double delta, double pose[16], double dx[6]) {
+  return sbg::gn_step(out48, last_error, eps, delta, pose, dx);
+}
+
+int sb_map_update(sb_ctx* c, const float pose[16], const sb_frame* frame) {
+  if (!c || !pose || !frame) return fail(c, SB_ERR_INVALID, "map_update: null argument");
+  if (frame->d.W != c->kp.W || frame->d.H != c->kp.H) return fail(c, SB_ERR_INVALID, "map_update: frame size mismatch");
+  cudaSetDevice(c->device);
+  int r = map_update(c, pose, frame);
+  if (r) return r;
+  SB_CUDA(c, cudaGetLastError());
+  return SB_OK;
+}
+
+int sb_map_update_poses(sb_ctx* c, const float* poses16, uint32_t count) {
+  if (!c || (!poses16 && count)) return SB_ERR_INVALID;
+  cudaSetDevice(c->device);
+  for (uint32_t t = 0; t < count && t < kMaxPoses; ++t) {
+    int r = set_pose_entry(c, t, poses16 + 16 * (size_t)t);
+    if (r) return r;
+  }
+  return SB_OK;
+}
+int sb_map_set_pose(sb_ctx* c, uint32_t t, const float pose[16]) {
+  if (!c || !pose) return SB_ERR_INVALID;
+  cudaSetDevice(c->device);
+  return set_pose_entry(c, t, pose);
+}
+int sb_map_size(sb_ctx* c, uint32_t* n) {
+  if (!c || !n) return SB_ERR_INVALID;
+  *n = c->n_host;
+  return SB_OK;
+}
+int sb_map_timestamp(sb_ctx* c, uint32_t* t) {
+  if (!c || !t) return SB_ERR_INVALID;
+  *t = c->map_timestamp;
+  return SB_OK;
+}
+int sb_map_download(sb_ctx* c, sb_surfel* dst, uint32_t cap, uint32_t* n) {
+  if (!c || (!dst && cap)) return SB_ERR_INVALID;
+  cudaSetDevice(c->device);
+  uint32_t k = c->n_host < cap ? c->n_host : cap;
+  if (n) *n = k;
+  if (k == 0) return SB_OK;
+  // transpose the SoA lanes into 64-byte records inside the (idle) T lanes, then one D2H copy
+  launch_soa_to_aos(L_(c), c->A, reinterpret_cast<sb_surfel*>(c->T.p0), k);
+  SB_CUDA(c, cudaMemcpyAsync(dst, c->T.p0, (size_t)k * 64, cudaMemcpyDeviceToHost, c->stream));
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SB_OK;
+}
+int sb_map_upload(sb_ctx* c, const sb_surfel* src, uint32_t n, uint32_t timestamp) {
+  if (!c || (!src && n)) return SB_ERR_INVALID;
+  if (n > kMaxSurfels) return fail(c, SB_ERR_CAPACITY, "map_upload: more than 4194304 surfels");
+  cudaSetDevice(c->device);
+  if (n) {
+    SB_CUDA(c, cudaMemcpyAsync(c->T.p0, src, (size_t)n * 64, cudaMemcpyHostToDevice, c->stream));
+    launch_aos_to_soa(L_(c), reinterpret_cast<const sb_surfel*>(c->T.p0), c->A, 0, n);
+  }
+  c->n_host = n;
+  c->map_timestamp = timestamp;
+  SB_CUDA(c, cudaMemcpyAsync(c->d_counts, &c->n_host, 4, cudaMemcpyHostToDevice, c->stream));
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SB_OK;
+}
+int sb_map_update_debug(sb_ctx* c, uint32_t* index_map, float* radius_map4, uint8_t* integrated, uint32_t* n_updated,
+                        uint32_t* n_new) {
+  if (!c) return SB_ERR_INVALID;
+  cudaSetDevice(c->device);
+  size_t Pd = (size_t)c->kp.W * c->kp.H;
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (index_map) {
+    std::vector<unsigned long long> keys(Pd);
+    SB_CUDA(c, cudaMemcpy(keys.data(), c->key_index, Pd * 8, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < Pd; ++i) index_map[i] = keys[i] == ~0ull ? 0u : (uint32_t)(keys[i] & 0xffffffffull) + 1u;
+  }
+  if (radius_map4) SB_CUDA(c, cudaMemcpy(radius_map4, c->radius_map, Pd * 16, cudaMemcpyDeviceToHost));
+  if (integrated) SB_CUDA(c, cudaMemcpy(integrated, c->integrated, Pd, cudaMemcpyDeviceToHost));
+  if (n_updated) *n_updated = c->n_updated;
+  if (n_new) *n_new = c->n_new;
+  return SB_OK;
+}
+int sb_map_submap_origin(sb_ctx* c, int32_t* i, int32_t* j, uint32_t* pending) {
+  if (!c) return SB_ERR_INVALID;
+  if (i) *i = c->origin_i;
+  if (j) *j = c->origin_j;
+  if (pending) *pending = (uint32_t)c->extraction.size();
+  return SB_OK;
+}
+
+int sb_process_scan(sb_ctx* c, const float* pts4, const float* labels, const float* probs, uint32_t n, int on_device) {
+  if (!c || (!pts4 && n)) return fail(c, SB_ERR_INVALID, "process_scan: null argument");
+  cudaSetDevice(c->device);
+  const sb_params& p = c->p;
+  double t_all = now_s();
+  // initialize(), SurfelMapping.cpp:323-331
+  std::swap(c->cur, c->last);
+  std::swap(c->cur_model, c->last_model);
+  c->last_has_semantics = c->cur_has_semantics;
+  c->cur_has_semantics = labels != nullptr;
+  // preprocess(), :342-358
+  double t0 = now_s();
+  const float4* dp; const float* dl; const float* dq;
+  int r = upload_scan(c, pts4, labels, probs, n, on_device, &dp, &dl, &dq);
+  if (r) return r;
+  launch_preprocess(L_(c), c->kp, dp, dl, dq, n, c->timestamp, c->keys_data, c->sem_raw, c->eroded, c->cur->d);
+  float ct = conf_threshold(c);
+  float Pold[16], Pnew[16];
+  cast_f(c->currentPose_old, Pold);
+  cast_f(c->currentPose_new, Pnew);
+  if ((r = render_full(c, Pold, Pnew, ct, c->last_model))) return r;
+  c->stats[8] = now_s() - t0;
+  t0 = now_s();
+  if (c->timestamp > 0 && (r = update_pose(c))) return r;
+  c->stats[9] = now_s() - t0;
+  // updateMap(), :797-804
+  t0 = now_s();
+  float Pc[16];
+  cast_f(c->currentPose, Pc);
+  if ((r = map_update(c, Pc, c->cur))) return r;
+  if (p.render_after_update) {
+    ct = conf_threshold(c);
+    if ((r = render_full(c, Pc, Pc, ct, c->cur_model))) return r;
+  }
+  c->stats[10] = now_s() - t0;
+  c->stats[7] = c->n_host;
+  SB_CUDA(c, cudaGetLastError());
+  c->stats[11] = now_s() - t_all;
+  c->timestamp += 1;
+  return SB_OK;
+}
+
+int sb_get_pose(sb_ctx* c, double pose[16]) {
+  if (!c || !pose) return SB_ERR_INVALID;
+  memcpy(pose, c->currentPose, sizeof(c->currentPose));
+  return SB_OK;
+}
+int sb_timestamp(sb_ctx* c, uint32_t* t) {
+  if (!c || !t) return SB_ERR_INVALID;
+  *t = c->timestamp;
+  return SB_OK;
+}
+int sb_slam_frame(sb_ctx* c, int which, sb_frame** out) {
+  if (!c || !out || which < 0 || which > 3) return SB_ERR_INVALID;
+  sb_frame* f[4] = {c->cur, c->last, c->cur_model, c->last_model};
+  *out = f[which];
+  return SB_OK;
+}
+int sb_get_statistics(sb_ctx* c, double stats[16]) {
+  if (!c || !stats) return SB_ERR_INVALID;
+  memcpy(stats, c->stats, sizeof(c->stats));
+  return SB_OK;
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------------------------
+int sb_comm_export(sb_ctx* c, uint8_t handle[64]) {
+  if (!c || !handle) return SB_ERR_INVALID;
+  cudaSetDevice(c->device);
+  if (!c->mailbox) {
+    SB_CUDA(c, cudaMalloc(&c->mailbox, 2 * 8 * 40 * sizeof(long long)));
+    SB_CUDA(c, cudaMemset(c->mailbox, 0, 2 * 8 * 40 * sizeof(long long)));
+  }
+  cudaIpcMemHandle_t h;
+  SB_CUDA(c, cudaIpcGetMemHandle(&h, c->mailbox));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle, &h, 64);
+  return SB_OK;
+}
+
+int sb_comm_init(sb_ctx* c, int rank, int nranks, const uint8_t* handles, int row_begin, int row_end) {
+  if (!c || !handles || nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks)
+    return fail(c, SB_ERR_INVALID, "comm_init: bad rank / nranks (max 8)");
+  if (row_begin < 0 || row_end > c->kp.H || row_begin > row_end) return fail(c, SB_ERR_INVALID, "comm_init: bad rows");
+  if (!c->mailbox) return fail(c, SB_ERR_STATE, "comm_init: call sb_comm_export first");
+  cudaSetDevice(c->device);
+  memset(&c->comm, 0, sizeof(c->comm));
+  c->comm.rank = rank;
+  c->comm.nranks = nranks;
+  c->comm.epoch = c->comm_epoch;
+  c->peer_ptrs.clear();
+  for (int r = 0; r < nranks; ++r) {
+    if (r == rank) {
+      c->comm.mailbox[r] = c->mailbox;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * (size_t)r, 64);
+    void* ptr = nullptr;
+    SB_CUDA(c, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    c->comm.mailbox[r] = (long long*)ptr;
+    c->peer_ptrs.push_back(ptr);
+  }
+  SB_CUDA(c, cudaMemset(c->comm_epoch, 0, 64));
+  c->row_begin = row_begin;
+  c->row_end = row_end;
+  c->comm_on = nranks > 1;
+  return SB_OK;
+}
+
+int sb_comm_shutdown(sb_ctx* c) {
+  if (!c) return SB_ERR_INVALID;
+  for (void* p : c->peer_ptrs) cudaIpcCloseMemHandle(p);
+  c->peer_ptrs.clear();
+  c->comm_on = false;
+  return SB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+// sb_internal.cuh -- internal declarations shared by the kernels and the C-ABI layer of libsuma_b200.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/suma_b200.h"
+#include "sb_math.cuh"
+
+namespace sb {
+
+constexpr uint32_t kMaxSurfels = 2048u * 2048u;  // SurfelMap.h:87
+constexpr uint32_t kMaxPoses = 10000u;           // SurfelMap.h:205
+constexpr uint32_t kExtractCap = 500000u;        // SurfelMap.cpp:279
+constexpr uint32_t kComposeAge = 100u;           // SurfelMap.h:144
+constexpr int kMaxGnIter = 256;
+
+// everything the kernels need from sb_params plus the derived constants the reference computes on the host
+struct KParams {
+  int W, H, Wm, Hm;
+  float fov_up, fov, min_depth, max_depth;          // data image (abs values, Preprocessing.cpp:94-95)
+  float m_fov_up, m_fov, m_min_depth, m_max_depth;  // model image (SurfelMap.cpp:440-443)
+  int weighting, bilinear;
+  float factor;
+  int use_stability, unstable_age, confidence_mode, active_timestamps;
+  int weighting_scheme, averaging_scheme, update_always;
+  float confidence_threshold, p_stable, p_unstable, log_prior, log_unstable;
+  float sigma_angle, sigma_distance, max_weight;
+  float pixel_size, min_radius, max_radius, radconf_angle_thresh, update_angle_thresh, map_max_distance;
+  float max_loop_closure_distance;
+  int label_offset_quirk;
+};
+
+// Frame.h:21-79: three RGBA32F images; one allocation, SoA of images
+struct FrameDev {
+  int W, H;
+  float4* vertex;
+  float4* normal;
+  float4* semantic;
+};
+
+// Surfel store: structure of arrays of 16-byte lanes so that every pass streams exactly the lanes it needs with
+// fully coalesced 128-bit accesses (the reference keeps 64-byte AoS records, Surfel.h:5-15):
+//   p0 = (x, y, z, radius)   p1 = (nx, ny, nz, confidence)
+//   p2 = (timestamp:u32, color, weight, count)   p3 = (r, g, b, w)  semantic label/255 x3 + probability
+struct SurfelPlanes {
+  float4* p0;
+  float4* p1;
+  float4* p2;
+  float4* p3;
+};
+
+// ---- device state of one fused Gauss-Newton run (LieGaussNewton.cpp:13-79) ----
+struct GnState {
+  double pose[16];       // Tk_
+  double last_error;     // last_error
+  double out48[48];      // sums of the last evaluated iteration
+  int k;                 // k_
+  int done;              // loop left (converged or max iterations)
+  int history_len;
+  int pad;
+  double history[(kMaxGnIter + 1) * 16];
+};
+
+struct IcpArgs {
+  const float4* data_v; const float4* data_n; const float4* data_s;
+  const float4* model_v; const float4* model_n; const float4* model_s;
+  float distance_thresh, angle_thresh;  // Frame2Model.cpp:66-67
+  int row_begin, row_end;
+  int has_semantics;
+};
+
+// peer mailboxes for the multi-GPU one-shot all-reduce (fused into the Jacobian kernel's last block)
+struct CommDev {
+  int rank, nranks;
+  long long* mailbox[8];  // mailbox[r]: rank r's mailbox (peer-mapped): [epoch parity 2][source rank 8][40] int64
+  unsigned int* epoch;    // local all-reduce counter (identical on every rank by construction)
+};
+
+struct Mat4 {
+  float m[16];
+};
+struct Mat4d {
+  double m[16];
+};
+
+// ---------------- launchers (implemented in the .cu files) ----------------
+struct Launch {
+  cudaStream_t stream;
+  uint64_t* counter;  // number of kernels launched
+};
+
+// sb_preprocess.cu
+void launch_preprocess(const Launch& L, const KParams& kp, const float4* pts, const float* labels, const float* probs,
+                       uint32_t n, uint32_t timestamp, unsigned long long* keys, float4* sem_raw, float4* eroded,
+                       FrameDev out);
+
+// sb_icp.cu
+void launch_icp_jacobian(const Launch& L, const KParams& kp, const IcpArgs& a, const Mat4& pose, int iteration,
+                         long long* acc32, int blocks);
+void launch_icp_fused_iteration(const Launch& L, const KParams& kp, const IcpArgs& a, GnState* st, long long* acc32,
+                                unsigned int* ticket, int max_iter, double eps, double delta, const CommDev* comm,
+                                int blocks);
+void launch_gn_init(const Launch& L, GnState* st, const Mat4d& T0, long long* acc32, unsigned int* ticket);
+int icp_grid_blocks(int sm_count);
+
+// sb_map.cu
+struct RenderTargets {
+  unsigned long long* key_old;   // may be null
+  unsigned long long* key_new;   // may be null
+  unsigned long long* key_comp;  // may be null
+};
+void launch_pose_products(const Launch& L, const Mat4& A, const float* poses, float* out, uint32_t count);
+void launch_render_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, const uint32_t* n_dev, uint32_t n_upper,
+                           const float* M, float conf_thr, int t_thr, int emit_old, int emit_new, int lequal,
+                           RenderTargets t);
+void launch_render_resolve(const Launch& L, const KParams& kp, SurfelPlanes s, const float* M_old, const float* M_new,
+                           RenderTargets t, FrameDev f_old, FrameDev f_new, FrameDev f_comp, FrameDev f_out,
+                           int keep_semantic, int lequal);
+void launch_index_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, const uint32_t* n_dev, uint32_t n_upper,
+                          const float* M, unsigned long long* keys);
+void launch_radius(const Launch& L, const KParams& kp, FrameDev frame, float4* radius_map);
+void launch_update_surfels(const Launch& L, const KParams& kp, SurfelPlanes src, SurfelPlanes tmp, const uint32_t* n_dev,
+                           uint32_t n_upper, const Mat4& pose, const Mat4& inv_pose, const float* poses,
+                           const float* poses_inv, const unsigned long long* index_keys, const float4* radius_map,
+                           FrameDev frame, int timestamp, float2 submap_center, float submap_extent,
+                           uint8_t* integrated, uint8_t* keep, uint32_t* block_counts);
+void launch_gen_surfels(const Launch& L, const KParams& kp, FrameDev frame, const float4* radius_map,
+                        const uint8_t* integrated, const float* poses, int timestamp, float2 submap_center,
+                        float submap_extent, SurfelPlanes tmp, uint8_t* keep, uint32_t* block_counts);
+// ordered compaction: items flagged in keep[0..n) of src go to dst[base..) in order; *count_out = base + #kept
+void launch_compact(const Launch& L, SurfelPlanes src, const uint8_t* keep, const uint32_t* block_counts,
+                    uint32_t* block_offsets, const uint32_t* n_dev, uint32_t n_upper, SurfelPlanes dst,
+                    const uint32_t* base_dev, uint32_t cap, uint32_t* count_out, uint32_t* kept_out);
+void launch_extract_flags(const Launch& L, SurfelPlanes s, const uint32_t* n_dev, uint32_t n_upper, const float* poses,
+                          float2 center, float extent, uint8_t* keep, uint32_t* block_counts);
+void launch_aos_to_soa(const Launch& L, const sb_surfel* aos, SurfelPlanes s, uint32_t offset, uint32_t n);
+void launch_soa_to_aos(const Launch& L, SurfelPlanes s, sb_surfel* aos, uint32_t n);
+void launch_fill_u64(const Launch& L, unsigned long long* p, unsigned long long v, size_t n);
+
+}  // namespace sb

@@ -1,0 +1,722 @@
+// sb_map.cu -- K4 (model rendering) and K6 (surfel update / initialise / merge) of the surfel map.
+// Replaces SurfelMap::render* (core/SurfelMap.cpp:847-1165; render_surfels.{vert,geom,frag}, render_compose.frag)
+// and SurfelMap::update (core/SurfelMap.cpp:492-698; gen_indexmap, init_radiusConf, update_surfels, gen_surfels,
+// copy_surfels, extract_surfels).
+//
+// B200 mapping
+//  * GL triangle rasterisation + 24-bit z-buffer  ->  one thread per surfel walks the quad's pixel bounding box
+//    with exact integer edge functions and resolves visibility with a 64-bit atomicMin on
+//    (depth24 << 40 | pass << 32 | surfel index): "earliest primitive wins" falls out of the key order.
+//    One pass over the surfel lanes feeds the old / new / composed views at once (the reference draws the whole
+//    buffer four times per render()).
+//  * transform feedback (ordered stream compaction)  ->  per-block counts + a single-block scan + an ordered scatter,
+//    so surfel order (and therefore every surfel index) is identical to the reference's.
+//  * surfels live as four float4 lanes (SoA), every pass streams only the lanes it needs with 128-bit accesses.
+#include "sb_gn.cuh"
+#include "sb_internal.cuh"
+
+namespace sb {
+using namespace sbm;
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ int pose_index(float count) {
+  int c = (int)count;
+  c = c < 0 ? 0 : c;
+  c = c >= (int)kMaxPoses ? (int)kMaxPoses - 1 : c;
+  return c;
+}
+
+__device__ __forceinline__ void load_mat(const float* __restrict__ table, int idx, float* M) {
+  const float4* t = reinterpret_cast<const float4*>(table + 16 * (size_t)idx);
+  float4 a = __ldg(t), b = __ldg(t + 1), c = __ldg(t + 2), d = __ldg(t + 3);
+  M[0] = a.x; M[1] = a.y; M[2] = a.z; M[3] = a.w;
+  M[4] = b.x; M[5] = b.y; M[6] = b.z; M[7] = b.w;
+  M[8] = c.x; M[9] = c.y; M[10] = c.z; M[11] = c.w;
+  M[12] = d.x; M[13] = d.y; M[14] = d.z; M[15] = d.w;
+}
+
+// out[t] = A * poses[t]  (render_surfels.vert:46 evaluates (inv_pose * surfelPose) * v; the product is shared by all
+// surfels created at time t)
+__global__ void k_pose_products(Mat4 A, const float* __restrict__ poses, float* __restrict__ out, uint32_t count) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  float a[16], b[16], c[16];
+  for (int i = 0; i < 16; ++i) a[i] = A.m[i];
+  load_mat(poses, (int)t, b);
+  mat4_mul<float>(a, b, c);
+  for (int i = 0; i < 16; ++i) out[16 * (size_t)t + i] = c[i];
+}
+
+void launch_pose_products(const Launch& L, const Mat4& A, const float* poses, float* out, uint32_t count) {
+  if (count == 0) return;
+  k_pose_products<<<(count + 127) / 128, 128, 0, L.stream>>>(A, poses, out, count);
+  ++*L.counter;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K4 rasteriser
+// ------------------------------------------------------------------------------------------------------------
+struct RVert {
+  long long X, Y;
+  float z, tx, ty;
+};
+
+__device__ __forceinline__ long long floor_div256(long long a) { return a >> 8; }  // arithmetic shift = floor
+__device__ __forceinline__ long long ceil_div256(long long a) { return -((-a) >> 8); }
+__device__ __forceinline__ long long edge_fn(const RVert& P, const RVert& Q, long long X, long long Y) {
+  return (Q.X - P.X) * (Y - P.Y) - (Q.Y - P.Y) * (X - P.X);
+}
+__device__ __forceinline__ bool edge_in(long long w, const RVert& P, const RVert& Q) {
+  if (w > 0) return true;
+  if (w < 0) return false;
+  long long dx = Q.X - P.X, dy = Q.Y - P.Y;
+  return dy > 0 || (dy == 0 && dx > 0);
+}
+
+struct EmitCtx {
+  unsigned long long* key_a;   // old or new image (LESS, pass bit 0)
+  unsigned long long* key_b;   // second class image when a surfel is both old and new
+  unsigned long long* key_c;   // composed image
+  unsigned long long low_a, low_b;            // idx
+  unsigned long long low_c_old, low_c_new;    // (pass << 32 | idx) or the inverted LEQUAL form
+  bool to_a, to_b, c_old, c_new;
+  bool lequal;
+  int W, H;
+};
+
+__device__ __forceinline__ void raster_tri(const EmitCtx& e, RVert A, RVert B, RVert C) {
+  long long area = (B.X - A.X) * (C.Y - A.Y) - (B.Y - A.Y) * (C.X - A.X);
+  if (area == 0) return;
+  if (area < 0) {
+    RVert t = B;
+    B = C;
+    C = t;
+    area = -area;
+  }
+  long long minX = min(A.X, min(B.X, C.X)), maxX = max(A.X, max(B.X, C.X));
+  long long minY = min(A.Y, min(B.Y, C.Y)), maxY = max(A.Y, max(B.Y, C.Y));
+  long long i0 = ceil_div256(minX - 128), i1 = floor_div256(maxX - 128);
+  long long j0 = ceil_div256(minY - 128), j1 = floor_div256(maxY - 128);
+  if (i0 < 0) i0 = 0;
+  if (j0 < 0) j0 = 0;
+  if (i1 > e.W - 1) i1 = e.W - 1;
+  if (j1 > e.H - 1) j1 = e.H - 1;
+  const float farea = (float)area;
+  for (long long j = j0; j <= j1; ++j)
+    for (long long i = i0; i <= i1; ++i) {
+      long long X = i * 256 + 128, Y = j * 256 + 128;
+      long long wA = edge_fn(B, C, X, Y), wB = edge_fn(C, A, X, Y), wC = edge_fn(A, B, X, Y);
+      if (!edge_in(wA, B, C) || !edge_in(wB, C, A) || !edge_in(wC, A, B)) continue;
+      float fB = (float)wB / farea, fC = (float)wC / farea;
+      float fA = (1.0f - fB) - fC;
+      float tx = (fA * A.tx + fB * B.tx) + fC * C.tx;
+      float ty = (fA * A.ty + fB * B.ty) + fC * C.ty;
+      if (tx * tx + ty * ty > 1.0f) continue;  // render_surfels.frag:22-28
+      float z = (fA * A.z + fB * B.z) + fC * C.z;
+      if (!(z >= 0.0f && z <= 1.0f)) continue;  // near / far clip
+      unsigned long long d = (unsigned long long)depth24(z);
+      if (!e.lequal && d >= kDepthClear) continue;  // GL_LESS against the cleared depth
+      size_t pix = (size_t)j * e.W + (size_t)i;
+      unsigned long long hi = d << 40;
+      if (e.to_a) atomicMin(e.key_a + pix, hi | e.low_a);
+      if (e.to_b) atomicMin(e.key_b + pix, hi | e.low_b);
+      if (e.c_old) atomicMin(e.key_c + pix, hi | e.low_c_old);
+      if (e.c_new) atomicMin(e.key_c + pix, hi | e.low_c_new);
+    }
+}
+
+// render_surfels.vert:42-54 + .geom:76-122 for every surfel of the map
+__global__ void __launch_bounds__(kThreads) k_render_scatter(KParams kp, SurfelPlanes s, const uint32_t* __restrict__ n_dev,
+                                                            const float* __restrict__ Mtab, float conf_thr, int t_thr,
+                                                            int emit_old, int emit_new, int lequal, RenderTargets t) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= *n_dev) return;
+  float4 p2 = __ldg(s.p2 + k);
+  float4 p1 = __ldg(s.p1 + k);
+  if (!(!kp.use_stability || p1.w > conf_thr)) return;  // .geom:87 (cheap test first)
+  int creation = (int)p2.w, ts = (int)__float_as_uint(p2.x);
+  bool is_old = emit_old && (creation < t_thr);                       // .geom:90
+  bool is_new = emit_new && (creation >= t_thr || ts >= t_thr);       // .geom:91
+  if (!is_old && !is_new) return;
+  float4 p0 = __ldg(s.p0 + k);
+  float M[16];
+  load_mat(Mtab, pose_index(p2.w), M);
+  V3 pp = xform_point(M, mk3(p0.x, p0.y, p0.z));
+  V3 nn = xform_dir(M, mk3(p1.x, p1.y, p1.z));
+  float r = p0.w;
+  bool visible = dot3(nn, divs3(neg3(pp), len3(pp))) > 0.01f;  // .geom:84
+  float cx, cy, cz;
+  project01(pp, kp.m_fov_up, kp.m_fov, kp.m_min_depth, kp.m_max_depth, cx, cy, cz);
+  if (!(visible && cx >= 0.0f && cy >= 0.0f && cz >= 0.0f && cx < 1.0f && cy < 1.0f && cz < 1.0f)) return;
+  V3 u = normalize3(mk3(nn.y - nn.z, -nn.x, nn.x));
+  V3 v = normalize3(cross3(nn, u));
+  V3 ru = scale3(r, u), rv = scale3(r, v);
+  V3 corner[4];
+  corner[0] = sub3(sub3(pp, ru), rv);
+  corner[1] = sub3(add3(pp, ru), rv);
+  corner[2] = add3(sub3(pp, ru), rv);
+  corner[3] = add3(add3(pp, ru), rv);
+  RVert q[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float x, y, z;
+    project01(corner[i], kp.m_fov_up, kp.m_fov, kp.m_min_depth, kp.m_max_depth, x, y, z);
+    if (cx - x > 0.5f) x += 1.0f;  // .geom:68
+    if (x - cx > 0.5f) x -= 1.0f;  // .geom:69
+    float xw = (0.5f * (2.0f * x - 1.0f) + 0.5f) * (float)kp.Wm;
+    float yw = (0.5f * (2.0f * y - 1.0f) + 0.5f) * (float)kp.Hm;
+    q[i].z = 0.5f * (2.0f * z - 1.0f) + 0.5f;
+    q[i].X = __float2ll_rn(xw * 256.0f);
+    q[i].Y = __float2ll_rn(yw * 256.0f);
+    q[i].tx = (i & 1) ? 1.0f : -1.0f;
+    q[i].ty = (i & 2) ? 1.0f : -1.0f;
+  }
+  EmitCtx e;
+  e.W = kp.Wm;
+  e.H = kp.Hm;
+  e.lequal = lequal != 0;
+  e.key_a = is_old ? t.key_old : t.key_new;
+  e.key_b = t.key_new;
+  e.to_a = (is_old ? t.key_old : t.key_new) != nullptr;
+  e.to_b = is_old && is_new && t.key_new != nullptr;
+  e.low_a = e.low_b = (unsigned long long)k;
+  e.key_c = t.key_comp;
+  e.c_old = is_old && t.key_comp != nullptr;
+  e.c_new = is_new && t.key_comp != nullptr;
+  if (!lequal) {
+    e.low_c_old = (unsigned long long)k;                 // old pass is drawn first: wins depth ties
+    e.low_c_new = (1ull << 32) | (unsigned long long)k;
+  } else {                                               // GL_LEQUAL: the latest fragment wins depth ties
+    e.low_c_old = (1ull << 32) | (unsigned long long)(0xffffffffu - k);
+    e.low_c_new = (unsigned long long)(0xffffffffu - k);
+  }
+  raster_tri(e, q[0], q[1], q[2]);
+  raster_tri(e, q[1], q[2], q[3]);
+}
+
+void launch_render_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, const uint32_t* n_dev, uint32_t n_upper,
+                           const float* M, float conf_thr, int t_thr, int emit_old, int emit_new, int lequal,
+                           RenderTargets t) {
+  if (n_upper == 0) return;
+  k_render_scatter<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr,
+                                                                                  emit_old, emit_new, lequal, t);
+  ++*L.counter;
+}
+
+struct Px {
+  float4 v, n, s;
+};
+
+__device__ __forceinline__ Px resolve_px(const SurfelPlanes& s, unsigned long long key, const float* __restrict__ M_old,
+                                         const float* __restrict__ M_new, int fixed_pass, int lequal) {
+  Px o;
+  o.v = o.n = o.s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (key == ~0ull) return o;
+  uint32_t low = (uint32_t)(key & 0xffffffffull);
+  int pass = (int)((key >> 32) & 1ull);
+  uint32_t k = low;
+  if (lequal && fixed_pass < 0) {
+    k = 0xffffffffu - low;
+    pass = 1 - pass;
+  }
+  if (fixed_pass >= 0) pass = fixed_pass;
+  float4 p0 = __ldg(s.p0 + k), p1 = __ldg(s.p1 + k), p2 = __ldg(s.p2 + k);
+  float M[16];
+  load_mat(pass ? M_new : M_old, pose_index(p2.w), M);
+  V3 pp = xform_point(M, mk3(p0.x, p0.y, p0.z));
+  V3 nn = xform_dir(M, mk3(p1.x, p1.y, p1.z));
+  o.v = make_float4(pp.x, pp.y, pp.z, 1.0f);  // render_surfels.frag:30, .geom:95-97 (flat: surfel centre)
+  o.n = make_float4(nn.x, nn.y, nn.z, 1.0f);
+  o.s = __ldg(s.p3 + k);
+  return o;
+}
+
+// resolve the key images into vertex / normal / semantic maps; optionally fuses render_compose.frag:26-48
+__global__ void __launch_bounds__(kThreads) k_render_resolve(KParams kp, SurfelPlanes s, const float* __restrict__ M_old,
+                                                            const float* __restrict__ M_new, RenderTargets t,
+                                                            FrameDev f_old, FrameDev f_new, FrameDev f_comp,
+                                                            FrameDev f_out, int keep_semantic, int lequal) {
+  int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= kp.Wm * kp.Hm) return;
+  Px po, pn;
+  if (t.key_old) {
+    po = resolve_px(s, t.key_old[pix], M_old, M_new, 0, 0);
+    f_old.vertex[pix] = po.v;
+    f_old.normal[pix] = po.n;
+    if (!keep_semantic) f_old.semantic[pix] = po.s;
+  }
+  if (t.key_new) {
+    pn = resolve_px(s, t.key_new[pix], M_old, M_new, 1, 0);
+    f_new.vertex[pix] = pn.v;
+    f_new.normal[pix] = pn.n;
+    if (!keep_semantic) f_new.semantic[pix] = pn.s;
+  }
+  if (t.key_comp) {
+    Px pc = resolve_px(s, t.key_comp[pix], M_old, M_new, -1, lequal);
+    f_comp.vertex[pix] = pc.v;
+    f_comp.normal[pix] = pc.n;
+    if (!keep_semantic) f_comp.semantic[pix] = pc.s;
+  }
+  if (f_out.vertex && t.key_old && t.key_new) {  // render_compose.frag
+    bool valid = po.v.w > 0.5f && po.n.w > 0.5f;
+    bool new_valid = pn.v.w > 0.5f && pn.n.w > 0.5f;
+    Px o = pn;
+    if (!new_valid && valid &&
+        (pn.v.w < 0.5f ||
+         len3(sub3(mk3(pn.v.x, pn.v.y, pn.v.z), mk3(po.v.x, po.v.y, po.v.z))) < kp.max_loop_closure_distance))
+      o = po;
+    f_out.vertex[pix] = o.v;
+    f_out.normal[pix] = o.n;
+    f_out.semantic[pix] = o.s;
+  }
+}
+
+void launch_render_resolve(const Launch& L, const KParams& kp, SurfelPlanes s, const float* M_old, const float* M_new,
+                           RenderTargets t, FrameDev f_old, FrameDev f_new, FrameDev f_comp, FrameDev f_out,
+                           int keep_semantic, int lequal) {
+  int P = kp.Wm * kp.Hm;
+  k_render_resolve<<<(P + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, s, M_old, M_new, t, f_old, f_new,
+                                                                            f_comp, f_out, keep_semantic, lequal);
+  ++*L.counter;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K6a: gen_indexmap.vert:62-81 -- nearest visible surfel per data pixel
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_index_scatter(KParams kp, SurfelPlanes s, const uint32_t* __restrict__ n_dev,
+                                                           const float* __restrict__ Mtab,
+                                                           unsigned long long* __restrict__ keys) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= *n_dev) return;
+  float4 p0 = __ldg(s.p0 + k), p1 = __ldg(s.p1 + k), p2 = __ldg(s.p2 + k);
+  float M[16];
+  load_mat(Mtab, pose_index(p2.w), M);
+  V3 v = xform_point(M, mk3(p0.x, p0.y, p0.z));
+  V3 n = xform_dir(M, mk3(p1.x, p1.y, p1.z));
+  if (!(dot3(n, divs3(neg3(v), len3(v))) > 0.01f)) return;
+  float x, y, z;
+  project01(v, kp.fov_up, kp.fov, kp.min_depth, kp.max_depth, x, y, z);
+  float fx = floorf(x * (float)kp.W), fy = floorf(y * (float)kp.H);
+  if (!(fx >= 0.0f && fx < (float)kp.W && fy >= 0.0f && fy < (float)kp.H)) return;
+  float zn = 2.0f * z - 1.0f;
+  if (!(zn >= -1.0f && zn <= 1.0f)) return;
+  uint32_t d24 = depth24(0.5f * zn + 0.5f);
+  if (d24 >= kDepthClear) return;
+  size_t pix = (size_t)(int)fy * kp.W + (size_t)(int)fx;
+  atomicMin(keys + pix, ((unsigned long long)d24 << 32) | (unsigned long long)k);
+}
+
+void launch_index_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, const uint32_t* n_dev, uint32_t n_upper,
+                          const float* M, unsigned long long* keys) {
+  if (n_upper == 0) return;
+  k_index_scatter<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, s, n_dev, M, keys);
+  ++*L.counter;
+}
+
+// K6b: init_radiusConf.vert:41-68
+__global__ void __launch_bounds__(kThreads) k_radius(KParams kp, FrameDev f, float4* __restrict__ radius_map) {
+  int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= kp.W * kp.H) return;
+  float4 V = __ldg(f.vertex + pix), N = __ldg(f.normal + pix);
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  V3 v = mk3(V.x, V.y, V.z), n = mk3(N.x, N.y, N.z);
+  float d = len3(v);
+  V3 view_dir = divs3(neg3(v), d);
+  float angle = dot3(n, view_dir);
+  if (V.w > 0.5f && N.w > 0.5f && angle > kp.radconf_angle_thresh) {
+    float c = angle < 0.5f ? 0.5f : (angle > 1.0f ? 1.0f : angle);
+    float radius = ((1.41f * d) * kp.pixel_size) / c;
+    float lo = radius > kp.min_radius ? radius : kp.min_radius;
+    radius = lo < kp.max_radius ? lo : kp.max_radius;
+    o.x = radius;
+    o.w = 1.0f;  // Q3: the confidence channel stays 0
+  }
+  radius_map[pix] = o;
+}
+
+void launch_radius(const Launch& L, const KParams& kp, FrameDev frame, float4* radius_map) {
+  int P = kp.W * kp.H;
+  k_radius<<<(P + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, frame, radius_map);
+  ++*L.counter;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K6c: update_surfels.vert:140-333, fused with the K6e predicate of copy_surfels.vert:38-56
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 data_tex(const float4* __restrict__ img, int W, int H, float fx, float fy) {
+  if (!(fx >= 0.0f && fx < (float)W && fy >= 0.0f && fy < (float)H)) return make_float4(0.f, 0.f, 0.f, 0.f);
+  return __ldg(img + (size_t)(int)fy * W + (size_t)(int)fx);
+}
+
+__device__ __forceinline__ V3 slerp(V3 v0, V3 v1, float weight) {  // update_surfels.vert:113-124
+  float omega = acosf_(dot3(normalize3(v0), normalize3(v1)));
+  float eta = 1.0f / sinf_(omega);
+  float w0 = eta * sinf_(weight * omega);
+  float w1 = eta * sinf_((1.0f - weight) * omega);
+  return add3(scale3(w0, v0), scale3(w1, v1));
+}
+
+__device__ __forceinline__ bool submap_keep(const float* __restrict__ poses, float4 p0, float4 p2, float2 center,
+                                            float extent) {
+  float M[16];
+  load_mat(poses, pose_index(p2.w), M);
+  V3 w = xform_point(M, mk3(p0.x, p0.y, p0.z));
+  if ((int)__float_as_uint(p2.x) < 0 || fabsf(w.x - center.x) > extent || fabsf(w.y - center.y) > extent) return false;
+  return true;
+}
+
+struct UpdateArgs {
+  Mat4 pose;               // current sensor pose (by value: no upload on the critical path)
+  Mat4 inv_pose;
+  const float* poses;      // pose table
+  const float* poses_inv;  // inverse pose table
+  const unsigned long long* index_keys;
+  const float4* radius_map;
+  int timestamp;
+  float2 submap_center;
+  float submap_extent;
+};
+
+__global__ void __launch_bounds__(kThreads) k_update_surfels(KParams kp, SurfelPlanes src, SurfelPlanes tmp,
+                                                            const uint32_t* __restrict__ n_dev, UpdateArgs ua,
+                                                            FrameDev f, uint8_t* __restrict__ integrated,
+                                                            uint8_t* __restrict__ keep,
+                                                            uint32_t* __restrict__ block_counts) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  bool kept = false;
+  if (k < *n_dev) {
+    const int W = kp.W, H = kp.H;
+    float4 p0 = __ldg(src.p0 + k), p1 = __ldg(src.p1 + k), p2 = __ldg(src.p2 + k), p3 = __ldg(src.p3 + k);
+    const int timestamp = ua.timestamp;
+    int s_ts = (int)__float_as_uint(p2.x);
+    int surfel_age = timestamp - s_ts;
+    int creation = (int)p2.w;
+    int ci = pose_index(p2.w);
+    float SP[16];
+    load_mat(ua.poses, ci, SP);
+    const float* POSE = ua.pose.m;
+    const float* INV = ua.inv_pose.m;
+    V3 old_position = xform_point(SP, mk3(p0.x, p0.y, p0.z));
+    V3 old_normal = xform_dir(SP, mk3(p1.x, p1.y, p1.z));
+    float old_radius = p0.w, old_conf = p1.w, old_weight = p2.z;
+    bool valid_out = true;
+    if (old_conf < kp.confidence_threshold && kp.use_stability) valid_out = surfel_age < kp.unstable_age;
+    float4 o0 = p0, o1 = p1, o2 = p2, o3 = p3;
+    o2.y = pack_rgb(0.3f, 0.3f, 0.3f);
+    V3 vertex = xform_point(INV, old_position);
+    V3 normal = normalize3(xform_dir(INV, old_normal));
+    bool visible = dot3(normal, divs3(neg3(vertex), len3(vertex))) > 0.0f;
+    float x, y, z;
+    project01(vertex, kp.fov_up, kp.fov, kp.min_depth, kp.max_depth, x, y, z);
+    float ix = floorf(x * (float)W) + 0.5f, iy = floorf(y * (float)H) + 0.5f;
+    float4 Vt = data_tex(f.vertex, W, H, ix, iy);
+    float4 Nt = data_tex(f.normal, W, H, ix, iy);
+    bool valid = (Vt.w > 0.5f) && (Nt.w > 0.5f);
+    bool inside = (ix < (float)W && iy < (float)H && z < 1.0f) && !(ix < 0.0f && iy < 0.0f && z < 0.0f);
+    float penalty = 0.0f;
+    float update_conf = kp.log_prior;
+    if (valid && inside && visible) {
+      float4 St = data_tex(f.semantic, W, H, ix, iy);
+      float4 Rt = data_tex(ua.radius_map, W, H, ix, iy);
+      float data_label = St.x * 255.0f, data_prob = St.w;
+      float model_label = p3.x * 255.0f, model_prob = p3.w;
+      bool label_diff = roundf_(data_label) != roundf_(model_label);
+      if (label_diff && is_movable(model_label)) penalty = 1.0f;
+      V3 v = mk3(Vt.x, Vt.y, Vt.z), n = mk3(Nt.x, Nt.y, Nt.z);
+      V3 v_global = xform_point(POSE, v);
+      V3 n_global = normalize3(xform_dir(POSE, n));
+      V3 view_dir = divs3(neg3(v), len3(v));
+      float distance = fabsf(dot3(old_normal, sub3(v_global, old_position)));
+      float angle = len3(cross3(n_global, old_normal));
+      float new_radius = Rt.x, new_conf = Rt.y;
+      size_t dpix = (size_t)(int)iy * W + (size_t)(int)ix;
+      if (distance < kp.map_max_distance && angle < kp.update_angle_thresh) {
+        float zn = 2.0f * z - 1.0f;
+        if (zn >= -1.0f && zn <= 1.0f && depth24(0.5f * zn + 0.5f) < kDepthClear) integrated[dpix] = 1;
+        float confidence = old_conf + new_conf;
+        o1.w = confidence;
+        o2.x = __uint_as_float((uint32_t)timestamp);
+        float avg_radius = new_radius < old_radius ? new_radius : old_radius;
+        avg_radius = avg_radius > 0.0f ? avg_radius : 0.0f;  // update program's min_radius uniform is 0 (SurfelMap.cpp:422)
+        o0.w = avg_radius;
+        valid_out = true;
+        o2.y = pack_rgb(0.0f, 0.7f, 0.0f);
+        o2.w = (float)creation;
+        float a = angle, d = distance;
+        float pr = kp.p_stable;
+        if (kp.confidence_mode == 1 || kp.confidence_mode == 3)
+          pr = pr * expf_(((-a) * a) / (kp.sigma_angle * kp.sigma_angle));
+        if (kp.confidence_mode == 2 || kp.confidence_mode == 3)
+          pr = pr * expf_(((-d) * d) / (kp.sigma_distance * kp.sigma_distance));
+        pr = pr > kp.p_unstable ? pr : kp.p_unstable;
+        pr = pr < 1.0f ? pr : 1.0f;
+        update_conf = logf_(pr / (1.0f - pr));
+        if ((new_radius < old_radius && timestamp - creation < kp.active_timestamps) || kp.update_always) {
+          float w1 = 0.9f, w2 = 0.1f;
+          if (kp.weighting_scheme > 0) {
+            w1 = old_weight;
+            w2 = 1.0f;
+            if (kp.weighting_scheme == 2) w2 = dot3(n, view_dir);
+            float sw = w1 + w2;
+            o2.z = kp.max_weight < sw ? kp.max_weight : sw;
+            float sum = w1 + w2;
+            w1 = w1 / sum;
+            w2 = w2 / sum;
+          }
+          V3 avg_position = add3(scale3(w1, old_position), scale3(w2, v_global));
+          V3 avg_normal = slerp(old_normal, n_global, w1);
+          float avg_prob;
+          if (label_diff)
+            avg_prob = w1 * model_prob + w2 * (1.0f - data_prob);
+          else
+            avg_prob = w1 * model_prob + w2 * data_prob;
+          o3.w = avg_prob;
+          if (kp.averaging_scheme == 1) {
+            avg_position = add3(old_position, scale3(w2 * distance, old_normal));
+            avg_normal = slerp(old_normal, n_global, w1);
+          }
+          avg_normal = normalize3(avg_normal);
+          float SPI[16];
+          load_mat(ua.poses_inv, ci, SPI);
+          avg_position = xform_point(SPI, avg_position);
+          avg_normal = xform_dir(SPI, avg_normal);
+          o0 = make_float4(avg_position.x, avg_position.y, avg_position.z, avg_radius);
+          o1 = make_float4(avg_normal.x, avg_normal.y, avg_normal.z, confidence);
+          o2.y = pack_rgb(1.0f, 0.0f, 1.0f);
+        }
+      } else {
+        unsigned long long key = ua.index_keys[dpix];
+        int idx = (key == ~0ull) ? -1 : (int)(uint32_t)(key & 0xffffffffull);
+        if (idx == (int)k) {  // closest visible surfel of that pixel
+          update_conf = logf_(kp.p_unstable / (1.0f - kp.p_unstable));
+          o2.y = pack_rgb(0.0f, 1.0f, 1.0f);
+        }
+      }
+    }
+    update_conf = update_conf - penalty;
+    if (kp.use_stability) {
+      float c = (old_conf + update_conf) - kp.log_prior;
+      o1.w = c < 20.0f ? c : 20.0f;
+    } else {
+      o1.w = old_conf;
+    }
+    if (o1.w < kp.log_unstable && kp.use_stability) valid_out = false;
+    kept = valid_out && submap_keep(ua.poses, o0, o2, ua.submap_center, ua.submap_extent);
+    tmp.p0[k] = o0;
+    tmp.p1[k] = o1;
+    tmp.p2[k] = o2;
+    tmp.p3[k] = o3;
+    keep[k] = kept ? 1 : 0;
+  }
+  int cnt = __syncthreads_count(kept ? 1 : 0);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)cnt;
+}
+
+// K6d: gen_surfels.vert:38-52 + .geom:109-145; thread t <-> pixel (x = t / H, y = t % H): x-major order
+// (SurfelMap.cpp:88-92), fused with the K6e predicate
+__global__ void __launch_bounds__(kThreads) k_gen_surfels(KParams kp, FrameDev f, const float4* __restrict__ radius_map,
+                                                         const uint8_t* __restrict__ integrated,
+                                                         const float* __restrict__ poses, int timestamp,
+                                                         float2 center, float extent, SurfelPlanes tmp,
+                                                         uint8_t* __restrict__ keep,
+                                                         uint32_t* __restrict__ block_counts) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  bool kept = false;
+  if (t < kp.W * kp.H) {
+    int x = t / kp.H, y = t - x * kp.H;
+    size_t pix = (size_t)y * kp.W + x;
+    float4 V = __ldg(f.vertex + pix), N = __ldg(f.normal + pix), R = __ldg(radius_map + pix);
+    bool invalid = (V.w < 1.0f) || (N.w < 1.0f);
+    invalid = invalid || (R.w < 0.5f);
+    bool integ = integrated[pix] != 0;
+    V3 v = mk3(V.x, V.y, V.z), n = mk3(N.x, N.y, N.z);
+    V3 view_dir = divs3(neg3(v), len3(v));
+    bool valid = !invalid && !integ && (dot3(n, view_dir) > 0.01f);
+    if (valid) {
+      V3 ng = normalize3(n);
+      float4 S = __ldg(f.semantic + pix);
+      float conf = is_movable(S.x * 255.0f) ? kp.log_prior - 0.5f : kp.log_prior;
+      float4 o0 = make_float4(v.x, v.y, v.z, R.x);
+      float4 o1 = make_float4(ng.x, ng.y, ng.z, conf);
+      float4 o2 = make_float4(__uint_as_float((uint32_t)timestamp), pack_rgb(0.0f, 0.0f, 1.0f), 1.0f, (float)timestamp);
+      kept = submap_keep(poses, o0, o2, center, extent);
+      tmp.p0[t] = o0;
+      tmp.p1[t] = o1;
+      tmp.p2[t] = o2;
+      tmp.p3[t] = S;
+    }
+    keep[t] = kept ? 1 : 0;
+  }
+  int cnt = __syncthreads_count(kept ? 1 : 0);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)cnt;
+}
+
+// extract_surfels.vert:44-62: flags of the surfels inside one submap tile
+__global__ void __launch_bounds__(kThreads) k_extract_flags(SurfelPlanes s, const uint32_t* __restrict__ n_dev,
+                                                           const float* __restrict__ poses, float2 center, float extent,
+                                                           uint8_t* __restrict__ keep,
+                                                           uint32_t* __restrict__ block_counts) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  bool kept = false;
+  if (k < *n_dev) {
+    float4 p0 = __ldg(s.p0 + k), p2 = __ldg(s.p2 + k);
+    float M[16];
+    load_mat(poses, pose_index(p2.w), M);
+    V3 w = xform_point(M, mk3(p0.x, p0.y, p0.z));
+    kept = !(fabsf(w.x - center.x) > extent || fabsf(w.y - center.y) > extent);
+    keep[k] = kept ? 1 : 0;
+  }
+  int cnt = __syncthreads_count(kept ? 1 : 0);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)cnt;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// ordered compaction (transform feedback semantics): block_counts[b] hold the kept items of block b (256 items)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
+                                                      const uint32_t* __restrict__ n_dev, uint32_t n_fixed,
+                                                      const uint32_t* __restrict__ base_dev, uint32_t cap,
+                                                      uint32_t* __restrict__ count_out,
+                                                      uint32_t* __restrict__ kept_out) {
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t s_total;
+  uint32_t n = n_dev ? *n_dev : n_fixed;
+  uint32_t nblocks = (n + kThreads - 1) / kThreads;
+  uint32_t per = (nblocks + 1023) / 1024;
+  uint32_t b0 = threadIdx.x * per, b1 = min(b0 + per, nblocks);
+  uint32_t local = 0;
+  for (uint32_t b = b0; b < b1; ++b) local += counts[b];
+  // block-wide exclusive scan of `local`
+  uint32_t v = local;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += u;
+  }
+  if (lane == 31) warp_tot[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += u;
+    }
+    warp_tot[lane] = w;  // inclusive
+    if (lane == 31) s_total = w;
+  }
+  __syncthreads();
+  uint32_t excl = (v - local) + (warp > 0 ? warp_tot[warp - 1] : 0u);
+  uint32_t run = excl;
+  for (uint32_t b = b0; b < b1; ++b) {
+    offsets[b] = run;
+    run += counts[b];
+  }
+  if (threadIdx.x == 0) {
+    uint32_t base = base_dev ? *base_dev : 0u;
+    uint32_t tot = base + s_total;
+    if (kept_out) *kept_out = s_total;
+    *count_out = tot < cap ? tot : cap;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_compact_scatter(SurfelPlanes src, const uint8_t* __restrict__ keep,
+                                                             const uint32_t* __restrict__ offsets,
+                                                             const uint32_t* __restrict__ n_dev, uint32_t n_fixed,
+                                                             SurfelPlanes dst, const uint32_t* __restrict__ base_dev,
+                                                             uint32_t cap) {
+  __shared__ uint32_t warp_cnt[kThreads / 32];
+  uint32_t n = n_dev ? *n_dev : n_fixed;
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  bool kept = (k < n) && keep[k];
+  unsigned m = __ballot_sync(0xffffffffu, kept);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_cnt[warp] = __popc(m);
+  __syncthreads();
+  uint32_t before = 0;
+  for (int w = 0; w < warp; ++w) before += warp_cnt[w];
+  if (!kept) return;
+  uint32_t rank = before + __popc(m & ((1u << lane) - 1u));
+  uint32_t base = base_dev ? *base_dev : 0u;
+  uint32_t d = base + offsets[blockIdx.x] + rank;
+  if (d >= cap) return;  // transform feedback drops what does not fit
+  dst.p0[d] = src.p0[k];
+  dst.p1[d] = src.p1[k];
+  dst.p2[d] = src.p2[k];
+  dst.p3[d] = src.p3[k];
+}
+
+void launch_compact(const Launch& L, SurfelPlanes src, const uint8_t* keep, const uint32_t* block_counts,
+                    uint32_t* block_offsets, const uint32_t* n_dev, uint32_t n_upper, SurfelPlanes dst,
+                    const uint32_t* base_dev, uint32_t cap, uint32_t* count_out, uint32_t* kept_out) {
+  k_scan_blocks<<<1, 1024, 0, L.stream>>>(block_counts, block_offsets, n_dev, n_upper, base_dev, cap, count_out,
+                                          kept_out);
+  ++*L.counter;
+  if (n_upper == 0) return;
+  k_compact_scatter<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(src, keep, block_offsets, n_dev,
+                                                                                   n_upper, dst, base_dev, cap);
+  ++*L.counter;
+}
+
+void launch_update_surfels(const Launch& L, const KParams& kp, SurfelPlanes src, SurfelPlanes tmp, const uint32_t* n_dev,
+                           uint32_t n_upper, const Mat4& pose, const Mat4& inv_pose, const float* poses,
+                           const float* poses_inv, const unsigned long long* index_keys, const float4* radius_map,
+                           FrameDev frame, int timestamp, float2 submap_center, float submap_extent,
+                           uint8_t* integrated, uint8_t* keep, uint32_t* block_counts) {
+  if (n_upper == 0) return;
+  UpdateArgs ua{pose, inv_pose, poses, poses_inv, index_keys, radius_map, timestamp, submap_center, submap_extent};
+  k_update_surfels<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, src, tmp, n_dev, ua, frame,
+                                                                                  integrated, keep, block_counts);
+  ++*L.counter;
+}
+
+void launch_gen_surfels(const Launch& L, const KParams& kp, FrameDev frame, const float4* radius_map,
+                        const uint8_t* integrated, const float* poses, int timestamp, float2 submap_center,
+                        float submap_extent, SurfelPlanes tmp, uint8_t* keep, uint32_t* block_counts) {
+  int P = kp.W * kp.H;
+  k_gen_surfels<<<(P + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, frame, radius_map, integrated, poses,
+                                                                         timestamp, submap_center, submap_extent, tmp,
+                                                                         keep, block_counts);
+  ++*L.counter;
+}
+
+void launch_extract_flags(const Launch& L, SurfelPlanes s, const uint32_t* n_dev, uint32_t n_upper, const float* poses,
+                          float2 center, float extent, uint8_t* keep, uint32_t* block_counts) {
+  if (n_upper == 0) return;
+  k_extract_flags<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(s, n_dev, poses, center, extent, keep,
+                                                                                 block_counts);
+  ++*L.counter;
+}
+
+// ---- 64-byte AoS records (Surfel.h) <-> SoA lanes, for upload / download at the ABI ----
+__global__ void k_aos_to_soa(const float4* __restrict__ aos, SurfelPlanes s, uint32_t offset, uint32_t n) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  s.p0[offset + k] = aos[4 * (size_t)k + 0];
+  s.p1[offset + k] = aos[4 * (size_t)k + 1];
+  s.p2[offset + k] = aos[4 * (size_t)k + 2];
+  s.p3[offset + k] = aos[4 * (size_t)k + 3];
+}
+__global__ void k_soa_to_aos(SurfelPlanes s, float4* __restrict__ aos, uint32_t n) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  aos[4 * (size_t)k + 0] = s.p0[k];
+  aos[4 * (size_t)k + 1] = s.p1[k];
+  aos[4 * (size_t)k + 2] = s.p2[k];
+  aos[4 * (size_t)k + 3] = s.p3[k];
+}
+void launch_aos_to_soa(const Launch& L, const sb_surfel* aos, SurfelPlanes s, uint32_t offset, uint32_t n) {
+  if (n == 0) return;
+  k_aos_to_soa<<<(n + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(reinterpret_cast<const float4*>(aos), s, offset,
+                                                                        n);
+  ++*L.counter;
+}
+void launch_soa_to_aos(const Launch& L, SurfelPlanes s, sb_surfel* aos, uint32_t n) {
+  if (n == 0) return;
+  k_soa_to_aos<<<(n + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(s, reinterpret_cast<float4*>(aos), n);
+  ++*L.counter;
+}
+
+}  // namespace sb

