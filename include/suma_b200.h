@@ -167,6 +167,13 @@ int sb_slam_frame(sb_ctx* ctx, int which, sb_frame** out); /* getCurrentFrame / 
  * [7] surfels; wall seconds: [8] preprocessing [9] icp [10] mapping [11] complete (getStatistics keys) */
 int sb_get_statistics(sb_ctx* ctx, double stats[16]);
 
+/* ---- per-kernel device time (CUDA events on the context's stream around every launch; off by default) ------------ */
+int sb_profile_enable(sb_ctx* ctx, int on);
+int sb_profile_kernels(void);              /* number of kernel classes */
+const char* sb_profile_name(int id);
+/* sums since the last collect: total_ms[id], count[id]; cap >= sb_profile_kernels(). Synchronises the stream. */
+int sb_profile_collect(sb_ctx* ctx, double* total_ms, uint64_t* count, int cap);
+
 /* ---- multi-GPU: row-striped K5 with a one-shot peer-memory all-reduce of the 32 fixed-point sums ---------------
  * Every rank calls sb_comm_export to obtain an opaque 64-byte handle of its mailbox, exchanges the handles out of
  * band (e.g. torch.distributed.all_gather) and passes all of them to sb_comm_init. Afterwards sb_icp_minimize /

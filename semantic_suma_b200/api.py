@@ -120,6 +120,8 @@ def lib(build_if_missing=True):
         "sb_get_statistics": [vp, pd],
         "sb_comm_export": [vp, vp], "sb_comm_init": [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int],
         "sb_comm_shutdown": [vp],
+        "sb_profile_enable": [vp, C.c_int], "sb_profile_collect": [vp, pd, C.POINTER(C.c_uint64), C.c_int],
+        "sb_profile_kernels": [],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -129,6 +131,7 @@ def lib(build_if_missing=True):
     L.sb_stream.argtypes = [vp]; L.sb_stream.restype = vp
     L.sb_launch_count.argtypes = [vp]; L.sb_launch_count.restype = C.c_uint64
     L.sb_device_count.argtypes = []; L.sb_device_count.restype = C.c_int
+    L.sb_profile_name.argtypes = [C.c_int]; L.sb_profile_name.restype = C.c_char_p
     L.sb_se3_exp.argtypes = [pd, pd]; L.sb_se3_exp.restype = None
     L.sb_se3_log.argtypes = [pd, pd]; L.sb_se3_log.restype = None
     L.sb_icp_unpack.argtypes = [C.POINTER(C.c_int64), pd]; L.sb_icp_unpack.restype = None
@@ -144,7 +147,8 @@ EXPORTED_SYMBOLS = [
     "sb_icp_minimize", "sb_se3_exp", "sb_se3_log", "sb_ldlt_solve6", "sb_gn_step", "sb_map_update",
     "sb_map_update_poses", "sb_map_size", "sb_map_timestamp", "sb_map_download", "sb_map_upload", "sb_map_set_pose",
     "sb_map_update_debug", "sb_map_submap_origin", "sb_process_scan", "sb_get_pose", "sb_timestamp", "sb_slam_frame",
-    "sb_get_statistics", "sb_comm_export", "sb_comm_init", "sb_comm_shutdown",
+    "sb_get_statistics", "sb_comm_export", "sb_comm_init", "sb_comm_shutdown", "sb_profile_enable",
+    "sb_profile_kernels", "sb_profile_name", "sb_profile_collect",
 ]
 
 
@@ -218,6 +222,16 @@ class Context:
 
     def stream(self):
         return lib().sb_stream(self.h)
+
+    def profile(self, on):
+        self.check(lib().sb_profile_enable(self.h, 1 if on else 0), "profile_enable")
+
+    def profile_collect(self):
+        """{kernel name: (total_ms, launches)} since the last call (CUDA events on the context's stream)."""
+        n = lib().sb_profile_kernels()
+        ms = np.zeros(n); cnt = np.zeros(n, np.uint64)
+        self.check(lib().sb_profile_collect(self.h, _dp(ms), cnt.ctypes.data_as(C.POINTER(C.c_uint64)), n), "profile")
+        return {lib().sb_profile_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}
 
     def set_params(self, params):
         self.check(lib().sb_set_params(self.h, C.byref(params)), "set_params")

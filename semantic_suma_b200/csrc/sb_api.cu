@@ -35,6 +35,7 @@ struct sb_ctx {
   KParams kp;
   std::string err;
   uint64_t launches = 0;
+  Profiler prof;
 
   // ---- preprocessing scratch
   unsigned long long* keys_data = nullptr;  // P_data
@@ -114,7 +115,7 @@ int fail(sb_ctx* c, int code, const std::string& msg) {
       return fail(ctx, SB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));               \
   } while (0)
 
-Launch L_(sb_ctx* c) { return Launch{c->stream, &c->launches}; }
+Launch L_(sb_ctx* c) { return Launch{c->stream, &c->launches, &c->prof}; }
 
 void ident_d(double* M) {
   for (int i = 0; i < 16; ++i) M[i] = (i % 5 == 0) ? 1.0 : 0.0;
@@ -1108,6 +1109,35 @@ int sb_slam_frame(sb_ctx* c, int which, sb_frame** out) {
 int sb_get_statistics(sb_ctx* c, double stats[16]) {
   if (!c || !stats) return SB_ERR_INVALID;
   memcpy(stats, c->stats, sizeof(c->stats));
+  return SB_OK;
+}
+
+// ---- profiling ------------------------------------------------------------------------------------------------
+int sb_profile_enable(sb_ctx* c, int on) {
+  if (!c) return SB_ERR_INVALID;
+  c->prof.on = on != 0;
+  return SB_OK;
+}
+int sb_profile_kernels(void) { return K_COUNT; }
+const char* sb_profile_name(int id) { return kernel_name(id); }
+int sb_profile_collect(sb_ctx* c, double* total_ms, uint64_t* count, int cap) {
+  if (!c || !total_ms || !count || cap < K_COUNT) return SB_ERR_INVALID;
+  cudaSetDevice(c->device);
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < K_COUNT; ++i) {
+    total_ms[i] = 0.0;
+    count[i] = 0;
+  }
+  for (auto& r : c->prof.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      total_ms[r.id] += ms;
+      count[r.id] += 1;
+    }
+    c->prof.pool.push_back(r.e0);
+    c->prof.pool.push_back(r.e1);
+  }
+  c->prof.recs.clear();
   return SB_OK;
 }
 

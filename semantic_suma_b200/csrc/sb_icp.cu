@@ -210,8 +210,10 @@ __global__ void __launch_bounds__(kIcpThreads) k_icp_jacobian(KParams kp, IcpArg
 void launch_icp_jacobian(const Launch& L, const KParams& kp, const IcpArgs& a, const Mat4& pose, int iteration,
                          long long* acc32, int blocks) {
   cudaMemsetAsync(acc32, 0, 32 * sizeof(long long), L.stream);
-  k_icp_jacobian<<<blocks, kIcpThreads, 0, L.stream>>>(kp, a, pose, iteration, acc32);
-  ++*L.counter;
+  {
+    ScopedKernel sk(L, K_ICP_JACOBIAN);
+    k_icp_jacobian<<<blocks, kIcpThreads, 0, L.stream>>>(kp, a, pose, iteration, acc32);
+  }
 }
 
 // ---- fused Gauss-Newton iteration ----
@@ -230,8 +232,10 @@ __global__ void k_gn_init(GnState* st, Mat4d T0, long long* acc32, unsigned int*
 }
 
 void launch_gn_init(const Launch& L, GnState* st, const Mat4d& T0, long long* acc32, unsigned int* ticket) {
-  k_gn_init<<<1, 64, 0, L.stream>>>(st, T0, acc32, ticket);
-  ++*L.counter;
+  {
+    ScopedKernel sk(L, K_GN_INIT);
+    k_gn_init<<<1, 64, 0, L.stream>>>(st, T0, acc32, ticket);
+  }
 }
 
 // one-shot all-reduce of the 32 sums over the ranks' peer-mapped mailboxes (only thread 0 of the last block runs it):
@@ -328,8 +332,10 @@ void launch_icp_fused_iteration(const Launch& L, const KParams& kp, const IcpArg
     memset(&cd, 0, sizeof(cd));
     cd.nranks = 1;
   }
-  k_icp_fused<<<blocks, kIcpThreads, 0, L.stream>>>(kp, a, st, acc32, ticket, max_iter, eps, delta, cd);
-  ++*L.counter;
+  {
+    ScopedKernel sk(L, K_ICP_FUSED);
+    k_icp_fused<<<blocks, kIcpThreads, 0, L.stream>>>(kp, a, st, acc32, ticket, max_iter, eps, delta, cd);
+  }
 }
 
 }  // namespace sb

@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/suma_b200.h"
 #include "sb_math.cuh"
 
@@ -85,10 +87,48 @@ struct Mat4d {
   double m[16];
 };
 
+// ---------------- kernel ids (launch accounting + the optional CUDA-event profiler) ----------------
+enum KernelId {
+  K_FILL = 0, K_PROJECT_SCATTER, K_PROJECT_RESOLVE, K_NORMALS_ERODE, K_FLOODFILL, K_ICP_JACOBIAN, K_GN_INIT,
+  K_ICP_FUSED, K_POSE_PRODUCTS, K_RENDER_SCATTER, K_RENDER_RESOLVE, K_INDEX_SCATTER, K_RADIUS, K_UPDATE_SURFELS,
+  K_GEN_SURFELS, K_EXTRACT_FLAGS, K_SCAN_BLOCKS, K_COMPACT_SCATTER, K_AOS_TO_SOA, K_SOA_TO_AOS, K_COUNT
+};
+const char* kernel_name(int id);
+
+// per-kernel device time with CUDA events on the launching stream (off by default: zero overhead)
+struct Profiler {
+  bool on = false;
+  struct Rec { int id; cudaEvent_t e0, e1; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+};
+
 // ---------------- launchers (implemented in the .cu files) ----------------
 struct Launch {
   cudaStream_t stream;
   uint64_t* counter;  // number of kernels launched
+  Profiler* prof;
+};
+
+struct ScopedKernel {
+  const Launch& L;
+  int slot = -1;
+  ScopedKernel(const Launch& l, int id) : L(l) {
+    ++*L.counter;
+    if (L.prof && L.prof->on) {
+      Profiler::Rec r{id, L.prof->get(), L.prof->get()};
+      cudaEventRecord(r.e0, L.stream);
+      L.prof->recs.push_back(r);
+      slot = (int)L.prof->recs.size() - 1;
+    }
+  }
+  ~ScopedKernel() {
+    if (slot >= 0) cudaEventRecord(L.prof->recs[slot].e1, L.stream);
+  }
 };
 
 // sb_preprocess.cu

@@ -20,6 +20,14 @@ using namespace sbm;
 
 constexpr int kThreads = 256;
 
+const char* kernel_name(int id) {
+  static const char* names[K_COUNT] = {"fill_u64", "project_scatter", "project_resolve", "normals_erode", "floodfill",
+                                       "icp_jacobian", "gn_init", "icp_fused", "pose_products", "render_scatter",
+                                       "render_resolve", "index_scatter", "radius", "update_surfels", "gen_surfels",
+                                       "extract_flags", "scan_blocks", "compact_scatter", "aos_to_soa", "soa_to_aos"};
+  return (id >= 0 && id < K_COUNT) ? names[id] : "?";
+}
+
 __device__ __forceinline__ int pose_index(float count) {
   int c = (int)count;
   c = c < 0 ? 0 : c;
@@ -50,8 +58,10 @@ __global__ void k_pose_products(Mat4 A, const float* __restrict__ poses, float* 
 
 void launch_pose_products(const Launch& L, const Mat4& A, const float* poses, float* out, uint32_t count) {
   if (count == 0) return;
-  k_pose_products<<<(count + 127) / 128, 128, 0, L.stream>>>(A, poses, out, count);
-  ++*L.counter;
+  {
+    ScopedKernel sk(L, K_POSE_PRODUCTS);
+    k_pose_products<<<(count + 127) / 128, 128, 0, L.stream>>>(A, poses, out, count);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -199,9 +209,11 @@ void launch_render_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, c
                            const float* M, float conf_thr, int t_thr, int emit_old, int emit_new, int lequal,
                            RenderTargets t) {
   if (n_upper == 0) return;
-  k_render_scatter<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr,
+  {
+    ScopedKernel sk(L, K_RENDER_SCATTER);
+    k_render_scatter<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr,
                                                                                   emit_old, emit_new, lequal, t);
-  ++*L.counter;
+  }
 }
 
 struct Px {
@@ -276,9 +288,11 @@ void launch_render_resolve(const Launch& L, const KParams& kp, SurfelPlanes s, c
                            RenderTargets t, FrameDev f_old, FrameDev f_new, FrameDev f_comp, FrameDev f_out,
                            int keep_semantic, int lequal) {
   int P = kp.Wm * kp.Hm;
-  k_render_resolve<<<(P + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, s, M_old, M_new, t, f_old, f_new,
+  {
+    ScopedKernel sk(L, K_RENDER_RESOLVE);
+    k_render_resolve<<<(P + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, s, M_old, M_new, t, f_old, f_new,
                                                                             f_comp, f_out, keep_semantic, lequal);
-  ++*L.counter;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -310,8 +324,10 @@ __global__ void __launch_bounds__(kThreads) k_index_scatter(KParams kp, SurfelPl
 void launch_index_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, const uint32_t* n_dev, uint32_t n_upper,
                           const float* M, unsigned long long* keys) {
   if (n_upper == 0) return;
-  k_index_scatter<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, s, n_dev, M, keys);
-  ++*L.counter;
+  {
+    ScopedKernel sk(L, K_INDEX_SCATTER);
+    k_index_scatter<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, s, n_dev, M, keys);
+  }
 }
 
 // K6b: init_radiusConf.vert:41-68
@@ -337,8 +353,10 @@ __global__ void __launch_bounds__(kThreads) k_radius(KParams kp, FrameDev f, flo
 
 void launch_radius(const Launch& L, const KParams& kp, FrameDev frame, float4* radius_map) {
   int P = kp.W * kp.H;
-  k_radius<<<(P + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, frame, radius_map);
-  ++*L.counter;
+  {
+    ScopedKernel sk(L, K_RADIUS);
+    k_radius<<<(P + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, frame, radius_map);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -651,13 +669,17 @@ __global__ void __launch_bounds__(kThreads) k_compact_scatter(SurfelPlanes src, 
 void launch_compact(const Launch& L, SurfelPlanes src, const uint8_t* keep, const uint32_t* block_counts,
                     uint32_t* block_offsets, const uint32_t* n_dev, uint32_t n_upper, SurfelPlanes dst,
                     const uint32_t* base_dev, uint32_t cap, uint32_t* count_out, uint32_t* kept_out) {
-  k_scan_blocks<<<1, 1024, 0, L.stream>>>(block_counts, block_offsets, n_dev, n_upper, base_dev, cap, count_out,
+  {
+    ScopedKernel sk(L, K_SCAN_BLOCKS);
+    k_scan_blocks<<<1, 1024, 0, L.stream>>>(block_counts, block_offsets, n_dev, n_upper, base_dev, cap, count_out,
                                           kept_out);
-  ++*L.counter;
+  }
   if (n_upper == 0) return;
-  k_compact_scatter<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(src, keep, block_offsets, n_dev,
+  {
+    ScopedKernel sk(L, K_COMPACT_SCATTER);
+    k_compact_scatter<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(src, keep, block_offsets, n_dev,
                                                                                    n_upper, dst, base_dev, cap);
-  ++*L.counter;
+  }
 }
 
 void launch_update_surfels(const Launch& L, const KParams& kp, SurfelPlanes src, SurfelPlanes tmp, const uint32_t* n_dev,
@@ -667,27 +689,33 @@ void launch_update_surfels(const Launch& L, const KParams& kp, SurfelPlanes src,
                            uint8_t* integrated, uint8_t* keep, uint32_t* block_counts) {
   if (n_upper == 0) return;
   UpdateArgs ua{pose, inv_pose, poses, poses_inv, index_keys, radius_map, timestamp, submap_center, submap_extent};
-  k_update_surfels<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, src, tmp, n_dev, ua, frame,
+  {
+    ScopedKernel sk(L, K_UPDATE_SURFELS);
+    k_update_surfels<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, src, tmp, n_dev, ua, frame,
                                                                                   integrated, keep, block_counts);
-  ++*L.counter;
+  }
 }
 
 void launch_gen_surfels(const Launch& L, const KParams& kp, FrameDev frame, const float4* radius_map,
                         const uint8_t* integrated, const float* poses, int timestamp, float2 submap_center,
                         float submap_extent, SurfelPlanes tmp, uint8_t* keep, uint32_t* block_counts) {
   int P = kp.W * kp.H;
-  k_gen_surfels<<<(P + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, frame, radius_map, integrated, poses,
+  {
+    ScopedKernel sk(L, K_GEN_SURFELS);
+    k_gen_surfels<<<(P + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, frame, radius_map, integrated, poses,
                                                                          timestamp, submap_center, submap_extent, tmp,
                                                                          keep, block_counts);
-  ++*L.counter;
+  }
 }
 
 void launch_extract_flags(const Launch& L, SurfelPlanes s, const uint32_t* n_dev, uint32_t n_upper, const float* poses,
                           float2 center, float extent, uint8_t* keep, uint32_t* block_counts) {
   if (n_upper == 0) return;
-  k_extract_flags<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(s, n_dev, poses, center, extent, keep,
+  {
+    ScopedKernel sk(L, K_EXTRACT_FLAGS);
+    k_extract_flags<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(s, n_dev, poses, center, extent, keep,
                                                                                  block_counts);
-  ++*L.counter;
+  }
 }
 
 // ---- 64-byte AoS records (Surfel.h) <-> SoA lanes, for upload / download at the ABI ----
@@ -709,14 +737,18 @@ __global__ void k_soa_to_aos(SurfelPlanes s, float4* __restrict__ aos, uint32_t 
 }
 void launch_aos_to_soa(const Launch& L, const sb_surfel* aos, SurfelPlanes s, uint32_t offset, uint32_t n) {
   if (n == 0) return;
-  k_aos_to_soa<<<(n + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(reinterpret_cast<const float4*>(aos), s, offset,
+  {
+    ScopedKernel sk(L, K_AOS_TO_SOA);
+    k_aos_to_soa<<<(n + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(reinterpret_cast<const float4*>(aos), s, offset,
                                                                         n);
-  ++*L.counter;
+  }
 }
 void launch_soa_to_aos(const Launch& L, SurfelPlanes s, sb_surfel* aos, uint32_t n) {
   if (n == 0) return;
-  k_soa_to_aos<<<(n + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(s, reinterpret_cast<float4*>(aos), n);
-  ++*L.counter;
+  {
+    ScopedKernel sk(L, K_SOA_TO_AOS);
+    k_soa_to_aos<<<(n + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(s, reinterpret_cast<float4*>(aos), n);
+  }
 }
 
 }  // namespace sb

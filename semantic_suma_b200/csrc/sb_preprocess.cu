@@ -20,8 +20,10 @@ void launch_fill_u64(const Launch& L, unsigned long long* p, unsigned long long 
   int blocks = (int)((n + 1023) / 1024);
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
-  k_fill_u64<<<blocks, 256, 0, L.stream>>>(p, v, n);
-  ++*L.counter;
+  {
+    ScopedKernel sk(L, K_FILL);
+    k_fill_u64<<<blocks, 256, 0, L.stream>>>(p, v, n);
+  }
 }
 
 // K1a: gen_vertexmap.vert:73-91 -- one thread per point, scatter-min into the key image
@@ -167,15 +169,25 @@ void launch_preprocess(const Launch& L, const KParams& kp, const float4* pts, co
   const int P = kp.W * kp.H;
   launch_fill_u64(L, keys, ~0ull, (size_t)P);
   if (n > 0) {
-    k_project_scatter<<<(n + 255) / 256, 256, 0, L.stream>>>(kp, pts, n, keys);
-    ++*L.counter;
+    {
+      ScopedKernel sk(L, K_PROJECT_SCATTER);
+      k_project_scatter<<<(n + 255) / 256, 256, 0, L.stream>>>(kp, pts, n, keys);
+    }
   }
   const int pb = (P + 255) / 256;
-  k_project_resolve<<<pb, 256, 0, L.stream>>>(kp, pts, labels, probs, n, timestamp < 10 ? 1 : 0, keys, out.vertex,
-                                              sem_raw);
-  k_normals_erode<<<pb, 256, 0, L.stream>>>(kp, out.vertex, sem_raw, out.normal, eroded);
-  k_floodfill<<<pb, 256, 0, L.stream>>>(kp, out.vertex, eroded, out.semantic);
-  *L.counter += 3;
+  {
+    ScopedKernel sk(L, K_PROJECT_RESOLVE);
+    k_project_resolve<<<pb, 256, 0, L.stream>>>(kp, pts, labels, probs, n, timestamp < 10 ? 1 : 0, keys, out.vertex,
+                                                sem_raw);
+  }
+  {
+    ScopedKernel sk(L, K_NORMALS_ERODE);
+    k_normals_erode<<<pb, 256, 0, L.stream>>>(kp, out.vertex, sem_raw, out.normal, eroded);
+  }
+  {
+    ScopedKernel sk(L, K_FLOODFILL);
+    k_floodfill<<<pb, 256, 0, L.stream>>>(kp, out.vertex, eroded, out.semantic);
+  }
 }
 
 }  // namespace sb
