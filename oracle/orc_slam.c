@@ -99,7 +99,7 @@ static void update_pose(orc_slam* s) {
   float angle = (float)(0.5 * (((delta[0] + delta[5]) + delta[10]) - 1.0));
   float ca = angle < 1.0f ? angle : 1.0f;
   ca = ca > -1.0f ? ca : -1.0f;
-  float r_err = acosf(ca);
+  float r_err = orc_acosf(ca); /* fixed polynomial (orc_math.h): the device-side pose bookkeeping must take the same branch */
   if (s->timestamp > 1 && (t_err > 0.4 || r_err > 0.1) && p->fallback_mode) {
     s->trackLoss += 1;
     /* recovery_->setData(currentFrame_, lastFrame_): frame-to-frame with the fallback thresholds, :89-96, 438-449 */

@@ -21,6 +21,16 @@ constexpr int kIcpThreads = 256;
 
 int icp_grid_blocks(int sm_count) { return sm_count * 2; }
 
+// number of blocks such that every thread gets the same number of pixels (the GN iteration time is the time of the
+// slowest block): P/256 work units, u = ceil(units / max_blocks) units per block
+int icp_balanced_blocks(int pixels, int max_blocks) {
+  int units = (pixels + kIcpThreads - 1) / kIcpThreads;
+  if (max_blocks < 1) max_blocks = 1;
+  int u = (units + max_blocks - 1) / max_blocks;
+  int blocks = (units + u - 1) / u;
+  return blocks < 1 ? 1 : blocks;
+}
+
 __device__ __forceinline__ float4 tex_border(const float4* __restrict__ img, int W, int H, int x, int y) {
   if (x < 0 || x >= W || y < 0 || y >= H) return make_float4(0.f, 0.f, 0.f, 0.f);
   return __ldg(img + (size_t)y * W + x);
@@ -160,6 +170,7 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 }
 
 // block-level reduction of Acc into 32 global int64 accumulators
+template <bool kFence>
 __device__ __forceinline__ void block_reduce_to_global(Acc& acc, long long* __restrict__ g_acc) {
   __shared__ long long sm[kIcpThreads / 32][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -182,8 +193,63 @@ __device__ __forceinline__ void block_reduce_to_global(Acc& acc, long long* __re
 #pragma unroll
     for (int w = 0; w < kIcpThreads / 32; ++w) v += sm[w][lane];
     if (v != 0) atomicAdd((unsigned long long*)(g_acc + lane), (unsigned long long)v);
-    __threadfence();
+    if (kFence) __threadfence();
   }
+}
+
+// Warp-level reduction of 32 values x 32 lanes with a transposing butterfly: at every step each lane keeps half of its
+// values and trades the other half with its partner, so the whole reduction costs 16+8+4+2+1 = 31 exchanges instead of
+// 32 x 5. Afterwards lane l holds the warp total of value l. (int64, so the association order is irrelevant.)
+__device__ __forceinline__ long long warp_transpose_reduce(long long (&v)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      long long keep = upper ? v[i + half] : v[i];
+      long long send = upper ? v[i] : v[i + half];
+      long long recv = __shfl_xor_sync(0xffffffffu, send, half);
+      v[i] = keep + recv;
+    }
+  }
+  return v[0];
+}
+
+constexpr int kAccReplicas = 8;  // blocks spread their REDs over 8 replicas of the 32 accumulators (less contention)
+
+// block-level reduction: lane l of warp 0 ends up with the block total of value l and adds it to one replica
+__device__ __forceinline__ void block_reduce_to_replica(Acc& acc, long long* __restrict__ replicas) {
+  __shared__ long long sm[kIcpThreads / 32][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long v[32];
+#pragma unroll
+  for (int i = 0; i < 29; ++i) v[i] = acc.s[i];
+  v[29] = acc.n_valid;
+  v[30] = acc.n_outlier;
+  v[31] = acc.n_invalid;
+  sm[warp][lane] = warp_transpose_reduce(v, lane);
+  __syncthreads();
+  if (warp == 0) {
+    long long t = 0;
+#pragma unroll
+    for (int w = 0; w < kIcpThreads / 32; ++w) t += sm[w][lane];
+    if (t != 0)
+      atomicAdd((unsigned long long*)(replicas + (size_t)(blockIdx.x % kAccReplicas) * 32 + lane), (unsigned long long)t);
+  }
+}
+
+// executed by warp 0 of the last block: lane l returns the total of value l over the replicas and clears them
+__device__ __forceinline__ long long sum_replicas(long long* __restrict__ replicas, int lane) {
+  long long r[kAccReplicas];
+#pragma unroll
+  for (int i = 0; i < kAccReplicas; ++i) r[i] = *(volatile long long*)(replicas + (size_t)i * 32 + lane);
+  long long tot = 0;
+#pragma unroll
+  for (int i = 0; i < kAccReplicas; ++i) {
+    tot += r[i];
+    replicas[(size_t)i * 32 + lane] = 0;
+  }
+  return tot;
 }
 
 __device__ __forceinline__ void icp_accumulate(const KParams& kp, const IcpArgs& a, const float* M, int iteration,
@@ -196,28 +262,41 @@ __device__ __forceinline__ void icp_accumulate(const KParams& kp, const IcpArgs&
     icp_pixel(kp, a, M, pix, iteration, acc);
 }
 
-// ---- plain evaluation: one K5 pass, result = 32 int64 sums in g_acc (zeroed by the caller) ----
+// ---- plain evaluation: one K5 pass, result = 32 int64 sums written to g_acc by the last block ----
 __global__ void __launch_bounds__(kIcpThreads) k_icp_jacobian(KParams kp, IcpArgs a, Mat4 pose, int iteration,
-                                                              long long* __restrict__ g_acc) {
+                                                              long long* __restrict__ g_acc,
+                                                              long long* __restrict__ slots, unsigned int* ticket) {
   float M[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) M[i] = pose.m[i];
   Acc acc;
   icp_accumulate(kp, a, M, iteration, acc);
-  block_reduce_to_global(acc, g_acc);
+  block_reduce_to_replica(acc, slots);
+  __shared__ bool is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last || threadIdx.x >= 32) return;
+  __threadfence();
+  long long tot = sum_replicas(slots, threadIdx.x);
+  g_acc[threadIdx.x] = tot;
+  if (threadIdx.x == 0) *ticket = 0;
 }
 
 void launch_icp_jacobian(const Launch& L, const KParams& kp, const IcpArgs& a, const Mat4& pose, int iteration,
-                         long long* acc32, int blocks) {
-  cudaMemsetAsync(acc32, 0, 32 * sizeof(long long), L.stream);
+                         long long* acc32, long long* slots, unsigned int* ticket, int blocks) {
   {
     ScopedKernel sk(L, K_ICP_JACOBIAN);
-    k_icp_jacobian<<<blocks, kIcpThreads, 0, L.stream>>>(kp, a, pose, iteration, acc32);
+    k_icp_jacobian<<<blocks, kIcpThreads, 0, L.stream>>>(kp, a, pose, iteration, acc32, slots, ticket);
   }
 }
 
 // ---- fused Gauss-Newton iteration ----
-__global__ void k_gn_init(GnState* st, Mat4d T0, long long* acc32, unsigned int* ticket) {
+__global__ void k_gn_init(GnState* st, Mat4d T0, long long* acc32, unsigned int* ticket, unsigned int* epoch_flag) {
   int i = threadIdx.x;
   if (i < 16) st->pose[i] = T0.m[i];
   if (i < 32) acc32[i] = 0;
@@ -228,13 +307,15 @@ __global__ void k_gn_init(GnState* st, Mat4d T0, long long* acc32, unsigned int*
     st->done = 0;
     st->history_len = 0;
     *ticket = 0;
+    *epoch_flag = 0;
   }
 }
 
-void launch_gn_init(const Launch& L, GnState* st, const Mat4d& T0, long long* acc32, unsigned int* ticket) {
+void launch_gn_init(const Launch& L, GnState* st, const Mat4d& T0, long long* acc32, unsigned int* ticket,
+                    unsigned int* epoch_flag) {
   {
     ScopedKernel sk(L, K_GN_INIT);
-    k_gn_init<<<1, 64, 0, L.stream>>>(st, T0, acc32, ticket);
+    k_gn_init<<<1, 64, 0, L.stream>>>(st, T0, acc32, ticket, epoch_flag);
   }
 }
 
@@ -276,7 +357,7 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_icp_fused(KParams kp, IcpArg
   const int k = st->k;
   Acc acc;
   icp_accumulate(kp, a, M, k, acc);
-  block_reduce_to_global(acc, g_acc);
+  block_reduce_to_global<true>(acc, g_acc);
   __shared__ bool is_last;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -320,6 +401,433 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_icp_fused(KParams kp, IcpArg
   st->history_len = hl;
   __threadfence();
   st->done = done;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Persistent Gauss-Newton kernel: ONE cooperative launch runs every iteration. All blocks are co-resident; after the
+// reduction the last block to arrive performs the GN step (warp-parallel 6x6 LDL^T, SE3 exp, pose update), then
+// releases the other blocks through an epoch flag in HBM. No kernel boundary and no host round trip per iteration
+// (the reference does a 48-float read-back and two glFinish per iteration, Frame2Model.cpp:205-258).
+// ------------------------------------------------------------------------------------------------------------
+struct GnShared {
+  double A[36];
+  double O[48];
+  double P[16];
+  double E[16];
+  double dx[6];
+  int perm[6];
+  int result;
+};
+
+__device__ __forceinline__ void tri_cr(int k, int& c, int& r) {  // k-th entry of the column-wise lower triangle
+  const int start[6] = {0, 6, 11, 15, 18, 20};
+  c = 0;
+#pragma unroll
+  for (int i = 1; i < 6; ++i)
+    if (k >= start[i]) c = i;
+  r = c + (k - start[c]);
+}
+
+// same arithmetic as sbg::ldlt_solve6 / sbg::gn_step, spread over the 32 lanes of one warp (per-element operation
+// order unchanged, so the result is bit-identical to the sequential code)
+__device__ void gn_step_warp(GnShared& sh, long long raw, int lane, double last_error, double eps, double delta_thr,
+                             unsigned long long* tr) {
+#define SB_TG(slot)                                              \
+  if (tr && lane == 0) {                                         \
+    unsigned long long t__;                                      \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));      \
+    tr[slot] = t__;                                              \
+  }
+  const double s = 1.0 / 1073741824.0;
+  // unpack (Frame2Model.cpp:214-227)
+  if (lane < 21) {
+    int c, r;
+    tri_cr(lane, c, r);
+    double v = (double)raw * s;
+    sh.O[c * 6 + r] = v;
+    sh.O[r * 6 + c] = v;
+  } else if (lane < 27) {
+    sh.O[36 + (lane - 21)] = (double)raw * s;
+  } else if (lane == 27) {
+    sh.O[43] = (double)raw * s;
+  } else if (lane == 28) {
+    sh.O[45] = (double)raw * s;
+  } else if (lane == 29) {
+    sh.O[42] = (double)raw;
+  } else if (lane == 30) {
+    sh.O[44] = (double)raw;
+  } else {
+    sh.O[46] = (double)raw;
+    sh.O[47] = 0.0;
+  }
+  __syncwarp();
+  double* A = sh.A;
+  for (int i = lane; i < 36; i += 32) A[i] = sh.O[i];  // already symmetric
+  if (lane < 6) sh.perm[lane] = lane;
+  __syncwarp();
+#pragma unroll 1
+  for (int k = 0; k < 6; ++k) {
+    int piv = k;
+    double best = fabs(A[k * 6 + k]);
+    for (int i = k + 1; i < 6; ++i) {
+      double v = fabs(A[i * 6 + i]);
+      if (v > best) {
+        best = v;
+        piv = i;
+      }
+    }
+    if (piv != k) {  // warp-uniform
+      if (lane < 6) {
+        double t = A[k * 6 + lane];
+        A[k * 6 + lane] = A[piv * 6 + lane];
+        A[piv * 6 + lane] = t;
+      }
+      __syncwarp();
+      if (lane < 6) {
+        double t = A[lane * 6 + k];
+        A[lane * 6 + k] = A[lane * 6 + piv];
+        A[lane * 6 + piv] = t;
+      }
+      if (lane == 0) {
+        int t = sh.perm[k];
+        sh.perm[k] = sh.perm[piv];
+        sh.perm[piv] = t;
+      }
+      __syncwarp();
+    }
+    double dk = A[k * 6 + k];
+    if (dk == 0.0) continue;
+    if (lane > k && lane < 6) A[k * 6 + lane] = A[k * 6 + lane] / dk;
+    __syncwarp();
+    if (lane < 21) {
+      int c, r;
+      tri_cr(lane, c, r);
+      if (c > k) {
+        double v = A[c * 6 + r] - (A[k * 6 + r] * dk) * A[k * 6 + c];
+        A[c * 6 + r] = v;
+        A[r * 6 + c] = v;
+      }
+    }
+    __syncwarp();
+  }
+  SB_TG(12)
+  if (lane == 0) {
+    double y[6], dx[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] = -sh.O[36 + sh.perm[i]];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int k = 0; k < i; ++k) y[i] = y[i] - A[k * 6 + i] * y[k];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] = (A[i * 6 + i] == 0.0) ? 0.0 : y[i] / A[i * 6 + i];
+#pragma unroll
+    for (int i = 5; i >= 0; --i)
+#pragma unroll
+      for (int k = i + 1; k < 6; ++k) y[i] = y[i] - A[i * 6 + k] * y[k];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sh.dx[sh.perm[i]] = y[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dx[i] = sh.dx[i];
+    int result = 1;
+    double current_error = sh.O[43];
+    double linf = 0.0, maxc = sh.O[36];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      if (fabs(dx[i]) > linf) linf = fabs(dx[i]);
+      if (sh.O[36 + i] > maxc) maxc = sh.O[36 + i];
+    }
+    if (linf < delta_thr) result = 0;
+    if (fabs(maxc) < eps) result = 0;
+    if (current_error < last_error && fabs(current_error - last_error) < eps) result = 0;
+    sh.result = result;
+    SB_TG(13)
+    double E[16];
+    sbg::se3_exp(dx, E);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sh.E[i] = E[i];
+  }
+  __syncwarp();
+  double pn = 0.0;
+  if (lane < 16) {
+    int c = lane >> 2, r = lane & 3;
+    const double* Ea = sh.E;
+    const double* B = sh.P;
+    pn = ((Ea[0 * 4 + r] * B[c * 4 + 0] + Ea[1 * 4 + r] * B[c * 4 + 1]) + Ea[2 * 4 + r] * B[c * 4 + 2]) +
+         Ea[3 * 4 + r] * B[c * 4 + 3];
+  }
+  __syncwarp();
+  if (lane < 16) sh.P[lane] = pn;
+  __syncwarp();
+#undef SB_TG
+}
+
+// lane-parallel one-shot all-reduce of the 32 sums over the ranks' peer-mapped mailboxes (warp 0 of the last block)
+__device__ long long comm_allreduce32_warp(const CommDev& cd, long long raw, int lane) {
+  int epoch = 0;
+  if (lane == 0) {
+    epoch = (int)(*cd.epoch) + 1;  // stamps start at 1: a zeroed mailbox never matches
+    *cd.epoch = (unsigned int)epoch;
+  }
+  epoch = __shfl_sync(0xffffffffu, epoch, 0);
+  const int slot = epoch & 1;
+  for (int r = 0; r < cd.nranks; ++r) {
+    volatile long long* dst = cd.mailbox[r] + ((size_t)(slot * 8 + cd.rank)) * 40;
+    dst[lane] = raw;
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (lane == 0) {
+    for (int r = 0; r < cd.nranks; ++r) {
+      volatile long long* dst = cd.mailbox[r] + ((size_t)(slot * 8 + cd.rank)) * 40;
+      dst[32] = (long long)epoch;
+    }
+    __threadfence_system();
+    volatile long long* mine = cd.mailbox[cd.rank];
+    for (int r = 0; r < cd.nranks; ++r) {
+      volatile long long* src = mine + ((size_t)(slot * 8 + r)) * 40;
+      while (src[32] != (long long)epoch) {
+      }
+    }
+    __threadfence_system();
+  }
+  __syncwarp();
+  long long tot = 0;
+  volatile long long* mine = cd.mailbox[cd.rank];
+  for (int r = 0; r < cd.nranks; ++r) tot += mine[((size_t)(slot * 8 + r)) * 40 + lane];
+  return tot;
+}
+
+__global__ void __launch_bounds__(kIcpThreads, 2) k_icp_persistent(KParams kp, IcpArgs a, GnState* __restrict__ st,
+                                                                long long* __restrict__ slots, unsigned int* ticket,
+                                                                unsigned int* epoch_flag, int max_iter, double eps,
+                                                                double delta, CommDev cd, unsigned long long* trace) {
+#define SB_TR(slot)                                                                     \
+  if (trace && threadIdx.x == 0 && it < 16 && (blockIdx.x == 0 || (slot) >= 8)) {       \
+    unsigned long long t__;                                                             \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                             \
+    trace[it * 16 + (slot)] = t__;                                                      \
+  }
+  __shared__ GnShared sh;
+  __shared__ bool is_last;
+  __shared__ double s_pose[16];
+  __shared__ int s_k, s_done;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (unsigned int it = 0;; ++it) {
+    // Warp 0 waits for the previous iteration's step (epoch flag), then fetches the state written by that step with
+    // ONE round of coherent loads spread over its lanes and broadcasts it through shared memory (every thread reading
+    // the pose from L2 would hammer a single L2 sector with ~40k requests per iteration).
+    if (warp == 0) {
+      if (it > 0) {
+        if (lane == 0) {
+          while (*(volatile unsigned int*)epoch_flag != it) {
+          }
+          __threadfence();
+        }
+        __syncwarp();
+      }
+      if (lane < 16) s_pose[lane] = *(volatile double*)&st->pose[lane];
+      if (lane == 16) s_k = *(volatile int*)&st->k;
+      if (lane == 17) s_done = *(volatile int*)&st->done;
+    }
+    __syncthreads();
+    if (s_done) break;
+    SB_TR(0)
+    float M[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) M[i] = (float)s_pose[i];  // pose_.cast<float>(), Frame2Model.cpp:194
+    const int k = s_k;
+    Acc acc;
+    icp_accumulate(kp, a, M, k, acc);
+    __syncthreads();
+    SB_TR(1)
+    block_reduce_to_replica(acc, slots);
+    __syncthreads();
+    SB_TR(2)
+    if (threadIdx.x == 0) {
+      __threadfence();  // cumulative: orders this block's slot stores (observed through the barrier) before the ticket
+      unsigned int t = atomicAdd(ticket, 1u);
+      is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    SB_TR(3)
+    if (is_last && warp == 0) {
+      SB_TR(8)
+      __threadfence();
+      long long raw = sum_replicas(slots, lane);
+      SB_TR(9)
+      double last_error = 0.0;
+      if (lane == 16) last_error = *(volatile double*)&st->last_error;
+      last_error = __shfl_sync(0xffffffffu, last_error, 16);
+      if (cd.nranks > 1) raw = comm_allreduce32_warp(cd, raw, lane);
+      if (lane < 16) sh.P[lane] = s_pose[lane];
+      int hl = (int)it;  // one pose has been pushed per completed iteration
+      if (lane < 16) st->history[hl * 16 + lane] = s_pose[lane];  // history_.push_back(Tk_)
+      ++hl;
+      __syncwarp();
+      gn_step_warp(sh, raw, lane, last_error, eps, delta, (trace && it < 16) ? trace + it * 16 : nullptr);
+      SB_TR(10)
+      if (lane < 16) st->pose[lane] = sh.P[lane];
+      for (int i = lane; i < 48; i += 32) st->out48[i] = sh.O[i];
+      int kk = k, done = 0;
+      if (sh.result == 0) {
+        done = 1;
+      } else {
+        ++kk;
+        if (kk >= max_iter) {  // the loop pushes the pose once more and leaves (LieGaussNewton.cpp:24-27)
+          if (lane < 16) st->history[hl * 16 + lane] = sh.P[lane];
+          ++hl;
+          done = 1;
+        }
+      }
+      if (lane == 0) {
+        st->last_error = sh.O[43];
+        st->k = kk;
+        st->history_len = hl;
+        st->done = done;
+        *ticket = 0;
+      }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicExch(epoch_flag, it + 1u);
+      SB_TR(11)
+    }
+  }
+#undef SB_TR
+}
+
+int icp_persistent_max_blocks(int sm_count) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_persistent, kIcpThreads, 0) != cudaSuccess) return 0;
+  return per_sm * sm_count;
+}
+
+int launch_icp_persistent(const Launch& L, const KParams& kp, const IcpArgs& a, GnState* st, long long* slots,
+                          unsigned int* ticket, unsigned int* epoch_flag, int max_iter, double eps, double delta,
+                          const CommDev* comm, int blocks, unsigned long long* trace) {
+  CommDev cd;
+  if (comm) {
+    cd = *comm;
+  } else {
+    memset(&cd, 0, sizeof(cd));
+    cd.nranks = 1;
+  }
+  KParams kpv = kp;
+  IcpArgs av = a;
+  void* args[] = {&kpv, &av, &st, &slots, &ticket, &epoch_flag, &max_iter, &eps, &delta, &cd, &trace};
+  cudaError_t e;
+  {
+    ScopedKernel sk(L, K_ICP_FUSED);
+    e = cudaLaunchCooperativeKernel((void*)k_icp_persistent, dim3(blocks), dim3(kIcpThreads), args, 0, L.stream);
+  }
+  return e == cudaSuccess ? 0 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Device-side pose bookkeeping of SurfelMapping::updatePose (SurfelMapping.cpp:389-473). One thread, fp64, the same
+// functions (sbg::*) the host-side API uses, so host and device agree bit for bit.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_pose_after_icp(const GnState* __restrict__ gn, PoseDev* __restrict__ pd, Mat4d T0, uint32_t timestamp,
+                                 int fallback_mode) {
+  if (threadIdx.x != 0) return;
+  double inc[16], inv_last[16], delta[16], Pn[16];
+  for (int i = 0; i < 16; ++i) pd->T0[i] = T0.m[i];
+  for (int i = 0; i < 16; ++i) inc[i] = gn->pose[i];  // increment = gn_->pose()   :395
+  for (int i = 0; i < 16; ++i) pd->increment[i] = inc[i];
+  pd->icp_iterations = gn->k;
+  sbg::rigid_inverse_d(pd->lastIncrement, inv_last);
+  mat4_mul<double>(inv_last, inc, delta);           // delta = lastIncrement_.inverse() * increment   :397
+  mat4_mul<double>(pd->currentPose, inc, Pn);       // currentPose_new_ * increment   :406
+  for (int i = 0; i < 16; ++i) pd->P_active.m[i] = (float)Pn[i];
+  sbg::rigid_inverse_f(pd->P_active.m, pd->invP_active.m);
+  float t_err = (float)sqrt((delta[12] * delta[12] + delta[13] * delta[13]) + delta[14] * delta[14]);  // :433
+  float angle = (float)(0.5 * (((delta[0] + delta[5]) + delta[10]) - 1.0));
+  float ca = angle < 1.0f ? angle : 1.0f;
+  ca = ca > -1.0f ? ca : -1.0f;
+  float r_err = acosf_(ca);
+  pd->t_err = t_err;
+  pd->r_err = r_err;
+  int fb = (timestamp > 1 && ((double)t_err > 0.4 || (double)r_err > 0.1) && fallback_mode) ? 1 : 0;  // :437
+  pd->fallback = fb;
+  if (fb) pd->trackLoss += 1;
+}
+
+void launch_pose_after_icp(const Launch& L, const GnState* gn, PoseDev* pd, const Mat4d& T0, uint32_t timestamp,
+                           int fallback_mode) {
+  {
+    ScopedKernel sk(L, K_GN_INIT);
+    k_pose_after_icp<<<1, 32, 0, L.stream>>>(gn, pd, T0, timestamp, fallback_mode);
+  }
+}
+
+// prepares the GN state for the frame-to-frame fallback run; when no track loss was detected the state is marked done
+// and the minimisation kernel that follows returns at once
+__global__ void k_gn_init_fallback(GnState* st, const PoseDev* __restrict__ pd, long long* acc32, unsigned int* ticket,
+                                   unsigned int* epoch_flag) {
+  int i = threadIdx.x;
+  const int fb = pd->fallback;
+  if (fb) {
+    if (i < 16) st->pose[i] = pd->T0[i];
+    if (i < 48) st->out48[i] = 0.0;
+  }
+  if (i < 32) acc32[i] = 0;
+  if (i == 0) {
+    if (fb) {
+      st->last_error = (double)3.402823466e+38f;
+      st->k = 0;
+      st->history_len = 0;
+    }
+    st->done = fb ? 0 : 1;
+    *ticket = 0;
+    *epoch_flag = 0;
+  }
+}
+
+void launch_gn_init_fallback(const Launch& L, GnState* st, const PoseDev* pd, long long* acc32, unsigned int* ticket,
+                             unsigned int* epoch_flag) {
+  {
+    ScopedKernel sk(L, K_GN_INIT);
+    k_gn_init_fallback<<<1, 64, 0, L.stream>>>(st, pd, acc32, ticket, epoch_flag);
+  }
+}
+
+// lastPose_ = currentPose_; currentPose_ = currentPose_ * increment; ... (SurfelMapping.cpp:451-473) and the pose-table
+// entry of this scan (SurfelMap.cpp:494-495)
+__global__ void k_pose_finalize(const GnState* __restrict__ gn, PoseDev* __restrict__ pd, int had_icp,
+                                float* __restrict__ poses, float* __restrict__ poses_inv, uint32_t t) {
+  if (threadIdx.x != 0) return;
+  if (had_icp) {
+    double inc[16], np[16];
+    if (pd->fallback)
+      for (int i = 0; i < 16; ++i) inc[i] = gn->pose[i];  // increment = gn_->pose() of the recovery run   :446
+    else
+      for (int i = 0; i < 16; ++i) inc[i] = pd->increment[i];
+    for (int i = 0; i < 16; ++i) pd->lastPose[i] = pd->currentPose[i];
+    mat4_mul<double>(pd->currentPose, inc, np);  // :452
+    for (int i = 0; i < 16; ++i) {
+      pd->currentPose[i] = np[i];
+      pd->lastIncrement[i] = inc[i];  // :473
+      pd->increment[i] = inc[i];
+    }
+  }
+  for (int i = 0; i < 16; ++i) pd->P_cur.m[i] = (float)pd->currentPose[i];
+  sbg::rigid_inverse_f(pd->P_cur.m, pd->invP_cur.m);
+  if (t < kMaxPoses) {
+    float inv[16];
+    sbg::rigid_inverse_f(pd->P_cur.m, inv);
+    for (int i = 0; i < 16; ++i) {
+      poses[16 * (size_t)t + i] = pd->P_cur.m[i];
+      poses_inv[16 * (size_t)t + i] = inv[i];
+    }
+  }
+}
+
+void launch_pose_finalize(const Launch& L, const GnState* gn, PoseDev* pd, int had_icp, float* poses, float* poses_inv,
+                          uint32_t t) {
+  {
+    ScopedKernel sk(L, K_GN_INIT);
+    k_pose_finalize<<<1, 32, 0, L.stream>>>(gn, pd, had_icp, poses, poses_inv, t);
+  }
 }
 
 void launch_icp_fused_iteration(const Launch& L, const KParams& kp, const IcpArgs& a, GnState* st, long long* acc32,

@@ -71,6 +71,7 @@ struct IcpArgs {
   float distance_thresh, angle_thresh;  // Frame2Model.cpp:66-67
   int row_begin, row_end;
   int has_semantics;
+  int row_step;  // row permutation stride of the work distribution, coprime to (row_end - row_begin)
 };
 
 // peer mailboxes for the multi-GPU one-shot all-reduce (fused into the Jacobian kernel's last block)
@@ -85,6 +86,20 @@ struct Mat4 {
 };
 struct Mat4d {
   double m[16];
+};
+
+// Device-resident pose bookkeeping of SurfelMapping::updatePose (SurfelMapping.cpp:372-476): the per-scan pipeline is
+// enqueued without a host round trip; the host reads this block back once, at the end of the scan.
+struct PoseDev {
+  double currentPose[16], lastPose[16], lastIncrement[16], increment[16], T0[16];
+  Mat4 P_active, invP_active;  // currentPose_new * increment (render_active), and its inverse
+  Mat4 P_cur, invP_cur;        // the scan's final pose (float) and inverse: map update + model rendering
+  int fallback;                // track loss detected: the frame-to-frame minimisation runs
+  int trackLoss;               // counter
+  int icp_iterations;          // k_ of the frame-to-model minimisation
+  int pad;
+  float t_err, r_err;
+  int pad2[2];
 };
 
 // ---------------- kernel ids (launch accounting + the optional CUDA-event profiler) ----------------
@@ -138,12 +153,25 @@ void launch_preprocess(const Launch& L, const KParams& kp, const float4* pts, co
 
 // sb_icp.cu
 void launch_icp_jacobian(const Launch& L, const KParams& kp, const IcpArgs& a, const Mat4& pose, int iteration,
-                         long long* acc32, int blocks);
+                         long long* acc32, long long* slots, unsigned int* ticket, int blocks);
 void launch_icp_fused_iteration(const Launch& L, const KParams& kp, const IcpArgs& a, GnState* st, long long* acc32,
                                 unsigned int* ticket, int max_iter, double eps, double delta, const CommDev* comm,
                                 int blocks);
-void launch_gn_init(const Launch& L, GnState* st, const Mat4d& T0, long long* acc32, unsigned int* ticket);
+void launch_gn_init(const Launch& L, GnState* st, const Mat4d& T0, long long* acc32, unsigned int* ticket,
+                    unsigned int* epoch_flag);
+int launch_icp_persistent(const Launch& L, const KParams& kp, const IcpArgs& a, GnState* st, long long* slots,
+                          unsigned int* ticket, unsigned int* epoch_flag, int max_iter, double eps, double delta,
+                          const CommDev* comm, int blocks, unsigned long long* trace);
+int icp_persistent_max_blocks(int sm_count);
+// pose bookkeeping kernels (sb_icp.cu)
+void launch_pose_after_icp(const Launch& L, const GnState* gn, PoseDev* pd, const Mat4d& T0, uint32_t timestamp,
+                           int fallback_mode);
+void launch_gn_init_fallback(const Launch& L, GnState* st, const PoseDev* pd, long long* acc32, unsigned int* ticket,
+                             unsigned int* epoch_flag);
+void launch_pose_finalize(const Launch& L, const GnState* gn, PoseDev* pd, int had_icp, float* poses, float* poses_inv,
+                          uint32_t t);
 int icp_grid_blocks(int sm_count);
+int icp_balanced_blocks(int pixels, int max_blocks);
 
 // sb_map.cu
 struct RenderTargets {
@@ -151,7 +179,8 @@ struct RenderTargets {
   unsigned long long* key_new;   // may be null
   unsigned long long* key_comp;  // may be null
 };
-void launch_pose_products(const Launch& L, const Mat4& A, const float* poses, float* out, uint32_t count);
+void launch_pose_products(const Launch& L, const Mat4& A, const Mat4* A_dev, const float* poses, float* out,
+                          uint32_t count);
 void launch_render_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, const uint32_t* n_dev, uint32_t n_upper,
                            const float* M, float conf_thr, int t_thr, int emit_old, int emit_new, int lequal,
                            RenderTargets t);
@@ -162,7 +191,8 @@ void launch_index_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, co
                           const float* M, unsigned long long* keys);
 void launch_radius(const Launch& L, const KParams& kp, FrameDev frame, float4* radius_map);
 void launch_update_surfels(const Launch& L, const KParams& kp, SurfelPlanes src, SurfelPlanes tmp, const uint32_t* n_dev,
-                           uint32_t n_upper, const Mat4& pose, const Mat4& inv_pose, const float* poses,
+                           uint32_t n_upper, const Mat4& pose, const Mat4& inv_pose, const Mat4* pose_dev,
+                           const Mat4* inv_pose_dev, const float* poses,
                            const float* poses_inv, const unsigned long long* index_keys, const float4* radius_map,
                            FrameDev frame, int timestamp, float2 submap_center, float submap_extent,
                            uint8_t* integrated, uint8_t* keep, uint32_t* block_counts);

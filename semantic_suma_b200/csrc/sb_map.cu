@@ -46,21 +46,23 @@ __device__ __forceinline__ void load_mat(const float* __restrict__ table, int id
 
 // out[t] = A * poses[t]  (render_surfels.vert:46 evaluates (inv_pose * surfelPose) * v; the product is shared by all
 // surfels created at time t)
-__global__ void k_pose_products(Mat4 A, const float* __restrict__ poses, float* __restrict__ out, uint32_t count) {
+__global__ void k_pose_products(Mat4 A, const Mat4* __restrict__ A_dev, const float* __restrict__ poses,
+                                float* __restrict__ out, uint32_t count) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= count) return;
   float a[16], b[16], c[16];
-  for (int i = 0; i < 16; ++i) a[i] = A.m[i];
+  for (int i = 0; i < 16; ++i) a[i] = A_dev ? A_dev->m[i] : A.m[i];
   load_mat(poses, (int)t, b);
   mat4_mul<float>(a, b, c);
   for (int i = 0; i < 16; ++i) out[16 * (size_t)t + i] = c[i];
 }
 
-void launch_pose_products(const Launch& L, const Mat4& A, const float* poses, float* out, uint32_t count) {
+void launch_pose_products(const Launch& L, const Mat4& A, const Mat4* A_dev, const float* poses, float* out,
+                          uint32_t count) {
   if (count == 0) return;
   {
     ScopedKernel sk(L, K_POSE_PRODUCTS);
-    k_pose_products<<<(count + 127) / 128, 128, 0, L.stream>>>(A, poses, out, count);
+    k_pose_products<<<(count + 127) / 128, 128, 0, L.stream>>>(A, A_dev, poses, out, count);
   }
 }
 
@@ -77,31 +79,41 @@ __device__ __forceinline__ long long ceil_div256(long long a) { return -((-a) >>
 __device__ __forceinline__ long long edge_fn(const RVert& P, const RVert& Q, long long X, long long Y) {
   return (Q.X - P.X) * (Y - P.Y) - (Q.Y - P.Y) * (X - P.X);
 }
-__device__ __forceinline__ bool edge_in(long long w, const RVert& P, const RVert& Q) {
-  if (w > 0) return true;
-  if (w < 0) return false;
+
+// what a fragment of one surfel writes to: which key images, with which low key bits
+struct Emit {
+  uint32_t k;
+  uint32_t flags;  // bit0 old-class surfel, bit1 new-class surfel, bit2 GL_LEQUAL composed mode
+};
+
+__device__ __forceinline__ bool edge_tie(const RVert& P, const RVert& Q) {  // rule for pixels exactly on an edge
   long long dx = Q.X - P.X, dy = Q.Y - P.Y;
   return dy > 0 || (dy == 0 && dx > 0);
 }
 
-struct EmitCtx {
-  unsigned long long* key_a;   // old or new image (LESS, pass bit 0)
-  unsigned long long* key_b;   // second class image when a surfel is both old and new
-  unsigned long long* key_c;   // composed image
-  unsigned long long low_a, low_b;            // idx
-  unsigned long long low_c_old, low_c_new;    // (pass << 32 | idx) or the inverted LEQUAL form
-  bool to_a, to_b, c_old, c_new;
-  bool lequal;
-  int W, H;
+// Triangle prepared for pixel-centre coverage tests with exact integer edge functions. The edge values at the first
+// pixel centre of the bounding box and their per-pixel steps are int64 (no rounding anywhere):
+// E(P + (256,0)) = E(P) - 256*dy, E(P + (0,256)) = E(P) + 256*dx.
+struct TriSetup {
+  long long eA, eB, eC;     // edge(B,C), edge(C,A), edge(A,B) at the first pixel centre
+  long long sxA, sxB, sxC;  // step per pixel in x
+  long long syA, syB, syC;  // step per pixel in y
+  float farea;
+  float zA, zB, zC, txA, txB, txC, tyA, tyB, tyC;
+  int i0, j0, ni, nj;       // bounding box origin and extent (inclusive), clamped to the image
+  uint32_t ties;            // bit0..2: pixels exactly on edge A/B/C count as inside
+  uint32_t valid;
 };
 
-__device__ __forceinline__ void raster_tri(const EmitCtx& e, RVert A, RVert B, RVert C) {
+__device__ __forceinline__ TriSetup tri_prepare(RVert A, RVert B, RVert C, int W, int H) {
+  TriSetup t;
+  t.valid = 0;
   long long area = (B.X - A.X) * (C.Y - A.Y) - (B.Y - A.Y) * (C.X - A.X);
-  if (area == 0) return;
+  if (area == 0) return t;
   if (area < 0) {
-    RVert t = B;
+    RVert x = B;
     B = C;
-    C = t;
+    C = x;
     area = -area;
   }
   long long minX = min(A.X, min(B.X, C.X)), maxX = max(A.X, max(B.X, C.X));
@@ -110,99 +122,186 @@ __device__ __forceinline__ void raster_tri(const EmitCtx& e, RVert A, RVert B, R
   long long j0 = ceil_div256(minY - 128), j1 = floor_div256(maxY - 128);
   if (i0 < 0) i0 = 0;
   if (j0 < 0) j0 = 0;
-  if (i1 > e.W - 1) i1 = e.W - 1;
-  if (j1 > e.H - 1) j1 = e.H - 1;
-  const float farea = (float)area;
-  for (long long j = j0; j <= j1; ++j)
-    for (long long i = i0; i <= i1; ++i) {
-      long long X = i * 256 + 128, Y = j * 256 + 128;
-      long long wA = edge_fn(B, C, X, Y), wB = edge_fn(C, A, X, Y), wC = edge_fn(A, B, X, Y);
-      if (!edge_in(wA, B, C) || !edge_in(wB, C, A) || !edge_in(wC, A, B)) continue;
-      float fB = (float)wB / farea, fC = (float)wC / farea;
-      float fA = (1.0f - fB) - fC;
-      float tx = (fA * A.tx + fB * B.tx) + fC * C.tx;
-      float ty = (fA * A.ty + fB * B.ty) + fC * C.ty;
-      if (tx * tx + ty * ty > 1.0f) continue;  // render_surfels.frag:22-28
-      float z = (fA * A.z + fB * B.z) + fC * C.z;
-      if (!(z >= 0.0f && z <= 1.0f)) continue;  // near / far clip
-      unsigned long long d = (unsigned long long)depth24(z);
-      if (!e.lequal && d >= kDepthClear) continue;  // GL_LESS against the cleared depth
-      size_t pix = (size_t)j * e.W + (size_t)i;
-      unsigned long long hi = d << 40;
-      if (e.to_a) atomicMin(e.key_a + pix, hi | e.low_a);
-      if (e.to_b) atomicMin(e.key_b + pix, hi | e.low_b);
-      if (e.c_old) atomicMin(e.key_c + pix, hi | e.low_c_old);
-      if (e.c_new) atomicMin(e.key_c + pix, hi | e.low_c_new);
-    }
+  if (i1 > W - 1) i1 = W - 1;
+  if (j1 > H - 1) j1 = H - 1;
+  if (i0 > i1 || j0 > j1) return t;
+  t.farea = (float)area;
+  const long long X0 = i0 * 256 + 128, Y0 = j0 * 256 + 128;
+  t.eA = edge_fn(B, C, X0, Y0);
+  t.eB = edge_fn(C, A, X0, Y0);
+  t.eC = edge_fn(A, B, X0, Y0);
+  t.sxA = -256 * (C.Y - B.Y); t.sxB = -256 * (A.Y - C.Y); t.sxC = -256 * (B.Y - A.Y);
+  t.syA = 256 * (C.X - B.X); t.syB = 256 * (A.X - C.X); t.syC = 256 * (B.X - A.X);
+  t.ties = (edge_tie(B, C) ? 1u : 0u) | (edge_tie(C, A) ? 2u : 0u) | (edge_tie(A, B) ? 4u : 0u);
+  t.zA = A.z; t.zB = B.z; t.zC = C.z;
+  t.txA = A.tx; t.txB = B.tx; t.txC = C.tx;
+  t.tyA = A.ty; t.tyB = B.ty; t.tyC = C.ty;
+  t.i0 = (int)i0; t.j0 = (int)j0; t.ni = (int)(i1 - i0); t.nj = (int)(j1 - j0);
+  t.valid = 1;
+  return t;
 }
 
-// render_surfels.vert:42-54 + .geom:76-122 for every surfel of the map
-__global__ void __launch_bounds__(kThreads) k_render_scatter(KParams kp, SurfelPlanes s, const uint32_t* __restrict__ n_dev,
-                                                            const float* __restrict__ Mtab, float conf_thr, int t_thr,
-                                                            int emit_old, int emit_new, int lequal, RenderTargets t) {
+// fragment stage for one covered pixel (render_surfels.frag:19-33 + depth test)
+__device__ __forceinline__ void tri_fragment(const TriSetup& t, const Emit& e, const RenderTargets& rt, int W,
+                                             long long wB, long long wC, int di, int dj) {
+  float fB = (float)wB / t.farea, fC = (float)wC / t.farea;
+  float fA = (1.0f - fB) - fC;
+  float tx = (fA * t.txA + fB * t.txB) + fC * t.txC;
+  float ty = (fA * t.tyA + fB * t.tyB) + fC * t.tyC;
+  if (tx * tx + ty * ty > 1.0f) return;  // outside the disc
+  float z = (fA * t.zA + fB * t.zB) + fC * t.zC;
+  if (!(z >= 0.0f && z <= 1.0f)) return;  // near / far clip
+  unsigned long long d = (unsigned long long)depth24(z);
+  const bool lequal = (e.flags & 4u) != 0;
+  if (!lequal && d >= kDepthClear) return;  // GL_LESS against the cleared depth
+  size_t pix = (size_t)(t.j0 + dj) * W + (size_t)(t.i0 + di);
+  unsigned long long hi = d << 40;
+  // keys only ever decrease: a (possibly stale, L1-cached) read that is already smaller proves the atomic cannot
+  // win, so most hidden fragments never reach the L2 atomic unit
+  if (e.flags & 1u) {  // old-class surfel
+    if (rt.key_old) {
+      unsigned long long key = hi | e.k;
+      if (key < rt.key_old[pix]) atomicMin(rt.key_old + pix, key);
+    }
+    if (rt.key_comp) {  // old pass is drawn first: it wins depth ties under GL_LESS, loses them under GL_LEQUAL
+      unsigned long long key = lequal ? (hi | (1ull << 32) | (unsigned long long)(0xffffffffu - e.k)) : (hi | e.k);
+      if (key < rt.key_comp[pix]) atomicMin(rt.key_comp + pix, key);
+    }
+  }
+  if (e.flags & 2u) {  // new-class surfel
+    if (rt.key_new) {
+      unsigned long long key = hi | e.k;
+      if (key < rt.key_new[pix]) atomicMin(rt.key_new + pix, key);
+    }
+    if (rt.key_comp) {
+      unsigned long long key = lequal ? (hi | (unsigned long long)(0xffffffffu - e.k)) : (hi | (1ull << 32) | e.k);
+      if (key < rt.key_comp[pix]) atomicMin(rt.key_comp + pix, key);
+    }
+  }
+}
+
+// one lane walks its own (small) triangle: three 64-bit adds and sign tests per pixel
+__device__ __forceinline__ void raster_lane(const TriSetup& t, const Emit& e, const RenderTargets& rt, int W) {
+  long long rowA = t.eA, rowB = t.eB, rowC = t.eC;
+  const bool tieA = t.ties & 1u, tieB = t.ties & 2u, tieC = t.ties & 4u;
+  for (int dj = 0; dj <= t.nj; ++dj) {
+    long long wA = rowA, wB = rowB, wC = rowC;
+    for (int di = 0; di <= t.ni; ++di) {
+      bool in = (wA > 0 || (wA == 0 && tieA)) && (wB > 0 || (wB == 0 && tieB)) && (wC > 0 || (wC == 0 && tieC));
+      if (in) tri_fragment(t, e, rt, W, wB, wC, di, dj);
+      wA += t.sxA;
+      wB += t.sxB;
+      wC += t.sxC;
+    }
+    rowA += t.syA;
+    rowB += t.syB;
+    rowC += t.syC;
+  }
+}
+
+// the whole warp walks one (large) triangle: lane l takes pixels l, l+32, ... of the bounding box
+__device__ __forceinline__ void raster_warp(const TriSetup& t, const Emit& e, const RenderTargets& rt, int W, int lane) {
+  const int w = t.ni + 1, total = w * (t.nj + 1);
+  const bool tieA = t.ties & 1u, tieB = t.ties & 2u, tieC = t.ties & 4u;
+  for (int p = lane; p < total; p += 32) {
+    int dj = p / w, di = p - dj * w;
+    long long wA = t.eA + (long long)di * t.sxA + (long long)dj * t.syA;
+    long long wB = t.eB + (long long)di * t.sxB + (long long)dj * t.syB;
+    long long wC = t.eC + (long long)di * t.sxC + (long long)dj * t.syC;
+    bool in = (wA > 0 || (wA == 0 && tieA)) && (wB > 0 || (wB == 0 && tieB)) && (wC > 0 || (wC == 0 && tieC));
+    if (in) tri_fragment(t, e, rt, W, wB, wC, di, dj);
+  }
+}
+
+constexpr int kRenderThreads = 128;
+constexpr int kBigTriPixels = 96;  // bounding boxes larger than this are rasterised by the whole warp
+
+struct DeferredTri {
+  TriSetup t;
+  Emit e;
+};
+
+// render_surfels.vert:42-54 + .geom:76-122 for every surfel of the map. One lane per surfel for the transform,
+// visibility tests and corner projection; small quads are rasterised by their own lane, the heavy tail (surfels
+// created far away and seen from close by cover hundreds of pixels) is parked in shared memory and rasterised by
+// the whole warp, which keeps the lanes of a warp busy.
+__global__ void __launch_bounds__(kRenderThreads) k_render_scatter(KParams kp, SurfelPlanes s, const uint32_t* __restrict__ n_dev,
+                                                                   const float* __restrict__ Mtab, float conf_thr, int t_thr,
+                                                                   int emit_old, int emit_new, int lequal, RenderTargets rt) {
+  __shared__ DeferredTri s_def[kRenderThreads / 32][64];
+  __shared__ int s_cnt[kRenderThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_cnt[warp] = 0;
+  __syncwarp();
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= *n_dev) return;
-  float4 p2 = __ldg(s.p2 + k);
-  float4 p1 = __ldg(s.p1 + k);
-  if (!(!kp.use_stability || p1.w > conf_thr)) return;  // .geom:87 (cheap test first)
-  int creation = (int)p2.w, ts = (int)__float_as_uint(p2.x);
-  bool is_old = emit_old && (creation < t_thr);                       // .geom:90
-  bool is_new = emit_new && (creation >= t_thr || ts >= t_thr);       // .geom:91
-  if (!is_old && !is_new) return;
-  float4 p0 = __ldg(s.p0 + k);
-  float M[16];
-  load_mat(Mtab, pose_index(p2.w), M);
-  V3 pp = xform_point(M, mk3(p0.x, p0.y, p0.z));
-  V3 nn = xform_dir(M, mk3(p1.x, p1.y, p1.z));
-  float r = p0.w;
-  bool visible = dot3(nn, divs3(neg3(pp), len3(pp))) > 0.01f;  // .geom:84
-  float cx, cy, cz;
-  project01(pp, kp.m_fov_up, kp.m_fov, kp.m_min_depth, kp.m_max_depth, cx, cy, cz);
-  if (!(visible && cx >= 0.0f && cy >= 0.0f && cz >= 0.0f && cx < 1.0f && cy < 1.0f && cz < 1.0f)) return;
-  V3 u = normalize3(mk3(nn.y - nn.z, -nn.x, nn.x));
-  V3 v = normalize3(cross3(nn, u));
-  V3 ru = scale3(r, u), rv = scale3(r, v);
-  V3 corner[4];
-  corner[0] = sub3(sub3(pp, ru), rv);
-  corner[1] = sub3(add3(pp, ru), rv);
-  corner[2] = add3(sub3(pp, ru), rv);
-  corner[3] = add3(add3(pp, ru), rv);
-  RVert q[4];
+  bool alive = k < *n_dev;
+  float4 p0, p1, p2;
+  bool is_old = false, is_new = false;
+  if (alive) {
+    p2 = __ldg(s.p2 + k);
+    p1 = __ldg(s.p1 + k);
+    alive = !kp.use_stability || p1.w > conf_thr;  // .geom:87 (cheap test first)
+  }
+  if (alive) {
+    int creation = (int)p2.w, ts = (int)__float_as_uint(p2.x);
+    is_old = emit_old && (creation < t_thr);                  // .geom:90
+    is_new = emit_new && (creation >= t_thr || ts >= t_thr);  // .geom:91
+    alive = is_old || is_new;
+  }
+  if (alive) {
+    p0 = __ldg(s.p0 + k);
+    float M[16];
+    load_mat(Mtab, pose_index(p2.w), M);
+    V3 pp = xform_point(M, mk3(p0.x, p0.y, p0.z));
+    V3 nn = xform_dir(M, mk3(p1.x, p1.y, p1.z));
+    float r = p0.w;
+    bool visible = dot3(nn, divs3(neg3(pp), len3(pp))) > 0.01f;  // .geom:84
+    float cx, cy, cz;
+    project01(pp, kp.m_fov_up, kp.m_fov, kp.m_min_depth, kp.m_max_depth, cx, cy, cz);
+    if (visible && cx >= 0.0f && cy >= 0.0f && cz >= 0.0f && cx < 1.0f && cy < 1.0f && cz < 1.0f) {
+      V3 u = normalize3(mk3(nn.y - nn.z, -nn.x, nn.x));
+      V3 v = normalize3(cross3(nn, u));
+      V3 ru = scale3(r, u), rv = scale3(r, v);
+      V3 corner[4];
+      corner[0] = sub3(sub3(pp, ru), rv);
+      corner[1] = sub3(add3(pp, ru), rv);
+      corner[2] = add3(sub3(pp, ru), rv);
+      corner[3] = add3(add3(pp, ru), rv);
+      RVert q[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float x, y, z;
-    project01(corner[i], kp.m_fov_up, kp.m_fov, kp.m_min_depth, kp.m_max_depth, x, y, z);
-    if (cx - x > 0.5f) x += 1.0f;  // .geom:68
-    if (x - cx > 0.5f) x -= 1.0f;  // .geom:69
-    float xw = (0.5f * (2.0f * x - 1.0f) + 0.5f) * (float)kp.Wm;
-    float yw = (0.5f * (2.0f * y - 1.0f) + 0.5f) * (float)kp.Hm;
-    q[i].z = 0.5f * (2.0f * z - 1.0f) + 0.5f;
-    q[i].X = __float2ll_rn(xw * 256.0f);
-    q[i].Y = __float2ll_rn(yw * 256.0f);
-    q[i].tx = (i & 1) ? 1.0f : -1.0f;
-    q[i].ty = (i & 2) ? 1.0f : -1.0f;
+      for (int i = 0; i < 4; ++i) {
+        float x, y, z;
+        project01(corner[i], kp.m_fov_up, kp.m_fov, kp.m_min_depth, kp.m_max_depth, x, y, z);
+        if (cx - x > 0.5f) x += 1.0f;  // .geom:68
+        if (x - cx > 0.5f) x -= 1.0f;  // .geom:69
+        float xw = (0.5f * (2.0f * x - 1.0f) + 0.5f) * (float)kp.Wm;
+        float yw = (0.5f * (2.0f * y - 1.0f) + 0.5f) * (float)kp.Hm;
+        q[i].z = 0.5f * (2.0f * z - 1.0f) + 0.5f;
+        q[i].X = __float2ll_rn(xw * 256.0f);
+        q[i].Y = __float2ll_rn(yw * 256.0f);
+        q[i].tx = (i & 1) ? 1.0f : -1.0f;
+        q[i].ty = (i & 2) ? 1.0f : -1.0f;
+      }
+      Emit e;
+      e.k = k;
+      e.flags = (is_old ? 1u : 0u) | (is_new ? 2u : 0u) | (lequal ? 4u : 0u);
+#pragma unroll
+      for (int tri = 0; tri < 2; ++tri) {
+        TriSetup t = tri == 0 ? tri_prepare(q[0], q[1], q[2], kp.Wm, kp.Hm) : tri_prepare(q[1], q[2], q[3], kp.Wm, kp.Hm);
+        if (!t.valid) continue;
+        if ((t.ni + 1) * (t.nj + 1) > kBigTriPixels) {
+          int slot = atomicAdd(&s_cnt[warp], 1);
+          s_def[warp][slot].t = t;
+          s_def[warp][slot].e = e;
+        } else {
+          raster_lane(t, e, rt, kp.Wm);
+        }
+      }
+    }
   }
-  EmitCtx e;
-  e.W = kp.Wm;
-  e.H = kp.Hm;
-  e.lequal = lequal != 0;
-  e.key_a = is_old ? t.key_old : t.key_new;
-  e.key_b = t.key_new;
-  e.to_a = (is_old ? t.key_old : t.key_new) != nullptr;
-  e.to_b = is_old && is_new && t.key_new != nullptr;
-  e.low_a = e.low_b = (unsigned long long)k;
-  e.key_c = t.key_comp;
-  e.c_old = is_old && t.key_comp != nullptr;
-  e.c_new = is_new && t.key_comp != nullptr;
-  if (!lequal) {
-    e.low_c_old = (unsigned long long)k;                 // old pass is drawn first: wins depth ties
-    e.low_c_new = (1ull << 32) | (unsigned long long)k;
-  } else {                                               // GL_LEQUAL: the latest fragment wins depth ties
-    e.low_c_old = (1ull << 32) | (unsigned long long)(0xffffffffu - k);
-    e.low_c_new = (unsigned long long)(0xffffffffu - k);
-  }
-  raster_tri(e, q[0], q[1], q[2]);
-  raster_tri(e, q[1], q[2], q[3]);
+  __syncwarp();
+  const int nd = s_cnt[warp];
+  for (int d = 0; d < nd; ++d) raster_warp(s_def[warp][d].t, s_def[warp][d].e, rt, kp.Wm, lane);
 }
 
 void launch_render_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, const uint32_t* n_dev, uint32_t n_upper,
@@ -211,8 +310,8 @@ void launch_render_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, c
   if (n_upper == 0) return;
   {
     ScopedKernel sk(L, K_RENDER_SCATTER);
-    k_render_scatter<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr,
-                                                                                  emit_old, emit_new, lequal, t);
+    k_render_scatter<<<(n_upper + kRenderThreads - 1) / kRenderThreads, kRenderThreads, 0, L.stream>>>(
+        kp, s, n_dev, M, conf_thr, t_thr, emit_old, emit_new, lequal, t);
   }
 }
 
@@ -263,6 +362,16 @@ __global__ void __launch_bounds__(kThreads) k_render_resolve(KParams kp, SurfelP
     f_new.vertex[pix] = pn.v;
     f_new.normal[pix] = pn.n;
     if (!keep_semantic) f_new.semantic[pix] = pn.s;
+  }
+  if (f_comp.vertex && !t.key_comp && t.key_old && t.key_new) {
+    // GL_LESS, old pass drawn before the new pass on an uncleared buffer (SurfelMap.cpp:893-906): the winner of the
+    // union of both passes is the smaller of the two per-pass winners, depth first, then pass, then surfel index
+    unsigned long long ko = t.key_old[pix], kn = t.key_new[pix];
+    if (kn != ~0ull) kn |= (1ull << 32);
+    Px pc = resolve_px(s, ko < kn ? ko : kn, M_old, M_new, -1, 0);
+    f_comp.vertex[pix] = pc.v;
+    f_comp.normal[pix] = pc.n;
+    if (!keep_semantic) f_comp.semantic[pix] = pc.s;
   }
   if (t.key_comp) {
     Px pc = resolve_px(s, t.key_comp[pix], M_old, M_new, -1, lequal);
@@ -318,7 +427,8 @@ __global__ void __launch_bounds__(kThreads) k_index_scatter(KParams kp, SurfelPl
   uint32_t d24 = depth24(0.5f * zn + 0.5f);
   if (d24 >= kDepthClear) return;
   size_t pix = (size_t)(int)fy * kp.W + (size_t)(int)fx;
-  atomicMin(keys + pix, ((unsigned long long)d24 << 32) | (unsigned long long)k);
+  unsigned long long key = ((unsigned long long)d24 << 32) | (unsigned long long)k;
+  if (key < keys[pix]) atomicMin(keys + pix, key);
 }
 
 void launch_index_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, const uint32_t* n_dev, uint32_t n_upper,
@@ -387,6 +497,8 @@ __device__ __forceinline__ bool submap_keep(const float* __restrict__ poses, flo
 struct UpdateArgs {
   Mat4 pose;               // current sensor pose (by value: no upload on the critical path)
   Mat4 inv_pose;
+  const Mat4* pose_dev;    // or resident on the device (pipeline mode)
+  const Mat4* inv_pose_dev;
   const float* poses;      // pose table
   const float* poses_inv;  // inverse pose table
   const unsigned long long* index_keys;
@@ -413,8 +525,8 @@ __global__ void __launch_bounds__(kThreads) k_update_surfels(KParams kp, SurfelP
     int ci = pose_index(p2.w);
     float SP[16];
     load_mat(ua.poses, ci, SP);
-    const float* POSE = ua.pose.m;
-    const float* INV = ua.inv_pose.m;
+    const float* POSE = ua.pose_dev ? ua.pose_dev->m : ua.pose.m;
+    const float* INV = ua.inv_pose_dev ? ua.inv_pose_dev->m : ua.inv_pose.m;
     V3 old_position = xform_point(SP, mk3(p0.x, p0.y, p0.z));
     V3 old_normal = xform_dir(SP, mk3(p1.x, p1.y, p1.z));
     float old_radius = p0.w, old_conf = p1.w, old_weight = p2.z;
@@ -683,12 +795,14 @@ void launch_compact(const Launch& L, SurfelPlanes src, const uint8_t* keep, cons
 }
 
 void launch_update_surfels(const Launch& L, const KParams& kp, SurfelPlanes src, SurfelPlanes tmp, const uint32_t* n_dev,
-                           uint32_t n_upper, const Mat4& pose, const Mat4& inv_pose, const float* poses,
+                           uint32_t n_upper, const Mat4& pose, const Mat4& inv_pose, const Mat4* pose_dev,
+                           const Mat4* inv_pose_dev, const float* poses,
                            const float* poses_inv, const unsigned long long* index_keys, const float4* radius_map,
                            FrameDev frame, int timestamp, float2 submap_center, float submap_extent,
                            uint8_t* integrated, uint8_t* keep, uint32_t* block_counts) {
   if (n_upper == 0) return;
-  UpdateArgs ua{pose, inv_pose, poses, poses_inv, index_keys, radius_map, timestamp, submap_center, submap_extent};
+  UpdateArgs ua{pose, inv_pose, pose_dev, inv_pose_dev, poses, poses_inv, index_keys, radius_map, timestamp,
+                submap_center, submap_extent};
   {
     ScopedKernel sk(L, K_UPDATE_SURFELS);
     k_update_surfels<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, src, tmp, n_dev, ua, frame,
