@@ -180,59 +180,102 @@ __device__ __forceinline__ void tri_fragment(const TriSetup& t, const Emit& e, c
   }
 }
 
-// one lane walks its own (small) triangle: three 64-bit adds and sign tests per pixel
-__device__ __forceinline__ void raster_lane(const TriSetup& t, const Emit& e, const RenderTargets& rt, int W) {
-  long long rowA = t.eA, rowB = t.eB, rowC = t.eC;
-  const bool tieA = t.ties & 1u, tieB = t.ties & 2u, tieC = t.ties & 4u;
-  for (int dj = 0; dj <= t.nj; ++dj) {
-    long long wA = rowA, wB = rowB, wC = rowC;
-    for (int di = 0; di <= t.ni; ++di) {
-      bool in = (wA > 0 || (wA == 0 && tieA)) && (wB > 0 || (wB == 0 && tieB)) && (wC > 0 || (wC == 0 && tieC));
-      if (in) tri_fragment(t, e, rt, W, wB, wC, di, dj);
-      wA += t.sxA;
-      wB += t.sxB;
-      wC += t.sxC;
-    }
-    rowA += t.syA;
-    rowB += t.syB;
-    rowC += t.syC;
-  }
-}
-
-// the whole warp walks one (large) triangle: lane l takes pixels l, l+32, ... of the bounding box
-__device__ __forceinline__ void raster_warp(const TriSetup& t, const Emit& e, const RenderTargets& rt, int W, int lane) {
-  const int w = t.ni + 1, total = w * (t.nj + 1);
-  const bool tieA = t.ties & 1u, tieB = t.ties & 2u, tieC = t.ties & 4u;
-  for (int p = lane; p < total; p += 32) {
-    int dj = p / w, di = p - dj * w;
-    long long wA = t.eA + (long long)di * t.sxA + (long long)dj * t.syA;
-    long long wB = t.eB + (long long)di * t.sxB + (long long)dj * t.syB;
-    long long wC = t.eC + (long long)di * t.sxC + (long long)dj * t.syC;
-    bool in = (wA > 0 || (wA == 0 && tieA)) && (wB > 0 || (wB == 0 && tieB)) && (wC > 0 || (wC == 0 && tieC));
-    if (in) tri_fragment(t, e, rt, W, wB, wC, di, dj);
-  }
-}
-
 constexpr int kRenderThreads = 128;
-constexpr int kBigTriPixels = 96;  // bounding boxes larger than this are rasterised by the whole warp
+constexpr int kTrisPerWarp = 64;  // two triangles per surfel, 32 surfels per warp pass
 
-struct DeferredTri {
-  TriSetup t;
-  Emit e;
+// the triangles of one warp pass, structure-of-arrays in shared memory (lanes read different triangles: an array per
+// field keeps those reads spread over the banks)
+struct WarpTris {
+  long long e[3][kTrisPerWarp], sx[3][kTrisPerWarp], sy[3][kTrisPerWarp];
+  float farea[kTrisPerWarp], z[3][kTrisPerWarp], tx[3][kTrisPerWarp], ty[3][kTrisPerWarp];
+  int i0[kTrisPerWarp], j0[kTrisPerWarp], ni[kTrisPerWarp], nj[kTrisPerWarp];
+  uint32_t ties[kTrisPerWarp], k[kTrisPerWarp], flags[kTrisPerWarp];
+  int prefix[kTrisPerWarp + 1];  // exclusive prefix sums of the bounding-box pixel counts
 };
 
-// render_surfels.vert:42-54 + .geom:76-122 for every surfel of the map. One lane per surfel for the transform,
-// visibility tests and corner projection; small quads are rasterised by their own lane, the heavy tail (surfels
-// created far away and seen from close by cover hundreds of pixels) is parked in shared memory and rasterised by
-// the whole warp, which keeps the lanes of a warp busy.
+__device__ __forceinline__ void tris_store(WarpTris& w, int slot, const TriSetup& t, const Emit& e) {
+  w.e[0][slot] = t.eA; w.e[1][slot] = t.eB; w.e[2][slot] = t.eC;
+  w.sx[0][slot] = t.sxA; w.sx[1][slot] = t.sxB; w.sx[2][slot] = t.sxC;
+  w.sy[0][slot] = t.syA; w.sy[1][slot] = t.syB; w.sy[2][slot] = t.syC;
+  w.farea[slot] = t.farea;
+  w.z[0][slot] = t.zA; w.z[1][slot] = t.zB; w.z[2][slot] = t.zC;
+  w.tx[0][slot] = t.txA; w.tx[1][slot] = t.txB; w.tx[2][slot] = t.txC;
+  w.ty[0][slot] = t.tyA; w.ty[1][slot] = t.tyB; w.ty[2][slot] = t.tyC;
+  w.i0[slot] = t.i0; w.j0[slot] = t.j0; w.ni[slot] = t.ni; w.nj[slot] = t.nj;
+  w.ties[slot] = t.ties; w.k[slot] = e.k; w.flags[slot] = e.flags;
+  w.prefix[slot + 1] = (t.ni + 1) * (t.nj + 1);
+}
+__device__ __forceinline__ void tris_load(const WarpTris& w, int slot, TriSetup& t, Emit& e) {
+  t.eA = w.e[0][slot]; t.eB = w.e[1][slot]; t.eC = w.e[2][slot];
+  t.sxA = w.sx[0][slot]; t.sxB = w.sx[1][slot]; t.sxC = w.sx[2][slot];
+  t.syA = w.sy[0][slot]; t.syB = w.sy[1][slot]; t.syC = w.sy[2][slot];
+  t.farea = w.farea[slot];
+  t.zA = w.z[0][slot]; t.zB = w.z[1][slot]; t.zC = w.z[2][slot];
+  t.txA = w.tx[0][slot]; t.txB = w.tx[1][slot]; t.txC = w.tx[2][slot];
+  t.tyA = w.ty[0][slot]; t.tyB = w.ty[1][slot]; t.tyC = w.ty[2][slot];
+  t.i0 = w.i0[slot]; t.j0 = w.j0[slot]; t.ni = w.ni[slot]; t.nj = w.nj[slot];
+  t.ties = w.ties[slot]; t.valid = 1;
+  e.k = w.k[slot]; e.flags = w.flags[slot];
+}
+
+// Balanced rasterisation of all triangles of the warp pass: the bounding-box pixels of all triangles form one
+// flattened list of T items, lane l walks items [l*ch, (l+1)*ch). Quads differ by two orders of magnitude in size
+// (a surfel created far away and seen from close by covers hundreds of pixels); with one lane per quad the warp runs
+// as long as its largest quad while most lanes idle. Edge functions stay exact: incremental int64 adds inside a row,
+// re-based at every row / triangle change.
+__device__ __forceinline__ void raster_balanced(const WarpTris& w, int ntris, int total, const RenderTargets& rt, int W,
+                                                int lane) {
+  const int ch = (total + 31) >> 5;
+  int item = lane * ch;
+  const int end = min(item + ch, total);
+  if (item >= end) return;
+  int lo = 0, hi = ntris;  // largest j with prefix[j] <= item
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (w.prefix[mid] <= item) lo = mid; else hi = mid;
+  }
+  int j = lo;
+  while (item < end) {
+    TriSetup t;
+    Emit e;
+    tris_load(w, j, t, e);
+    const int first = w.prefix[j], cnt = w.prefix[j + 1] - first;
+    const int local = item - first;
+    const int wd = t.ni + 1;
+    int dj = local / wd, di = local - dj * wd;
+    int n_here = min(end - item, cnt - local);
+    const bool tieA = t.ties & 1u, tieB = t.ties & 2u, tieC = t.ties & 4u;
+    long long rowA = t.eA + (long long)dj * t.syA, rowB = t.eB + (long long)dj * t.syB, rowC = t.eC + (long long)dj * t.syC;
+    long long wA = rowA + (long long)di * t.sxA, wB = rowB + (long long)di * t.sxB, wC = rowC + (long long)di * t.sxC;
+    for (int q = 0; q < n_here; ++q) {
+      bool in = (wA > 0 || (wA == 0 && tieA)) && (wB > 0 || (wB == 0 && tieB)) && (wC > 0 || (wC == 0 && tieC));
+      if (in) tri_fragment(t, e, rt, W, wB, wC, di, dj);
+      if (++di > t.ni) {
+        di = 0;
+        ++dj;
+        rowA += t.syA; rowB += t.syB; rowC += t.syC;
+        wA = rowA; wB = rowB; wC = rowC;
+      } else {
+        wA += t.sxA; wB += t.sxB; wC += t.sxC;
+      }
+    }
+    item += n_here;
+    ++j;
+  }
+}
+
+// render_surfels.vert:42-54 + .geom:76-122 for every surfel of the map. One lane per surfel for the transform, the
+// visibility tests, the corner projection and the triangle setup; the rasterisation of the warp's triangles is then
+// shared evenly by its 32 lanes (raster_balanced).
 __global__ void __launch_bounds__(kRenderThreads) k_render_scatter(KParams kp, SurfelPlanes s, const uint32_t* __restrict__ n_dev,
                                                                    const float* __restrict__ Mtab, float conf_thr, int t_thr,
                                                                    int emit_old, int emit_new, int lequal, RenderTargets rt) {
-  __shared__ DeferredTri s_def[kRenderThreads / 32][64];
-  __shared__ int s_cnt[kRenderThreads / 32];
+  __shared__ WarpTris s_tris[kRenderThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) s_cnt[warp] = 0;
-  __syncwarp();
+  WarpTris& wt = s_tris[warp];
+  wt.prefix[2 * lane + 1] = 0;
+  wt.prefix[2 * lane + 2] = 0;
+  if (lane == 0) wt.prefix[0] = 0;
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   bool alive = k < *n_dev;
   float4 p0, p1, p2;
@@ -248,6 +291,8 @@ __global__ void __launch_bounds__(kRenderThreads) k_render_scatter(KParams kp, S
     is_new = emit_new && (creation >= t_thr || ts >= t_thr);  // .geom:91
     alive = is_old || is_new;
   }
+  TriSetup t0, t1;
+  t0.valid = t1.valid = 0;
   if (alive) {
     p0 = __ldg(s.p0 + k);
     float M[16];
@@ -282,26 +327,44 @@ __global__ void __launch_bounds__(kRenderThreads) k_render_scatter(KParams kp, S
         q[i].tx = (i & 1) ? 1.0f : -1.0f;
         q[i].ty = (i & 2) ? 1.0f : -1.0f;
       }
-      Emit e;
-      e.k = k;
-      e.flags = (is_old ? 1u : 0u) | (is_new ? 2u : 0u) | (lequal ? 4u : 0u);
-#pragma unroll
-      for (int tri = 0; tri < 2; ++tri) {
-        TriSetup t = tri == 0 ? tri_prepare(q[0], q[1], q[2], kp.Wm, kp.Hm) : tri_prepare(q[1], q[2], q[3], kp.Wm, kp.Hm);
-        if (!t.valid) continue;
-        if ((t.ni + 1) * (t.nj + 1) > kBigTriPixels) {
-          int slot = atomicAdd(&s_cnt[warp], 1);
-          s_def[warp][slot].t = t;
-          s_def[warp][slot].e = e;
-        } else {
-          raster_lane(t, e, rt, kp.Wm);
-        }
-      }
+      t0 = tri_prepare(q[0], q[1], q[2], kp.Wm, kp.Hm);
+      t1 = tri_prepare(q[1], q[2], q[3], kp.Wm, kp.Hm);
     }
   }
+  // slots of this lane's triangles: exclusive prefix of the per-lane triangle counts
+  const int cnt = (int)t0.valid + (int)t1.valid;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int ntris = __shfl_sync(0xffffffffu, incl, 31);
+  if (ntris == 0) return;
   __syncwarp();
-  const int nd = s_cnt[warp];
-  for (int d = 0; d < nd; ++d) raster_warp(s_def[warp][d].t, s_def[warp][d].e, rt, kp.Wm, lane);
+  if (cnt) {
+    Emit e;
+    e.k = k;
+    e.flags = (is_old ? 1u : 0u) | (is_new ? 2u : 0u) | (lequal ? 4u : 0u);
+    int slot = incl - cnt;
+    if (t0.valid) tris_store(wt, slot++, t0, e);
+    if (t1.valid) tris_store(wt, slot, t1, e);
+  }
+  __syncwarp();
+  // prefix sums of the pixel counts (pairs of adjacent slots per lane)
+  int a = wt.prefix[2 * lane + 1], b = wt.prefix[2 * lane + 2];
+  int sum = a + b, isum = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, isum, o);
+    if (lane >= o) isum += v;
+  }
+  const int total = __shfl_sync(0xffffffffu, isum, 31);
+  __syncwarp();
+  wt.prefix[2 * lane + 1] = isum - sum + a;
+  wt.prefix[2 * lane + 2] = isum;
+  __syncwarp();
+  raster_balanced(wt, ntris, total, rt, kp.Wm, lane);
 }
 
 void launch_render_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, const uint32_t* n_dev, uint32_t n_upper,
