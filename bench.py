@@ -64,36 +64,61 @@ def generate_scans(w, n_frames, seed):
 
 
 class ClockSampler(threading.Thread):
-    """samples nvidia-smi during the timed region (B200_PROFILING.md, clocks line)"""
+    """samples SM clock / power / throttle reasons during the timed region (B200_PROFILING.md, clocks line).
+    Uses NVML in-process (nvidia_ml_py): spawning nvidia-smi every 100 ms perturbs a 50 ms timed region."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        except Exception:  # noqa: BLE001
+            self.nvml = None
 
-    def run(self):
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:  # noqa: BLE001
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        flags = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+        return [sm, mx, pw] + [bool(r & v) for v in (flags["hw_slowdown"], flags["hw_thermal_slowdown"],
+                                                     flags["sw_thermal_slowdown"], flags["sw_power_cap"])]
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(",")]
+        return [float(f[0]), float(f[1]), float(f[2])] + [x.lower().startswith("active") for x in f[3:7]]
+
+    def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 7:
-                    self.samples.append(f)
+                self.samples.append(self._sample_nvml() if self.nvml else self._sample_smi())
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.1)
+            time.sleep(0.005 if self.nvml else 0.2)
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"]}
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i] for s in self.samples)]
+        return {"sm_mhz": statistics.median(s[0] for s in self.samples), "sm_max_mhz": max(s[1] for s in self.samples),
+                "power_w_max": round(max(s[2] for s in self.samples), 1), "reasons": reasons,
+                "samples": len(self.samples), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def algorithmic_bytes(kernel, P, S, N, semantic):
@@ -237,6 +262,8 @@ def run_native(args, w, rank, world, local_rank):
                        "icp_iterations": w["iters"], "semantic": sem, "sequences": world,
                        "surfels_end": int(surfels), "pose_drift_m": round(drift, 4),
                        "l2": "flushed between timed steps (256 MiB memset, untimed)",
+                       "step_ms_min_med_max": [round(min(per_step), 4), round(statistics.median(per_step), 4),
+                                               round(max(per_step), 4)],
                        "timing": "CUDA events on the library's stream around every step, summed; max over ranks",
                        "reference_defaults": "config/default.xml except image size, max iterations, eps=delta=0"},
             "e2e": {"value": round(e2e_value, 2), "unit": "scans/s", "ms_per_step": round(ms_e2e / args.steps, 4),

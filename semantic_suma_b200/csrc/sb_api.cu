@@ -62,6 +62,9 @@ struct sb_ctx {
   uint8_t* keep = nullptr;
   uint32_t* block_counts = nullptr;
   uint32_t* block_offsets = nullptr;
+  unsigned long long* lb_desc = nullptr;  // look-back descriptors of the single-pass compactions
+  uint32_t* lb_ticket = nullptr;
+  uint32_t lb_gen = 0;
   uint32_t* d_counts = nullptr;  // [0] n surfels, [1] n after update (base for new), [2] kept updated, [3] kept new, [4] extracted
   float* poses = nullptr;        // device pose table, kMaxPoses x 16
   float* poses_inv = nullptr;
@@ -222,6 +225,7 @@ int release_buffers(sb_ctx* c) {
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   free_planes(&c->A); free_planes(&c->T); free_planes(&c->G); free_planes(&c->X);
   cudaFree(c->keep); cudaFree(c->block_counts); cudaFree(c->block_offsets); cudaFree(c->d_counts);
+  cudaFree(c->lb_desc); cudaFree(c->lb_ticket);
   cudaFree(c->poses); cudaFree(c->poses_inv); cudaFree(c->Mtab_old); cudaFree(c->Mtab_new);
   cudaFree(c->key_old); cudaFree(c->key_index); cudaFree(c->radius_map); cudaFree(c->integrated);
   sb_frame* fr[] = {c->f_old, c->f_new, c->f_comp, c->cur, c->last, c->cur_model, c->last_model};
@@ -298,10 +302,14 @@ int alloc_buffers(sb_ctx* c) {
   if ((r = alloc_planes(c, &c->G, Pd))) return r;
   if ((r = alloc_planes(c, &c->X, kExtractCap))) return r;
   SB_CUDA(c, cudaMalloc(&c->keep, kMaxSurfels));
-  size_t nb = (kMaxSurfels + 255) / 256 + 16;
+  size_t nb = (kMaxSurfels + 127) / 128 + 16;  // blocks of the finest-grained surfel kernel
   SB_CUDA(c, cudaMalloc(&c->block_counts, nb * 4));
   SB_CUDA(c, cudaMalloc(&c->block_offsets, nb * 4));
   SB_CUDA(c, cudaMalloc(&c->d_counts, 16 * sizeof(uint32_t)));
+  SB_CUDA(c, cudaMalloc(&c->lb_desc, (nb + 16) * 8));
+  SB_CUDA(c, cudaMemsetAsync(c->lb_desc, 0, (nb + 16) * 8, c->stream));
+  SB_CUDA(c, cudaMalloc(&c->lb_ticket, 64));
+  SB_CUDA(c, cudaMemsetAsync(c->lb_ticket, 0, 64, c->stream));
   SB_CUDA(c, cudaMalloc(&c->poses, (size_t)kMaxPoses * 64));
   SB_CUDA(c, cudaMalloc(&c->poses_inv, (size_t)kMaxPoses * 64));
   SB_CUDA(c, cudaMalloc(&c->Mtab_old, (size_t)kMaxPoses * 64));
@@ -309,6 +317,8 @@ int alloc_buffers(sb_ctx* c) {
   SB_CUDA(c, cudaMalloc(&c->key_old, Pm * 8 * 3));
   c->key_new = c->key_old + Pm;
   c->key_comp = c->key_old + 2 * Pm;
+  SB_CUDA(c, cudaMemsetAsync(c->key_old, 0xff, Pm * 8 * 3, c->stream));
+  SB_CUDA(c, cudaMemsetAsync(c->keys_data, 0xff, Pd * 8, c->stream));
   SB_CUDA(c, cudaMalloc(&c->key_index, Pd * 8));
   SB_CUDA(c, cudaMalloc(&c->radius_map, Pd * 16));
   SB_CUDA(c, cudaMalloc(&c->integrated, Pd));
@@ -356,7 +366,7 @@ FrameDev null_frame() {
 }
 
 int render_full(sb_ctx* c, const float* pose_old, const float* pose_new, float conf_thr, sb_frame* out,
-                const Mat4* inv_dev = nullptr) {
+                const Mat4* inv_dev = nullptr, bool table_ready = false) {
   if (!inv_dev && c->rkey_valid && c->rkey.out == out && c->rkey.map_version == c->map_version &&
       c->rkey.map_timestamp == c->map_timestamp && c->rkey.compose == c->p.compose_rendering &&
       memcmp(&c->rkey.conf_thr, &conf_thr, 4) == 0 && memcmp(c->rkey.pose_old, pose_old, 64) == 0 &&
@@ -374,7 +384,8 @@ int render_full(sb_ctx* c, const float* pose_old, const float* pose_new, float c
   }
   const bool same = inv_dev != nullptr || memcmp(pose_old, pose_new, 64) == 0;
   uint32_t np = pose_table_count(c);
-  launch_pose_products(L, mat4_from(inv_old), inv_dev, c->poses, c->Mtab_old, np);
+  // table_ready: Mtab_old already holds inv(pose) * poseTable from the map update of this scan (same pose)
+  if (!table_ready) launch_pose_products(L, mat4_from(inv_old), inv_dev, c->poses, c->Mtab_old, np);
   float* Mnew = c->Mtab_old;
   if (!same) {
     launch_pose_products(L, mat4_from(inv_new), nullptr, c->poses, c->Mtab_new, np);
@@ -382,7 +393,7 @@ int render_full(sb_ctx* c, const float* pose_old, const float* pose_new, float c
   }
   if (c->p.compose_rendering) {
     // the composed view needs no atomics of its own: it is derived from the old / new key images in the resolve pass
-    launch_fill_u64(L, c->key_old, ~0ull, Pm * 2);
+    // (key images are cleared by the resolve pass that consumes them)
     RenderTargets t{c->key_old, c->key_new, nullptr};
     int thr = t_threshold(c);
     if (same) {
@@ -395,7 +406,6 @@ int render_full(sb_ctx* c, const float* pose_old, const float* pose_new, float c
     launch_render_resolve(L, kp, c->A, c->Mtab_old, Mnew, t, c->f_old->d, c->f_new->d, c->f_comp->d, out->d, 0, 0);
   } else {
     // SurfelMap.cpp:977-1017: one view with render_old_surfels = false, timestamp_threshold = 0, copied to old and new
-    launch_fill_u64(L, c->key_new, ~0ull, Pm);
     RenderTargets t{nullptr, c->key_new, nullptr};
     launch_render_scatter(L, kp, c->A, c->d_counts, n_grid(c), c->Mtab_old, conf_thr, 0, 0, 1, 0, t);
     launch_render_resolve(L, kp, c->A, c->Mtab_old, c->Mtab_old, t, null_frame(), c->f_new->d, null_frame(), null_frame(),
@@ -428,7 +438,6 @@ int render_single(sb_ctx* c, const float* pose, float conf_thr, int which, const
   if (pose) sbg::rigid_inverse_f(pose, inv);
   launch_pose_products(L, mat4_from(inv), inv_dev, c->poses, c->Mtab_old, pose_table_count(c));
   unsigned long long* key = which ? c->key_new : c->key_old;
-  launch_fill_u64(L, key, ~0ull, Pm);
   RenderTargets t{which ? nullptr : key, which ? key : nullptr, nullptr};
   launch_render_scatter(L, kp, c->A, c->d_counts, n_grid(c), c->Mtab_old, conf_thr, t_threshold(c), which ? 0 : 1,
                         which ? 1 : 0, 0, t);
@@ -644,17 +653,19 @@ int map_update(sb_ctx* c, const float* pose, const sb_frame* frame, const Mat4* 
   float2 ctr = submap_center(c, c->origin_i, c->origin_j);
   float extent = 2.0f * c->p.submap_dimension * c->p.submap_extent + c->p.submap_extent;  // :674
   if (c->p.partial_extraction && !c->extraction.empty()) extent += 2.0f * c->p.submap_extent;  // :677
+  // K6c + K6e predicate, then ordered compaction back into the map lanes: counts[1] = S', counts[2] = kept.
+  // (A single-pass variant with decoupled look-back exists -- k_update_compact -- but loses here: the blocks of a wave
+  // finish their heavy per-surfel work together and then resolve their offsets through a ~1000-block look-back chain.)
   launch_update_surfels(L, kp, c->A, c->T, c->d_counts, n_grid(c), mat4_from(pose_h), mat4_from(inv_pose), pose_dev,
                         inv_dev, c->poses, c->poses_inv, c->key_index, c->radius_map, frame->d, (int)c->map_timestamp,
                         ctr, extent, c->integrated, c->keep, c->block_counts);
-  // ordered compaction of the kept updated surfels back into the map: d_counts[1] = S'
   launch_compact(L, c->T, c->keep, c->block_counts, c->block_offsets, c->d_counts, n_grid(c), c->A, nullptr, kMaxSurfels,
                  c->d_counts + 1, c->d_counts + 2);
-  // K6d + K6e predicate, appended behind the updated surfels
-  launch_gen_surfels(L, kp, frame->d, c->radius_map, c->integrated, c->poses, (int)c->map_timestamp, ctr, extent, c->G,
-                     c->keep, c->block_counts);
-  launch_compact(L, c->G, c->keep, c->block_counts, c->block_offsets, nullptr, (uint32_t)Pd, c->A, c->d_counts + 1,
-                 kMaxSurfels, c->d_counts, c->d_counts + 3);
+  // K6d + K6e: new surfels appended behind the updated ones; counts[0] = new map size, counts[3] = new surfels
+  c->lb_gen = (c->lb_gen + 1) & 0x3fffffffu;
+  if (c->lb_gen == 0) c->lb_gen = 1;
+  launch_gen_compact(L, kp, frame->d, c->radius_map, c->integrated, c->poses, (int)c->map_timestamp, ctr, extent, c->A,
+                     c->lb_desc, c->lb_ticket, c->lb_gen, kMaxSurfels, c->d_counts);
   uint64_t up = (uint64_t)n_grid(c) + Pd;  // the map can grow by at most one surfel per pixel
   c->n_upper = up > kMaxSurfels ? kMaxSurfels : (uint32_t)up;
   if (deferred) {
@@ -985,7 +996,6 @@ int sb_map_render_composed(sb_ctx* c, const float pose_old[16], const float pose
   uint32_t np = pose_table_count(c);
   launch_pose_products(L, mat4_from(inv_old), nullptr, c->poses, c->Mtab_old, np);
   launch_pose_products(L, mat4_from(inv_new), nullptr, c->poses, c->Mtab_new, np);
-  launch_fill_u64(L, c->key_comp, ~0ull, Pm);
   RenderTargets t{nullptr, nullptr, c->key_comp};
   int thr = t_threshold(c);
   // GL_LEQUAL (SurfelMap.cpp:1126), old then new without clearing (:1146-1152); COLOR2 not attached (Q4)
@@ -1189,7 +1199,7 @@ int sb_process_scan(sb_ctx* c, const float* pts4, const float* labels, const flo
   if ((r = map_update(c, nullptr, c->cur, &c->pd->P_cur, &c->pd->invP_cur))) return r;
   float ct2 = conf_threshold(c);
   if (p.render_after_update) {
-    if ((r = render_full(c, nullptr, nullptr, ct2, c->cur_model, &c->pd->invP_cur))) return r;
+    if ((r = render_full(c, nullptr, nullptr, ct2, c->cur_model, &c->pd->invP_cur, true))) return r;
   }
   // ---- the scan's results: pose block, statistics sums, surfel counts ----
   char* hp = (char*)c->h_pinned;

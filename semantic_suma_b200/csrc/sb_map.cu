@@ -413,15 +413,21 @@ __global__ void __launch_bounds__(kThreads) k_render_resolve(KParams kp, SurfelP
                                                             FrameDev f_out, int keep_semantic, int lequal) {
   int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= kp.Wm * kp.Hm) return;
+  // every key image that is read here is cleared again ("consume and clear"): no separate fill before the next view
   Px po, pn;
+  unsigned long long ko_raw = ~0ull, kn_raw = ~0ull;
   if (t.key_old) {
-    po = resolve_px(s, t.key_old[pix], M_old, M_new, 0, 0);
+    ko_raw = t.key_old[pix];
+    t.key_old[pix] = ~0ull;
+    po = resolve_px(s, ko_raw, M_old, M_new, 0, 0);
     f_old.vertex[pix] = po.v;
     f_old.normal[pix] = po.n;
     if (!keep_semantic) f_old.semantic[pix] = po.s;
   }
   if (t.key_new) {
-    pn = resolve_px(s, t.key_new[pix], M_old, M_new, 1, 0);
+    kn_raw = t.key_new[pix];
+    t.key_new[pix] = ~0ull;
+    pn = resolve_px(s, kn_raw, M_old, M_new, 1, 0);
     f_new.vertex[pix] = pn.v;
     f_new.normal[pix] = pn.n;
     if (!keep_semantic) f_new.semantic[pix] = pn.s;
@@ -429,7 +435,7 @@ __global__ void __launch_bounds__(kThreads) k_render_resolve(KParams kp, SurfelP
   if (f_comp.vertex && !t.key_comp && t.key_old && t.key_new) {
     // GL_LESS, old pass drawn before the new pass on an uncleared buffer (SurfelMap.cpp:893-906): the winner of the
     // union of both passes is the smaller of the two per-pass winners, depth first, then pass, then surfel index
-    unsigned long long ko = t.key_old[pix], kn = t.key_new[pix];
+    unsigned long long ko = ko_raw, kn = kn_raw;
     if (kn != ~0ull) kn |= (1ull << 32);
     Px pc = resolve_px(s, ko < kn ? ko : kn, M_old, M_new, -1, 0);
     f_comp.vertex[pix] = pc.v;
@@ -437,7 +443,9 @@ __global__ void __launch_bounds__(kThreads) k_render_resolve(KParams kp, SurfelP
     if (!keep_semantic) f_comp.semantic[pix] = pc.s;
   }
   if (t.key_comp) {
-    Px pc = resolve_px(s, t.key_comp[pix], M_old, M_new, -1, lequal);
+    unsigned long long kc = t.key_comp[pix];
+    t.key_comp[pix] = ~0ull;
+    Px pc = resolve_px(s, kc, M_old, M_new, -1, lequal);
     f_comp.vertex[pix] = pc.v;
     f_comp.normal[pix] = pc.n;
     if (!keep_semantic) f_comp.semantic[pix] = pc.s;
@@ -530,6 +538,95 @@ void launch_radius(const Launch& L, const KParams& kp, FrameDev frame, float4* r
     ScopedKernel sk(L, K_RADIUS);
     k_radius<<<(P + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, frame, radius_map);
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Single-pass ordered compaction (transform-feedback semantics) with decoupled look-back: every block publishes the
+// number of items it keeps, obtains the number kept by all earlier blocks by walking back over the published
+// descriptors, and writes its items to their final position -- one read and one write per surfel, no flag / count /
+// scan passes. Blocks take their (virtual) index from a ticket so that earlier indices are always already running.
+// Descriptor: [63:34] launch generation, [33:32] status (0 none, 1 block aggregate, 2 inclusive prefix), [31:0] value.
+// ------------------------------------------------------------------------------------------------------------
+struct Lookback {
+  unsigned long long* desc;
+  uint32_t* ticket;
+  uint32_t gen;
+};
+__device__ __forceinline__ unsigned long long lb_pack(uint32_t gen, uint32_t status, uint32_t value) {
+  return ((unsigned long long)gen << 34) | ((unsigned long long)status << 32) | (unsigned long long)value;
+}
+
+__device__ __forceinline__ uint32_t block_ticket(const Lookback& lb) {
+  __shared__ uint32_t s_vb;
+  if (threadIdx.x == 0) s_vb = atomicAdd(lb.ticket, 1u);
+  __syncthreads();
+  return s_vb;
+}
+
+// rank of this thread's item among the kept items of the block, and the block's count
+template <int THREADS>
+__device__ __forceinline__ uint32_t block_rank(bool kept, uint32_t& block_count) {
+  __shared__ uint32_t s_warp[THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned m = __ballot_sync(0xffffffffu, kept);
+  if (lane == 0) s_warp[warp] = __popc(m);
+  __syncthreads();
+  uint32_t before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < THREADS / 32; ++w) {
+    uint32_t v = s_warp[w];
+    if (w < warp) before += v;
+    total += v;
+  }
+  block_count = total;
+  return before + __popc(m & ((1u << lane) - 1u));
+}
+
+// exclusive prefix of `count` over the blocks with a smaller virtual index (warp 0 walks back 32 descriptors at a time)
+__device__ __forceinline__ uint32_t lookback_exclusive(const Lookback& lb, uint32_t vb, uint32_t count) {
+  __shared__ uint32_t s_excl;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    if (vb == 0) {
+      if (lane == 0) {
+        s_excl = 0;
+        atomicExch(lb.desc + 0, lb_pack(lb.gen, 2u, count));
+      }
+    } else {
+      if (lane == 0) atomicExch(lb.desc + vb, lb_pack(lb.gen, 1u, count));
+      uint32_t sum = 0;
+      long long base = (long long)vb - 1;
+      for (;;) {
+        long long idx = base - lane;
+        uint32_t status = 2u, value = 0;  // virtual entries before block 0: prefix 0
+        if (idx >= 0) {
+          unsigned long long d;
+          for (;;) {
+            d = *(volatile unsigned long long*)(lb.desc + idx);
+            if ((uint32_t)(d >> 34) == lb.gen && ((d >> 32) & 3ull) != 0ull) break;
+            __nanosleep(200);  // polling from ~1000 resident blocks would otherwise eat a large share of L2 bandwidth
+          }
+          status = (uint32_t)((d >> 32) & 3ull);
+          value = (uint32_t)d;
+        }
+        unsigned pm = __ballot_sync(0xffffffffu, status == 2u);
+        int first = pm ? (__ffs(pm) - 1) : 32;  // closest inclusive prefix in this window
+        uint32_t contrib = (lane <= first) ? value : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        sum += contrib;
+        if (pm) break;
+        base -= 32;
+      }
+      if (lane == 0) {
+        s_excl = sum;
+        __threadfence();
+        atomicExch(lb.desc + vb, lb_pack(lb.gen, 2u, sum + count));
+      }
+    }
+  }
+  __syncthreads();
+  return s_excl;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -706,6 +803,158 @@ __global__ void __launch_bounds__(kThreads) k_update_surfels(KParams kp, SurfelP
   if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)cnt;
 }
 
+// K6c + K6e in ONE pass: update every surfel, decide keep / kill / outside-the-submap, and write the survivors in order
+// to the front of the SAME lanes (in-place: a block learns its output offset only after every earlier block has read
+// its input; later blocks read behind everything this block writes).
+constexpr int kUpdThreads = 128;  // small blocks: a block holds its SM slot while it waits for its output offset
+__global__ void __launch_bounds__(kUpdThreads) k_update_compact(KParams kp, SurfelPlanes src, const uint32_t* __restrict__ n_dev,
+                                                            UpdateArgs ua, FrameDev f, uint8_t* __restrict__ integrated,
+                                                            Lookback lb, uint32_t cap, uint32_t* __restrict__ counts) {
+  const uint32_t vb = block_ticket(lb);
+  uint32_t k = vb * blockDim.x + threadIdx.x;
+  bool kept = false;
+  float4 o0, o1, o2, o3;
+  o0 = o1 = o2 = o3 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (k < *n_dev) {
+    const int W = kp.W, H = kp.H;
+    // plain (coherent) loads: the same lanes are written in place by later blocks of this kernel
+    float4 p0 = src.p0[k], p1 = src.p1[k], p2 = src.p2[k], p3 = src.p3[k];
+    const int timestamp = ua.timestamp;
+    int s_ts = (int)__float_as_uint(p2.x);
+    int surfel_age = timestamp - s_ts;
+    int creation = (int)p2.w;
+    int ci = pose_index(p2.w);
+    float SP[16];
+    load_mat(ua.poses, ci, SP);
+    const float* POSE = ua.pose_dev ? ua.pose_dev->m : ua.pose.m;
+    const float* INV = ua.inv_pose_dev ? ua.inv_pose_dev->m : ua.inv_pose.m;
+    V3 old_position = xform_point(SP, mk3(p0.x, p0.y, p0.z));
+    V3 old_normal = xform_dir(SP, mk3(p1.x, p1.y, p1.z));
+    float old_radius = p0.w, old_conf = p1.w, old_weight = p2.z;
+    bool valid_out = true;
+    if (old_conf < kp.confidence_threshold && kp.use_stability) valid_out = surfel_age < kp.unstable_age;
+    o0 = p0; o1 = p1; o2 = p2; o3 = p3;
+    o2.y = pack_rgb(0.3f, 0.3f, 0.3f);
+    V3 vertex = xform_point(INV, old_position);
+    V3 normal = normalize3(xform_dir(INV, old_normal));
+    bool visible = dot3(normal, divs3(neg3(vertex), len3(vertex))) > 0.0f;
+    float x, y, z;
+    project01(vertex, kp.fov_up, kp.fov, kp.min_depth, kp.max_depth, x, y, z);
+    float ix = floorf(x * (float)W) + 0.5f, iy = floorf(y * (float)H) + 0.5f;
+    float4 Vt = data_tex(f.vertex, W, H, ix, iy);
+    float4 Nt = data_tex(f.normal, W, H, ix, iy);
+    bool valid = (Vt.w > 0.5f) && (Nt.w > 0.5f);
+    bool inside = (ix < (float)W && iy < (float)H && z < 1.0f) && !(ix < 0.0f && iy < 0.0f && z < 0.0f);
+    float penalty = 0.0f;
+    float update_conf = kp.log_prior;
+    if (valid && inside && visible) {
+      float4 St = data_tex(f.semantic, W, H, ix, iy);
+      float4 Rt = data_tex(ua.radius_map, W, H, ix, iy);
+      float data_label = St.x * 255.0f, data_prob = St.w;
+      float model_label = p3.x * 255.0f, model_prob = p3.w;
+      bool label_diff = roundf_(data_label) != roundf_(model_label);
+      if (label_diff && is_movable(model_label)) penalty = 1.0f;
+      V3 v = mk3(Vt.x, Vt.y, Vt.z), n = mk3(Nt.x, Nt.y, Nt.z);
+      V3 v_global = xform_point(POSE, v);
+      V3 n_global = normalize3(xform_dir(POSE, n));
+      V3 view_dir = divs3(neg3(v), len3(v));
+      float distance = fabsf(dot3(old_normal, sub3(v_global, old_position)));
+      float angle = len3(cross3(n_global, old_normal));
+      float new_radius = Rt.x, new_conf = Rt.y;
+      size_t dpix = (size_t)(int)iy * W + (size_t)(int)ix;
+      if (distance < kp.map_max_distance && angle < kp.update_angle_thresh) {
+        float zn = 2.0f * z - 1.0f;
+        if (zn >= -1.0f && zn <= 1.0f && depth24(0.5f * zn + 0.5f) < kDepthClear) integrated[dpix] = 1;
+        float confidence = old_conf + new_conf;
+        o1.w = confidence;
+        o2.x = __uint_as_float((uint32_t)timestamp);
+        float avg_radius = new_radius < old_radius ? new_radius : old_radius;
+        avg_radius = avg_radius > 0.0f ? avg_radius : 0.0f;  // update program's min_radius uniform is 0 (SurfelMap.cpp:422)
+        o0.w = avg_radius;
+        valid_out = true;
+        o2.y = pack_rgb(0.0f, 0.7f, 0.0f);
+        o2.w = (float)creation;
+        float a = angle, d = distance;
+        float pr = kp.p_stable;
+        if (kp.confidence_mode == 1 || kp.confidence_mode == 3)
+          pr = pr * expf_(((-a) * a) / (kp.sigma_angle * kp.sigma_angle));
+        if (kp.confidence_mode == 2 || kp.confidence_mode == 3)
+          pr = pr * expf_(((-d) * d) / (kp.sigma_distance * kp.sigma_distance));
+        pr = pr > kp.p_unstable ? pr : kp.p_unstable;
+        pr = pr < 1.0f ? pr : 1.0f;
+        update_conf = logf_(pr / (1.0f - pr));
+        if ((new_radius < old_radius && timestamp - creation < kp.active_timestamps) || kp.update_always) {
+          float w1 = 0.9f, w2 = 0.1f;
+          if (kp.weighting_scheme > 0) {
+            w1 = old_weight;
+            w2 = 1.0f;
+            if (kp.weighting_scheme == 2) w2 = dot3(n, view_dir);
+            float sw = w1 + w2;
+            o2.z = kp.max_weight < sw ? kp.max_weight : sw;
+            float sum = w1 + w2;
+            w1 = w1 / sum;
+            w2 = w2 / sum;
+          }
+          V3 avg_position = add3(scale3(w1, old_position), scale3(w2, v_global));
+          V3 avg_normal = slerp(old_normal, n_global, w1);
+          float avg_prob;
+          if (label_diff)
+            avg_prob = w1 * model_prob + w2 * (1.0f - data_prob);
+          else
+            avg_prob = w1 * model_prob + w2 * data_prob;
+          o3.w = avg_prob;
+          if (kp.averaging_scheme == 1) {
+            avg_position = add3(old_position, scale3(w2 * distance, old_normal));
+            avg_normal = slerp(old_normal, n_global, w1);
+          }
+          avg_normal = normalize3(avg_normal);
+          float SPI[16];
+          load_mat(ua.poses_inv, ci, SPI);
+          avg_position = xform_point(SPI, avg_position);
+          avg_normal = xform_dir(SPI, avg_normal);
+          o0 = make_float4(avg_position.x, avg_position.y, avg_position.z, avg_radius);
+          o1 = make_float4(avg_normal.x, avg_normal.y, avg_normal.z, confidence);
+          o2.y = pack_rgb(1.0f, 0.0f, 1.0f);
+        }
+      } else {
+        unsigned long long key = ua.index_keys[dpix];
+        int idx = (key == ~0ull) ? -1 : (int)(uint32_t)(key & 0xffffffffull);
+        if (idx == (int)k) {  // closest visible surfel of that pixel
+          update_conf = logf_(kp.p_unstable / (1.0f - kp.p_unstable));
+          o2.y = pack_rgb(0.0f, 1.0f, 1.0f);
+        }
+      }
+    }
+    update_conf = update_conf - penalty;
+    if (kp.use_stability) {
+      float c = (old_conf + update_conf) - kp.log_prior;
+      o1.w = c < 20.0f ? c : 20.0f;
+    } else {
+      o1.w = old_conf;
+    }
+    if (o1.w < kp.log_unstable && kp.use_stability) valid_out = false;
+    kept = valid_out && submap_keep(ua.poses, o0, o2, ua.submap_center, ua.submap_extent);
+  }
+  uint32_t block_count;
+  const uint32_t rank = block_rank<kUpdThreads>(kept, block_count);
+  const uint32_t excl = lookback_exclusive(lb, vb, block_count);
+  if (kept) {
+    uint32_t d = excl + rank;
+    if (d < cap) {  // transform feedback drops what does not fit
+      src.p0[d] = o0;
+      src.p1[d] = o1;
+      src.p2[d] = o2;
+      src.p3[d] = o3;
+    }
+  }
+  if (vb == gridDim.x - 1 && threadIdx.x == 0) {
+    uint32_t total = excl + block_count;
+    counts[1] = total < cap ? total : cap;  // S': base of the new surfels
+    counts[2] = total;                      // kept updated surfels
+    *lb.ticket = 0;
+  }
+}
+
 // K6d: gen_surfels.vert:38-52 + .geom:109-145; thread t <-> pixel (x = t / H, y = t % H): x-major order
 // (SurfelMap.cpp:88-92), fused with the K6e predicate
 __global__ void __launch_bounds__(kThreads) k_gen_surfels(KParams kp, FrameDev f, const float4* __restrict__ radius_map,
@@ -743,6 +992,59 @@ __global__ void __launch_bounds__(kThreads) k_gen_surfels(KParams kp, FrameDev f
   }
   int cnt = __syncthreads_count(kept ? 1 : 0);
   if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)cnt;
+}
+
+// K6d + K6e in ONE pass: new surfels are appended in x-major pixel order behind the updated ones
+__global__ void __launch_bounds__(kThreads) k_gen_compact(KParams kp, FrameDev f, const float4* __restrict__ radius_map,
+                                                         const uint8_t* __restrict__ integrated,
+                                                         const float* __restrict__ poses, int timestamp, float2 center,
+                                                         float extent, SurfelPlanes dst, Lookback lb, uint32_t cap,
+                                                         uint32_t* __restrict__ counts) {
+  const uint32_t vb = block_ticket(lb);
+  int t = (int)(vb * blockDim.x + threadIdx.x);
+  bool kept = false;
+  float4 o0, o1, o2, o3;
+  o0 = o1 = o2 = o3 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t < kp.W * kp.H) {
+    int x = t / kp.H, y = t - x * kp.H;
+    size_t pix = (size_t)y * kp.W + x;
+    float4 V = __ldg(f.vertex + pix), N = __ldg(f.normal + pix), R = __ldg(radius_map + pix);
+    bool invalid = (V.w < 1.0f) || (N.w < 1.0f);
+    invalid = invalid || (R.w < 0.5f);
+    bool integ = integrated[pix] != 0;
+    V3 v = mk3(V.x, V.y, V.z), n = mk3(N.x, N.y, N.z);
+    V3 view_dir = divs3(neg3(v), len3(v));
+    bool valid = !invalid && !integ && (dot3(n, view_dir) > 0.01f);
+    if (valid) {
+      V3 ng = normalize3(n);
+      float4 S = __ldg(f.semantic + pix);
+      float conf = is_movable(S.x * 255.0f) ? kp.log_prior - 0.5f : kp.log_prior;
+      o0 = make_float4(v.x, v.y, v.z, R.x);
+      o1 = make_float4(ng.x, ng.y, ng.z, conf);
+      o2 = make_float4(__uint_as_float((uint32_t)timestamp), pack_rgb(0.0f, 0.0f, 1.0f), 1.0f, (float)timestamp);
+      o3 = S;
+      kept = submap_keep(poses, o0, o2, center, extent);
+    }
+  }
+  uint32_t block_count;
+  const uint32_t rank = block_rank<kThreads>(kept, block_count);
+  const uint32_t excl = lookback_exclusive(lb, vb, block_count);
+  const uint32_t base = counts[1];
+  if (kept) {
+    uint32_t d = base + excl + rank;
+    if (d < cap) {
+      dst.p0[d] = o0;
+      dst.p1[d] = o1;
+      dst.p2[d] = o2;
+      dst.p3[d] = o3;
+    }
+  }
+  if (vb == gridDim.x - 1 && threadIdx.x == 0) {
+    uint32_t total = base + excl + block_count;
+    counts[0] = total < cap ? total : cap;  // new size of the map
+    counts[3] = excl + block_count;         // kept new surfels
+    *lb.ticket = 0;
+  }
 }
 
 // extract_surfels.vert:44-62: flags of the surfels inside one submap tile
@@ -882,6 +1184,37 @@ void launch_gen_surfels(const Launch& L, const KParams& kp, FrameDev frame, cons
     k_gen_surfels<<<(P + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, frame, radius_map, integrated, poses,
                                                                          timestamp, submap_center, submap_extent, tmp,
                                                                          keep, block_counts);
+  }
+}
+
+void launch_update_compact(const Launch& L, const KParams& kp, SurfelPlanes map, const uint32_t* n_dev, uint32_t n_upper,
+                           const Mat4& pose, const Mat4& inv_pose, const Mat4* pose_dev, const Mat4* inv_pose_dev,
+                           const float* poses, const float* poses_inv, const unsigned long long* index_keys,
+                           const float4* radius_map, FrameDev frame, int timestamp, float2 submap_center,
+                           float submap_extent, uint8_t* integrated, unsigned long long* desc, uint32_t* ticket,
+                           uint32_t gen, uint32_t cap, uint32_t* counts) {
+  UpdateArgs ua{pose, inv_pose, pose_dev, inv_pose_dev, poses, poses_inv, index_keys, radius_map, timestamp,
+                submap_center, submap_extent};
+  Lookback lb{desc, ticket, gen};
+  uint32_t blocks = (n_upper + kUpdThreads - 1) / kUpdThreads;
+  if (blocks == 0) blocks = 1;  // the last block also publishes the (zero) totals
+  {
+    ScopedKernel sk(L, K_UPDATE_SURFELS);
+    k_update_compact<<<blocks, kUpdThreads, 0, L.stream>>>(kp, map, n_dev, ua, frame, integrated, lb, cap, counts);
+  }
+}
+
+void launch_gen_compact(const Launch& L, const KParams& kp, FrameDev frame, const float4* radius_map,
+                        const uint8_t* integrated, const float* poses, int timestamp, float2 submap_center,
+                        float submap_extent, SurfelPlanes map, unsigned long long* desc, uint32_t* ticket, uint32_t gen,
+                        uint32_t cap, uint32_t* counts) {
+  int P = kp.W * kp.H;
+  Lookback lb{desc, ticket, gen};
+  {
+    ScopedKernel sk(L, K_GEN_SURFELS);
+    k_gen_compact<<<(P + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, frame, radius_map, integrated, poses,
+                                                                           timestamp, submap_center, submap_extent, map,
+                                                                           lb, cap, counts);
   }
 }
 

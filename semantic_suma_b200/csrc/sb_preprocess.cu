@@ -53,11 +53,12 @@ __global__ void __launch_bounds__(256) k_project_scatter(KParams kp, const float
 __global__ void __launch_bounds__(256) k_project_resolve(KParams kp, const float4* __restrict__ pts,
                                                          const float* __restrict__ labels,
                                                          const float* __restrict__ probs, uint32_t n, int isfirst,
-                                                         const unsigned long long* __restrict__ keys,
+                                                         unsigned long long* __restrict__ keys,
                                                          float4* __restrict__ vertex, float4* __restrict__ sem_raw) {
   int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= kp.W * kp.H) return;
   unsigned long long key = keys[pix];
+  keys[pix] = ~0ull;  // consume and clear: the key image is ready for the next scan without a separate fill
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f), s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (key != ~0ull) {
     uint32_t i = (uint32_t)(key & 0xffffffffull);
@@ -167,7 +168,6 @@ void launch_preprocess(const Launch& L, const KParams& kp, const float4* pts, co
                        uint32_t n, uint32_t timestamp, unsigned long long* keys, float4* sem_raw, float4* eroded,
                        FrameDev out) {
   const int P = kp.W * kp.H;
-  launch_fill_u64(L, keys, ~0ull, (size_t)P);
   if (n > 0) {
     {
       ScopedKernel sk(L, K_PROJECT_SCATTER);

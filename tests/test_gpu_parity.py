@@ -224,3 +224,41 @@ def test_process_scan_pipeline_bit_exact(width, semantic, frames):
     gt = np.linalg.inv(poses[0]) @ poses[frames - 1]
     assert np.linalg.norm(gsl.getCurrentPose()[:3, 3] - gt[:3, 3]) < 0.1
     gsl.ctx.close()
+
+
+def test_submap_paging_shift_extract_and_reinsert():
+    """SurfelMap::updateActiveSubmaps (SurfelMap.cpp:744-824): moving > 1.1 * extent shifts the active window, queues the
+    leaving tiles for extraction (one per update with partial extraction) and re-inserts cached tiles when coming back."""
+    po, pp = both_params(**sized(900))
+    ctx = api.Context(pp)
+    sc, poses = scans(900, n=3)
+    omap = O.Map(po)
+    gmap = api.SurfelMap(ctx)
+    frames = [_prep_both(po, ctx, s, 100) for s in sc]
+
+    def pose_at(x, y):
+        T = np.eye(4, dtype=np.float32)
+        T[0, 3], T[1, 3] = x, y
+        return T
+
+    # forward along +x far enough to drop tiles (window is 9x9 tiles of 20 m), sideways, then all the way back
+    xs = [0, 6, 12, 24, 36, 48, 60, 72, 84, 96, 108, 120, 120, 120, 108, 84, 60, 36, 12, 0, -12]
+    ys = [0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 12, 24, 24, 24, 24, 12, 0, 0, 0]
+    shifts = 0
+    for t, (x, y) in enumerate(zip(xs, ys)):
+        ov, f = frames[t % 3]
+        T = pose_at(x, y)
+        omap.update(T, ov)
+        gmap.update(T, f)
+        assert gmap.submap_origin() == omap.submap_origin(), "t=%d submap origin / pending" % t
+        assert gmap.size() == omap.size(), "t=%d size %d vs %d" % (t, gmap.size(), omap.size())
+        if omap.submap_origin()[:2] != (0, 0):
+            shifts += 1
+    assert shifts > 5
+    surfel_fields_equal(gmap.getAllSurfels(), omap.download(), "surfels after paging")
+    out = api.Frame(ctx, 900, 64)
+    orr = omap.render(pose_at(-12, 0), pose_at(-12, 0), -5.0)
+    gmap.render(pose_at(-12, 0), pose_at(-12, 0), out, -5.0)
+    for g, o in zip(out.maps(), orr):
+        assert_bits_equal(g, o, "render after paging")
+    ctx.close()
