@@ -23,8 +23,10 @@ struct sb_frame {
   float4* base;
 };
 
-struct HostTile {  // SubmapCache, SurfelMap.h:179-181 (kept as SoA lanes in host memory)
-  std::vector<float4> p0, p1, p2, p3;
+struct DevTile {  // SubmapCache, SurfelMap.h:179-181 -- kept in HBM (tile pool) instead of host RAM
+  uint32_t slot = 0;
+  bool known = false;  // base / count read back from the device record
+  uint32_t base = 0, count = 0;
 };
 
 struct sb_ctx {
@@ -87,7 +89,12 @@ struct sb_ctx {
   uint32_t map_timestamp = 0;
   int32_t origin_i = 0, origin_j = 0;
   std::vector<std::pair<int32_t, int32_t>> extraction;
-  std::map<std::pair<int32_t, int32_t>, HostTile> tiles;
+  std::map<std::pair<int32_t, int32_t>, DevTile> tiles;
+  SurfelPlanes pool{};            // tile cache lanes
+  uint32_t* d_pool_top = nullptr;
+  uint2* d_tile_rec = nullptr;    // {base, count} per extraction
+  uint32_t n_slots = 0;
+  bool tiles_pending = false;     // some records have not been read back yet
 
   // full-render memo: SurfelMapping re-renders the unchanged map at the unchanged pose at the start of the next scan
   // (SurfelMapping.cpp:351 after :803); identical arguments on an unmodified map reproduce identical images
@@ -223,7 +230,8 @@ int release_buffers(sb_ctx* c) {
   cudaFree(c->d_pts); cudaFree(c->d_labels); cudaFree(c->d_probs);
   cudaFree(c->gn); cudaFree(c->gn2); cudaFree(c->acc32); cudaFree(c->acc_slots); cudaFree(c->ticket);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
-  free_planes(&c->A); free_planes(&c->T); free_planes(&c->G); free_planes(&c->X);
+  free_planes(&c->A); free_planes(&c->T); free_planes(&c->G); free_planes(&c->X); free_planes(&c->pool);
+  cudaFree(c->d_pool_top); cudaFree(c->d_tile_rec);
   cudaFree(c->keep); cudaFree(c->block_counts); cudaFree(c->block_offsets); cudaFree(c->d_counts);
   cudaFree(c->lb_desc); cudaFree(c->lb_ticket);
   cudaFree(c->poses); cudaFree(c->poses_inv); cudaFree(c->Mtab_old); cudaFree(c->Mtab_new);
@@ -248,6 +256,9 @@ int reset_state(sb_ctx* c) {
   c->origin_i = c->origin_j = 0;
   c->extraction.clear();
   c->tiles.clear();
+  c->n_slots = 0;
+  c->tiles_pending = false;
+  SB_CUDA(c, cudaMemsetAsync(c->d_pool_top, 0, 64, c->stream));
   c->h_poses.assign((size_t)kMaxPoses * 16, 0.0f);
   for (uint32_t t = 0; t < kMaxPoses; ++t)
     for (int i = 0; i < 4; ++i) c->h_poses[16 * (size_t)t + 5 * i] = 1.0f;
@@ -300,7 +311,10 @@ int alloc_buffers(sb_ctx* c) {
   if ((r = alloc_planes(c, &c->A, kMaxSurfels))) return r;
   if ((r = alloc_planes(c, &c->T, kMaxSurfels))) return r;
   if ((r = alloc_planes(c, &c->G, Pd))) return r;
-  if ((r = alloc_planes(c, &c->X, kExtractCap))) return r;
+  if ((r = alloc_planes(c, &c->X, 16))) return r;
+  if ((r = alloc_planes(c, &c->pool, kTilePoolCap))) return r;
+  SB_CUDA(c, cudaMalloc(&c->d_pool_top, 64));
+  SB_CUDA(c, cudaMalloc(&c->d_tile_rec, (size_t)kMaxTileSlots * sizeof(uint2)));
   SB_CUDA(c, cudaMalloc(&c->keep, kMaxSurfels));
   size_t nb = (kMaxSurfels + 127) / 128 + 16;  // blocks of the finest-grained surfel kernel
   SB_CUDA(c, cudaMalloc(&c->block_counts, nb * 4));
@@ -553,47 +567,67 @@ int fetch_counts(sb_ctx* c, uint32_t* dst, int n) {
   return SB_OK;
 }
 
-int append_tiles(sb_ctx* c, int32_t i0, int32_t j0, int di, int dj) {  // SurfelMap.cpp:769-780
-  const int dim = c->p.submap_dimension;
-  for (int32_t k = -dim; k <= dim; ++k) {
-    HostTile& t = c->tiles[std::make_pair(i0 + di * k, j0 + dj * k)];
-    uint32_t room = kMaxSurfels - c->n_host;
-    uint32_t n = (uint32_t)t.p0.size();
-    if (n > room) n = room;
-    if (n == 0) continue;
-    SB_CUDA(c, cudaMemcpyAsync(c->A.p0 + c->n_host, t.p0.data(), (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
-    SB_CUDA(c, cudaMemcpyAsync(c->A.p1 + c->n_host, t.p1.data(), (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
-    SB_CUDA(c, cudaMemcpyAsync(c->A.p2 + c->n_host, t.p2.data(), (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
-    SB_CUDA(c, cudaMemcpyAsync(c->A.p3 + c->n_host, t.p3.data(), (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
-    c->n_host += n;
-    c->n_upper = c->n_host;
+int refresh_tile_records(sb_ctx* c) {  // read back {base, count} of the tiles extracted so far
+  if (!c->tiles_pending || c->n_slots == 0) return SB_OK;
+  std::vector<uint2> rec(c->n_slots);
+  SB_CUDA(c, cudaMemcpyAsync(rec.data(), c->d_tile_rec, (size_t)c->n_slots * sizeof(uint2), cudaMemcpyDeviceToHost,
+                             c->stream));
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (auto& kv : c->tiles) {
+    DevTile& t = kv.second;
+    if (!t.known) {
+      t.base = rec[t.slot].x;
+      t.count = rec[t.slot].y;
+      t.known = true;
+    }
   }
-  SB_CUDA(c, cudaMemcpyAsync(c->d_counts, &c->n_host, 4, cudaMemcpyHostToDevice, c->stream));
-  SB_CUDA(c, cudaStreamSynchronize(c->stream));  // n_host is a stack-adjacent member; keep the copy ordered
+  c->tiles_pending = false;
   return SB_OK;
 }
 
-int extract_surfels(sb_ctx* c, bool partially) {  // SurfelMap.cpp:708-742 + extract_surfels.vert
+int append_tiles(sb_ctx* c, int32_t i0, int32_t j0, int di, int dj) {  // SurfelMap.cpp:769-780
+  const int dim = c->p.submap_dimension;
+  int r;
+  bool appended = false;
+  for (int32_t k = -dim; k <= dim; ++k) {
+    auto it = c->tiles.find(std::make_pair(i0 + di * k, j0 + dj * k));
+    if (it == c->tiles.end()) continue;  // submapCache_[idx] of a tile never extracted: empty
+    if (!it->second.known && (r = refresh_tile_records(c))) return r;
+    const DevTile& t = it->second;
+    uint32_t room = kMaxSurfels - c->n_host;
+    uint32_t n = t.count < room ? t.count : room;
+    if (n == 0) continue;
+    SB_CUDA(c, cudaMemcpyAsync(c->A.p0 + c->n_host, c->pool.p0 + t.base, (size_t)n * 16, cudaMemcpyDeviceToDevice, c->stream));
+    SB_CUDA(c, cudaMemcpyAsync(c->A.p1 + c->n_host, c->pool.p1 + t.base, (size_t)n * 16, cudaMemcpyDeviceToDevice, c->stream));
+    SB_CUDA(c, cudaMemcpyAsync(c->A.p2 + c->n_host, c->pool.p2 + t.base, (size_t)n * 16, cudaMemcpyDeviceToDevice, c->stream));
+    SB_CUDA(c, cudaMemcpyAsync(c->A.p3 + c->n_host, c->pool.p3 + t.base, (size_t)n * 16, cudaMemcpyDeviceToDevice, c->stream));
+    c->n_host += n;
+    c->n_upper = c->n_host;
+    appended = true;
+  }
+  if (appended) {
+    SB_CUDA(c, cudaMemcpyAsync(c->d_counts, &c->n_host, 4, cudaMemcpyHostToDevice, c->stream));
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));  // the copy reads a member of the context: keep it ordered
+  }
+  return SB_OK;
+}
+
+// SurfelMap.cpp:708-742 + extract_surfels.vert: the tile is compacted into the HBM pool; nothing is read back here
+int extract_surfels(sb_ctx* c, bool partially) {
   Launch L = L_(c);
   while (!c->extraction.empty()) {
     std::pair<int32_t, int32_t> idx = c->extraction.back();
     c->extraction.pop_back();
+    if (c->n_slots >= kMaxTileSlots) return fail(c, SB_ERR_CAPACITY, "tile cache: out of record slots");
     float2 ctr = submap_center(c, idx.first, idx.second);
-    launch_extract_flags(L, c->A, c->d_counts, c->n_host, c->poses, ctr, c->p.submap_extent, c->keep, c->block_counts);
-    launch_compact(L, c->A, c->keep, c->block_counts, c->block_offsets, c->d_counts, c->n_host, c->X, nullptr,
-                   kExtractCap, c->d_counts + 4, nullptr);
-    uint32_t cnt[5];
-    int r = fetch_counts(c, cnt, 5);
-    if (r) return r;
-    uint32_t n = cnt[4];
-    HostTile& t = c->tiles[idx];
-    t.p0.resize(n); t.p1.resize(n); t.p2.resize(n); t.p3.resize(n);
-    if (n) {
-      SB_CUDA(c, cudaMemcpy(t.p0.data(), c->X.p0, (size_t)n * 16, cudaMemcpyDeviceToHost));
-      SB_CUDA(c, cudaMemcpy(t.p1.data(), c->X.p1, (size_t)n * 16, cudaMemcpyDeviceToHost));
-      SB_CUDA(c, cudaMemcpy(t.p2.data(), c->X.p2, (size_t)n * 16, cudaMemcpyDeviceToHost));
-      SB_CUDA(c, cudaMemcpy(t.p3.data(), c->X.p3, (size_t)n * 16, cudaMemcpyDeviceToHost));
-    }
+    uint32_t slot = c->n_slots++;
+    launch_extract_to_pool(L, c->A, c->d_counts, c->n_host, c->poses, ctr, c->p.submap_extent, c->keep, c->block_counts,
+                           c->block_offsets, c->pool, kTilePoolCap, c->d_pool_top, c->d_tile_rec + slot, kExtractCap);
+    DevTile t;
+    t.slot = slot;
+    t.known = false;
+    c->tiles[idx] = t;  // a tile extracted again replaces its cache entry (the old pool range is abandoned)
+    c->tiles_pending = true;
     if (partially) break;
   }
   return SB_OK;

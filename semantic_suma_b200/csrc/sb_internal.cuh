@@ -17,6 +17,8 @@ constexpr uint32_t kMaxPoses = 10000u;           // SurfelMap.h:205
 constexpr uint32_t kExtractCap = 500000u;        // SurfelMap.cpp:279
 constexpr uint32_t kComposeAge = 100u;           // SurfelMap.h:144
 constexpr int kMaxGnIter = 256;
+constexpr uint32_t kTilePoolCap = 16u * 1024u * 1024u;  // surfels held by the HBM tile cache (1 GiB)
+constexpr uint32_t kMaxTileSlots = 16384u;
 
 // everything the kernels need from sb_params plus the derived constants the reference computes on the host
 struct KParams {
@@ -214,6 +216,9 @@ void launch_gen_compact(const Launch& L, const KParams& kp, FrameDev frame, cons
 void launch_compact(const Launch& L, SurfelPlanes src, const uint8_t* keep, const uint32_t* block_counts,
                     uint32_t* block_offsets, const uint32_t* n_dev, uint32_t n_upper, SurfelPlanes dst,
                     const uint32_t* base_dev, uint32_t cap, uint32_t* count_out, uint32_t* kept_out);
+void launch_extract_to_pool(const Launch& L, SurfelPlanes map, const uint32_t* n_dev, uint32_t n_upper, const float* poses,
+                            float2 center, float extent, uint8_t* keep, uint32_t* block_counts, uint32_t* block_offsets,
+                            SurfelPlanes pool, uint32_t pool_cap, uint32_t* pool_top, uint2* rec, uint32_t tile_cap);
 void launch_extract_flags(const Launch& L, SurfelPlanes s, const uint32_t* n_dev, uint32_t n_upper, const float* poses,
                           float2 center, float extent, uint8_t* keep, uint32_t* block_counts);
 void launch_aos_to_soa(const Launch& L, const sb_surfel* aos, SurfelPlanes s, uint32_t offset, uint32_t n);

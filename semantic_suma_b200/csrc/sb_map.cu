@@ -1121,7 +1121,7 @@ __global__ void __launch_bounds__(kThreads) k_compact_scatter(SurfelPlanes src, 
                                                              const uint32_t* __restrict__ offsets,
                                                              const uint32_t* __restrict__ n_dev, uint32_t n_fixed,
                                                              SurfelPlanes dst, const uint32_t* __restrict__ base_dev,
-                                                             uint32_t cap) {
+                                                             uint32_t cap, uint32_t rel_cap) {
   __shared__ uint32_t warp_cnt[kThreads / 32];
   uint32_t n = n_dev ? *n_dev : n_fixed;
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1135,8 +1135,9 @@ __global__ void __launch_bounds__(kThreads) k_compact_scatter(SurfelPlanes src, 
   if (!kept) return;
   uint32_t rank = before + __popc(m & ((1u << lane) - 1u));
   uint32_t base = base_dev ? *base_dev : 0u;
-  uint32_t d = base + offsets[blockIdx.x] + rank;
-  if (d >= cap) return;  // transform feedback drops what does not fit
+  uint32_t rel = offsets[blockIdx.x] + rank;
+  uint32_t d = base + rel;
+  if (d >= cap || rel >= rel_cap) return;  // transform feedback drops what does not fit
   dst.p0[d] = src.p0[k];
   dst.p1[d] = src.p1[k];
   dst.p2[d] = src.p2[k];
@@ -1155,7 +1156,39 @@ void launch_compact(const Launch& L, SurfelPlanes src, const uint8_t* keep, cons
   {
     ScopedKernel sk(L, K_COMPACT_SCATTER);
     k_compact_scatter<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(src, keep, block_offsets, n_dev,
-                                                                                   n_upper, dst, base_dev, cap);
+                                                                                   n_upper, dst, base_dev, cap,
+                                                                                   0xffffffffu);
+  }
+}
+
+// ---- submap tile cache in HBM: a leaving tile is compacted straight into a device-resident pool (the reference
+// downloads it to host RAM, SurfelMap.cpp:708-742). rec = {base, count} of the tile inside the pool.
+__global__ void k_pool_alloc(uint2* __restrict__ rec, uint32_t* __restrict__ pool_top, uint32_t pool_cap) {
+  uint32_t base = *pool_top, cnt = rec->y;
+  if (base > pool_cap) base = pool_cap;
+  if (cnt > pool_cap - base) cnt = pool_cap - base;  // pool exhausted: the tail of the tile is lost
+  rec->x = base;
+  rec->y = cnt;
+  *pool_top = base + cnt;
+}
+
+void launch_extract_to_pool(const Launch& L, SurfelPlanes map, const uint32_t* n_dev, uint32_t n_upper, const float* poses,
+                            float2 center, float extent, uint8_t* keep, uint32_t* block_counts, uint32_t* block_offsets,
+                            SurfelPlanes pool, uint32_t pool_cap, uint32_t* pool_top, uint2* rec, uint32_t tile_cap) {
+  launch_extract_flags(L, map, n_dev, n_upper, poses, center, extent, keep, block_counts);
+  {
+    ScopedKernel sk(L, K_SCAN_BLOCKS);
+    k_scan_blocks<<<1, 1024, 0, L.stream>>>(block_counts, block_offsets, n_dev, n_upper, nullptr, tile_cap, &rec->y, nullptr);
+  }
+  {
+    ScopedKernel sk(L, K_SCAN_BLOCKS);
+    k_pool_alloc<<<1, 1, 0, L.stream>>>(rec, pool_top, pool_cap);
+  }
+  if (n_upper == 0) return;
+  {
+    ScopedKernel sk(L, K_COMPACT_SCATTER);
+    k_compact_scatter<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(
+        map, keep, block_offsets, n_dev, n_upper, pool, &rec->x, pool_cap, tile_cap);
   }
 }
 
