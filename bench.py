@@ -139,7 +139,7 @@ def run_native(args, w, rank, world, local_rank):
     from semantic_suma_b200 import api
 
     n_frames = args.warmup + args.steps
-    scans = generate_scans(w, n_frames, seed=1337 + 1000 * rank)
+    scans = generate_scans(w, n_frames, seed=1337 + (0 if args.striped else 1000 * rank))
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -148,6 +148,9 @@ def run_native(args, w, rank, world, local_rank):
     pp = api.default_params(**param_kwargs(w))
     slam = api.SurfelMapping(pp, device=local_rank)
     ctx = slam.ctx
+    if dist is not None and args.striped:
+        from semantic_suma_b200 import stripes
+        stripes.setup_comm(ctx, dist)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     sem = w["semantic"]
@@ -252,14 +255,18 @@ def run_native(args, w, rank, world, local_rank):
     out = None
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_baseline(w, scans, budget_s=args.cpu_budget)
-        value = world * args.steps / (ms_dev * 1e-3)
-        e2e_value = world * args.steps / (ms_e2e * 1e-3)
+        seqs = 1 if args.striped else world
+        value = seqs * args.steps / (ms_dev * 1e-3)
+        e2e_value = seqs * args.steps / (ms_e2e * 1e-3)
         out = {
             "metric": "scans_per_sec", "value": round(value, 2), "unit": "scans/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_dev / args.steps, 4),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if args.striped else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "range_image": "%dx%d" % (w["height"], w["width"]),
-                       "icp_iterations": w["iters"], "semantic": sem, "sequences": world,
+                       "icp_iterations": w["iters"], "semantic": sem, "sequences": 1 if args.striped else world,
+                       "parallelism": ("k5-row-stripes-x%d (peer-memory all-reduce in-kernel)" % world) if args.striped
+                       else "one sequence per GPU",
                        "surfels_end": int(surfels), "pose_drift_m": round(drift, 4),
                        "l2": "flushed between timed steps (256 MiB memset, untimed)",
                        "step_ms_min_med_max": [round(min(per_step), 4), round(statistics.median(per_step), 4),
@@ -342,6 +349,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="hdl64_2048_geometric", choices=sorted(WORKLOADS))
+    ap.add_argument("--striped", action="store_true",
+                    help="N > 1: all ranks process the SAME sequence, the K5 reduction is striped over image rows and "
+                         "all-reduced inside the kernel over peer memory (BASELINE.json configs[3]); strong scaling")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
