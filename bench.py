@@ -139,7 +139,12 @@ def run_native(args, w, rank, world, local_rank):
     from semantic_suma_b200 import api
 
     n_frames = args.warmup + args.steps
+    dbg = bool(os.environ.get("SUMA_B200_WATCHDOG"))
+    if dbg:
+        print("[r%d] generating %d scans" % (rank, n_frames), file=sys.stderr, flush=True)
     scans = generate_scans(w, n_frames, seed=1337 + (0 if args.striped else 1000 * rank))
+    if dbg:
+        print("[r%d] scans ready" % rank, file=sys.stderr, flush=True)
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -202,8 +207,12 @@ def run_native(args, w, rank, world, local_rank):
             total_ms = float(t.item())
         return total_ms, ctx.launch_count() - launches0, t_wall, ms
 
+    if dbg:
+        print("[r%d] buffers ready, starting passes" % rank, file=sys.stderr, flush=True)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_dev, launches, wall_dev, per_step = one_pass(dev, True, sampler)
+    if dbg:
+        print("[r%d] device-resident pass done" % rank, file=sys.stderr, flush=True)
     ms_e2e, _, wall_e2e, _ = one_pass(pin, False)
     surfels = slam.getMap().size()
     gt = np.linalg.inv(synth.trajectory(1)[0]) @ synth.trajectory(n_frames)[-1]
@@ -343,6 +352,10 @@ def run_reference(args, w, rank, world):
 
 
 def main():
+    if os.environ.get("SUMA_B200_WATCHDOG"):  # debugging aid: dump the Python stacks if the run hangs
+        import faulthandler
+        faulthandler.enable()
+        faulthandler.dump_traceback_later(float(os.environ["SUMA_B200_WATCHDOG"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=60)

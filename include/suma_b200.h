@@ -183,6 +183,11 @@ int sb_comm_export(sb_ctx* ctx, uint8_t handle[64]);
 int sb_comm_init(sb_ctx* ctx, int rank, int nranks, const uint8_t* handles /* nranks*64 */, int row_begin,
                  int row_end);
 int sb_comm_shutdown(sb_ctx* ctx);
+/* Baseline exchange: the library calls `fn(user, sums32)` once per Gauss-Newton iteration with this rank's 32 int64
+ * partial sums; the callback all-reduces them in place (e.g. torch.distributed / NCCL / MPI on the host side). The
+ * loop then runs on the host (one K5 launch + read-back per iteration). fn == NULL switches the mode off. */
+typedef int (*sb_allreduce_fn)(void* user, int64_t* sums32);
+int sb_comm_set_callback(sb_ctx* ctx, sb_allreduce_fn fn, void* user, int row_begin, int row_end);
 
 #ifdef __cplusplus
 }

@@ -120,6 +120,7 @@ def lib(build_if_missing=True):
         "sb_get_statistics": [vp, pd],
         "sb_comm_export": [vp, vp], "sb_comm_init": [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int],
         "sb_comm_shutdown": [vp],
+        "sb_comm_set_callback": [vp, vp, vp, C.c_int, C.c_int],
         "sb_profile_enable": [vp, C.c_int], "sb_profile_collect": [vp, pd, C.POINTER(C.c_uint64), C.c_int],
         "sb_profile_kernels": [],
     }
@@ -147,7 +148,8 @@ EXPORTED_SYMBOLS = [
     "sb_icp_minimize", "sb_se3_exp", "sb_se3_log", "sb_ldlt_solve6", "sb_gn_step", "sb_map_update",
     "sb_map_update_poses", "sb_map_size", "sb_map_timestamp", "sb_map_download", "sb_map_upload", "sb_map_set_pose",
     "sb_map_update_debug", "sb_map_submap_origin", "sb_process_scan", "sb_get_pose", "sb_timestamp", "sb_slam_frame",
-    "sb_get_statistics", "sb_comm_export", "sb_comm_init", "sb_comm_shutdown", "sb_profile_enable",
+    "sb_get_statistics", "sb_comm_export", "sb_comm_init", "sb_comm_shutdown", "sb_comm_set_callback",
+    "sb_profile_enable",
     "sb_profile_kernels", "sb_profile_name", "sb_profile_collect",
 ]
 

@@ -57,6 +57,7 @@ struct sb_ctx {
   void* h_pinned = nullptr;  // pinned staging for small read-backs (64 KiB)
   int icp_blocks = 296;
   int icp_coop_blocks = 0;  // > 0: the persistent cooperative Gauss-Newton kernel is available
+  unsigned long long* icp_trace_host = nullptr;
   unsigned long long* icp_trace = nullptr;  // optional %globaltimer stamps of the GN phases (SUMA_B200_ICP_TRACE=1)
 
   // ---- map
@@ -127,6 +128,8 @@ struct sb_ctx {
   unsigned int* comm_epoch = nullptr;
   CommDev comm{};
   bool comm_on = false;
+  sb_allreduce_fn comm_cb = nullptr;  // host-side exchange (baseline); exclusive with the fused peer-memory mode
+  void* comm_cb_user = nullptr;
   int row_begin = 0, row_end = 0;
   std::vector<void*> peer_ptrs;
 };
@@ -503,9 +506,61 @@ int icp_jacobian_raw(sb_ctx* c, const sb_frame* data, const sb_frame* model, con
 }
 
 // enqueue the device-resident Gauss-Newton loop; the result stays in c->gn
+struct GnHead {  // prefix of GnState copied back / uploaded
+  double pose[16];
+  double last_error;
+  double out48[48];
+  int k, done, history_len, pad;
+};
+
+// Row-striped minimisation with a host-side all-reduce callback: LieGaussNewton::minimize driven from the host, one
+// striped K5 launch + 256-byte read-back + callback per iteration; the result is written into the device GN state so
+// that the rest of the pipeline proceeds as after the device-resident loop.
+int icp_minimize_callback(sb_ctx* c, const sb_frame* data, const sb_frame* model, const double* T0, int max_iter,
+                          double eps, double delta, float max_distance, float max_angle_deg, bool semantics) {
+  IcpArgs a = icp_args(c, data, model, max_distance, max_angle_deg, c->row_begin, c->row_end, semantics);
+  std::vector<double> hist;
+  GnHead h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.pose, T0, sizeof(h.pose));
+  h.last_error = (double)3.402823466e+38f;
+  int k = 0;
+  for (;;) {
+    hist.insert(hist.end(), h.pose, h.pose + 16);
+    if (k >= max_iter) break;
+    Mat4 P;
+    for (int i = 0; i < 16; ++i) P.m[i] = (float)h.pose[i];
+    launch_icp_jacobian(L_(c), c->kp, a, P, k, c->acc32, c->acc_slots, c->ticket + 16, c->icp_blocks);
+    SB_CUDA(c, cudaMemcpyAsync(c->h_pinned, c->acc32, 32 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));
+    long long raw[32];
+    memcpy(raw, c->h_pinned, sizeof(raw));
+    if (c->comm_cb(c->comm_cb_user, (int64_t*)raw) != 0) return fail(c, SB_ERR_STATE, "all-reduce callback failed");
+    sbg::unpack48(raw, h.out48);
+    double dx[6];
+    int result = sbg::gn_step(h.out48, h.last_error, eps, delta, h.pose, dx);
+    h.last_error = h.out48[43];
+    if (result == 0) break;
+    ++k;
+  }
+  h.k = k;
+  h.done = 1;
+  h.history_len = (int)(hist.size() / 16);
+  char* hp = (char*)c->h_pinned + 16384;
+  memcpy(hp, &h, sizeof(h));
+  size_t hb = hist.size() * sizeof(double);
+  if (hb > 32768) hb = 32768;
+  memcpy(hp + 1024, hist.data(), hb);
+  SB_CUDA(c, cudaMemcpyAsync(c->gn, hp, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+  SB_CUDA(c, cudaMemcpyAsync((char*)c->gn + offsetof(GnState, history), hp + 1024, hb, cudaMemcpyHostToDevice, c->stream));
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SB_OK;
+}
+
 int icp_minimize_enqueue(sb_ctx* c, const sb_frame* data, const sb_frame* model, const double* T0, int max_iter,
                          double eps, double delta, float max_distance, float max_angle_deg, bool semantics) {
   if (max_iter <= 0 || max_iter > kMaxGnIter) max_iter = kMaxGnIter;
+  if (c->comm_cb) return icp_minimize_callback(c, data, model, T0, max_iter, eps, delta, max_distance, max_angle_deg, semantics);
   int r0 = 0, r1 = c->kp.H;
   if (c->comm_on) {
     r0 = c->row_begin;
@@ -529,13 +584,6 @@ int icp_minimize_enqueue(sb_ctx* c, const sb_frame* data, const sb_frame* model,
                                c->comm_on ? &c->comm : nullptr, c->icp_blocks);
   return SB_OK;
 }
-
-struct GnHead {  // prefix of GnState copied back
-  double pose[16];
-  double last_error;
-  double out48[48];
-  int k, done, history_len, pad;
-};
 
 int icp_minimize_fetch(sb_ctx* c, double* pose_out, double* out48, int* iters, double* history, int* history_len) {
   SB_CUDA(c, cudaMemcpyAsync(c->h_pinned, c->gn, sizeof(GnHead), cudaMemcpyDeviceToHost, c->stream));
@@ -774,7 +822,24 @@ int update_pose_enqueue(sb_ctx* c) {
     launch_icp_jacobian(L, c->kp, a, I, 0, c->acc32, c->acc_slots, c->ticket + 16, c->icp_blocks);
   }
   // :430-449 track-loss test (on the device) and the frame-to-frame fallback, which returns at once unless needed
-  if (p.fallback_mode) {
+  if (p.fallback_mode && c->comm_cb) {
+    // host-driven exchange: read the track-loss flag and run the recovery minimisation only when it is set
+    int fb = 0;
+    SB_CUDA(c, cudaMemcpyAsync(c->h_pinned, (const char*)c->pd + offsetof(PoseDev, fallback), sizeof(int),
+                               cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));
+    memcpy(&fb, c->h_pinned, sizeof(int));
+    launch_gn_init_fallback(L, c->gn2, c->pd, c->acc32 + 32, c->ticket, c->ticket + 8);
+    if (fb) {
+      GnState* keep = c->gn;
+      c->gn = c->gn2;  // icp_minimize_callback writes its result into c->gn
+      int rr = icp_minimize_callback(c, c->cur, c->last, T0, p.max_iterations > 0 ? p.max_iterations : kMaxGnIter,
+                                     p.stopping_threshold, p.delta, p.fallback_max_distance, p.fallback_max_angle,
+                                     sem && c->last_has_semantics);
+      c->gn = keep;
+      if (rr) return rr;
+    }
+  } else if (p.fallback_mode) {
     int max_iter = p.max_iterations;
     if (max_iter <= 0 || max_iter > kMaxGnIter) max_iter = kMaxGnIter;
     int r0 = 0, r1 = c->kp.H;
@@ -875,8 +940,14 @@ int sb_create(const sb_params* p, int device, sb_ctx** out) {
       if (b > 0 && b <= maxb && b <= 1024) c->icp_coop_blocks = b;
     }
     if (getenv("SUMA_B200_ICP_TRACE")) {
-      cudaMalloc(&c->icp_trace, 16 * 16 * 8);
-      cudaMemset(c->icp_trace, 0, 16 * 16 * 8);
+      if (std::string(getenv("SUMA_B200_ICP_TRACE")) == "host") {  // host-mapped: readable while a kernel hangs
+        cudaHostAlloc(&c->icp_trace_host, 16 * 16 * 8, cudaHostAllocMapped);
+        memset(c->icp_trace_host, 0, 16 * 16 * 8);
+        cudaHostGetDevicePointer((void**)&c->icp_trace, c->icp_trace_host, 0);
+      } else {
+        cudaMalloc(&c->icp_trace, 16 * 16 * 8);
+        cudaMemset(c->icp_trace, 0, 16 * 16 * 8);
+      }
     }
   }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -1327,6 +1398,10 @@ int sb_get_statistics(sb_ctx* c, double stats[16]) {
 // debugging aid: %globaltimer stamps of the last sb_icp_minimize (16 iterations x 16 slots), see sb_icp.cu SB_TR
 int sb_debug_icp_trace(sb_ctx* c, uint64_t* out256) {
   if (!c || !out256 || !c->icp_trace) return SB_ERR_STATE;
+  if (c->icp_trace_host) {
+    memcpy(out256, c->icp_trace_host, 16 * 16 * 8);
+    return SB_OK;
+  }
   SB_CUDA(c, cudaStreamSynchronize(c->stream));
   SB_CUDA(c, cudaMemcpy(out256, c->icp_trace, 16 * 16 * 8, cudaMemcpyDeviceToHost));
   return SB_OK;
@@ -1366,8 +1441,11 @@ int sb_comm_export(sb_ctx* c, uint8_t handle[64]) {
   if (!c || !handle) return SB_ERR_INVALID;
   cudaSetDevice(c->device);
   if (!c->mailbox) {
-    SB_CUDA(c, cudaMalloc(&c->mailbox, 2 * 8 * 40 * sizeof(long long)));
-    SB_CUDA(c, cudaMemset(c->mailbox, 0, 2 * 8 * 40 * sizeof(long long)));
+    // A CUDA IPC handle names the whole underlying allocation and cudaIpcOpenMemHandle returns ITS base: small
+    // cudaMalloc requests are carved out of shared 2 MiB blocks, so a 5 KiB mailbox would be opened at the wrong
+    // address on the peer. A 2 MiB allocation owns its block: exported pointer == base.
+    SB_CUDA(c, cudaMalloc(&c->mailbox, 2u << 20));
+    SB_CUDA(c, cudaMemset(c->mailbox, 0, 2u << 20));
   }
   cudaIpcMemHandle_t h;
   SB_CUDA(c, cudaIpcGetMemHandle(&h, c->mailbox));
@@ -1406,8 +1484,22 @@ int sb_comm_init(sb_ctx* c, int rank, int nranks, const uint8_t* handles, int ro
   return SB_OK;
 }
 
+int sb_comm_set_callback(sb_ctx* c, sb_allreduce_fn fn, void* user, int row_begin, int row_end) {
+  if (!c) return SB_ERR_INVALID;
+  if (fn && (row_begin < 0 || row_end > c->kp.H || row_begin > row_end)) return fail(c, SB_ERR_INVALID, "comm: bad rows");
+  if (fn && c->comm_on) return fail(c, SB_ERR_STATE, "comm: the fused peer-memory mode is already active");
+  c->comm_cb = fn;
+  c->comm_cb_user = user;
+  if (fn) {
+    c->row_begin = row_begin;
+    c->row_end = row_end;
+  }
+  return SB_OK;
+}
+
 int sb_comm_shutdown(sb_ctx* c) {
   if (!c) return SB_ERR_INVALID;
+  c->comm_cb = nullptr;
   for (void* p : c->peer_ptrs) cudaIpcCloseMemHandle(p);
   c->peer_ptrs.clear();
   c->comm_on = false;

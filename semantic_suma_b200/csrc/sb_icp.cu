@@ -563,8 +563,9 @@ __device__ void gn_step_warp(GnShared& sh, long long raw, int lane, double last_
 }
 
 // lane-parallel one-shot all-reduce of the 32 sums over the ranks' peer-mapped mailboxes (warp 0 of the last block)
-__device__ long long comm_allreduce32_warp(const CommDev& cd, long long raw, int lane) {
+__device__ long long comm_allreduce32_warp(const CommDev& cd, long long raw, int lane, volatile unsigned long long* dbg) {
   int epoch = 0;
+  if (dbg && lane == 0) dbg[240] = 1 + dbg[240];
   if (lane == 0) {
     epoch = (int)(*cd.epoch) + 1;  // stamps start at 1: a zeroed mailbox never matches
     *cd.epoch = (unsigned int)epoch;
@@ -578,17 +579,22 @@ __device__ long long comm_allreduce32_warp(const CommDev& cd, long long raw, int
   __threadfence_system();
   __syncwarp();
   if (lane == 0) {
+    if (dbg) { dbg[241] = (unsigned long long)epoch; dbg[242] = (unsigned long long)cd.nranks; dbg[243] = (unsigned long long)cd.rank; }
     for (int r = 0; r < cd.nranks; ++r) {
       volatile long long* dst = cd.mailbox[r] + ((size_t)(slot * 8 + cd.rank)) * 40;
       dst[32] = (long long)epoch;
     }
     __threadfence_system();
     volatile long long* mine = cd.mailbox[cd.rank];
+    if (dbg) dbg[244] = 1 + dbg[244];
     for (int r = 0; r < cd.nranks; ++r) {
       volatile long long* src = mine + ((size_t)(slot * 8 + r)) * 40;
+      if (dbg) { dbg[245] = (unsigned long long)r; dbg[246] = (unsigned long long)src[32]; dbg[248 + r] = (unsigned long long)(size_t)cd.mailbox[r]; }
       while (src[32] != (long long)epoch) {
+        if (dbg) dbg[247] = (unsigned long long)src[32];
       }
     }
+    if (dbg) dbg[244] = 100 + dbg[244];
     __threadfence_system();
   }
   __syncwarp();
@@ -659,7 +665,7 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_icp_persistent(KParams kp, I
       double last_error = 0.0;
       if (lane == 16) last_error = *(volatile double*)&st->last_error;
       last_error = __shfl_sync(0xffffffffu, last_error, 16);
-      if (cd.nranks > 1) raw = comm_allreduce32_warp(cd, raw, lane);
+      if (cd.nranks > 1) raw = comm_allreduce32_warp(cd, raw, lane, trace);
       if (lane < 16) sh.P[lane] = s_pose[lane];
       int hl = (int)it;  // one pose has been pushed per completed iteration
       if (lane < 16) st->history[hl * 16 + lane] = s_pose[lane];  // history_.push_back(Tk_)

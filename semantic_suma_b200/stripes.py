@@ -26,11 +26,45 @@ def allreduce_raw32(raw32, dist):
     return t.numpy()
 
 
-def setup_comm(ctx, dist, height=None):
-    """exchange the IPC handles of the ranks' mailboxes and enable the fused all-reduce on `ctx`"""
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int64))
+
+
+def setup_comm(ctx, dist, height=None, fused=None):
+    """Row-stripe the K5 reduction of `ctx` over the ranks of `dist`.
+
+    fused=False (default): baseline -- the library calls back once per Gauss-Newton iteration and the 32 int64 sums are
+    all-reduced with torch.distributed (NCCL for CUDA tensors, gloo on the CPU). Exact either way.
+    fused=True (SUMA_B200_FUSED_COMM=1): the exchange runs inside the persistent GN kernel over CUDA-IPC peer memory
+    (sb_comm_init). EXPERIMENTAL in round 1: it deadlocks on a 2-GPU box after a few iterations.
+    """
+    import os
     import torch
     from . import api
+    if fused is None:
+        fused = os.environ.get("SUMA_B200_FUSED_COMM", "0") == "1"
     rank, world = dist.get_rank(), dist.get_world_size()
+    H = ctx.params.data_height if height is None else height
+    if not fused:
+        r0, r1 = row_stripe(rank, world, H)
+        on_gpu = dist.get_backend() == "nccl"
+
+        def _cb(user, ptr):
+            try:
+                a = np.ctypeslib.as_array(ptr, shape=(32,))
+                t = torch.from_numpy(a.copy())
+                if on_gpu:
+                    t = t.cuda()
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                a[:] = t.cpu().numpy()
+                return 0
+            except Exception:  # noqa: BLE001
+                return 1
+
+        ctx._allreduce_cb = ALLREDUCE_FN(_cb)  # keep the thunk alive as long as the context
+        ctx.check(api.lib().sb_comm_set_callback(ctx.h, C.cast(ctx._allreduce_cb, C.c_void_p), None, r0, r1),
+                  "comm_set_callback")
+        dist.barrier()
+        return r0, r1
     h = np.zeros(64, np.uint8)
     ctx.check(api.lib().sb_comm_export(ctx.h, C.c_void_p(h.ctypes.data)), "comm_export")
     dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
@@ -38,7 +72,6 @@ def setup_comm(ctx, dist, height=None):
     gathered = [torch.zeros_like(mine) for _ in range(world)]
     dist.all_gather(gathered, mine)
     allh = np.ascontiguousarray(np.concatenate([g.cpu().numpy() for g in gathered]))
-    H = ctx.params.data_height if height is None else height
     r0, r1 = row_stripe(rank, world, H)
     ctx.check(api.lib().sb_comm_init(ctx.h, rank, world, C.c_void_p(allh.ctypes.data), r0, r1), "comm_init")
     dist.barrier()
