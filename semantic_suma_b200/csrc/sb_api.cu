@@ -566,6 +566,13 @@ int icp_minimize_enqueue(sb_ctx* c, const sb_frame* data, const sb_frame* model,
     r0 = c->row_begin;
     r1 = c->row_end;
   }
+  if (const char* dr = getenv("SUMA_B200_DEBUG_ROWS")) {  // debugging aid: persistent kernel on a row sub-range
+    int a0 = 0, a1 = 0;
+    if (sscanf(dr, "%d,%d", &a0, &a1) == 2 && a0 >= 0 && a1 <= c->kp.H && a0 < a1) {
+      r0 = a0;
+      r1 = a1;
+    }
+  }
   IcpArgs a = icp_args(c, data, model, max_distance, max_angle_deg, r0, r1, semantics);
   Mat4d T;
   memcpy(T.m, T0, sizeof(T.m));
@@ -941,12 +948,12 @@ int sb_create(const sb_params* p, int device, sb_ctx** out) {
     }
     if (getenv("SUMA_B200_ICP_TRACE")) {
       if (std::string(getenv("SUMA_B200_ICP_TRACE")) == "host") {  // host-mapped: readable while a kernel hangs
-        cudaHostAlloc(&c->icp_trace_host, 16 * 16 * 8, cudaHostAllocMapped);
-        memset(c->icp_trace_host, 0, 16 * 16 * 8);
+        cudaHostAlloc(&c->icp_trace_host, 4096 * 8, cudaHostAllocMapped);
+        memset(c->icp_trace_host, 0, 4096 * 8);
         cudaHostGetDevicePointer((void**)&c->icp_trace, c->icp_trace_host, 0);
       } else {
-        cudaMalloc(&c->icp_trace, 16 * 16 * 8);
-        cudaMemset(c->icp_trace, 0, 16 * 16 * 8);
+        cudaMalloc(&c->icp_trace, 4096 * 8);
+        cudaMemset(c->icp_trace, 0, 4096 * 8);
       }
     }
   }
@@ -1395,6 +1402,12 @@ int sb_get_statistics(sb_ctx* c, double stats[16]) {
   return SB_OK;
 }
 
+int sb_debug_icp_block_states(sb_ctx* c, uint64_t* out1024) {  // debugging aid: per-block progress (host-mapped trace)
+  if (!c || !out1024 || !c->icp_trace_host) return SB_ERR_STATE;
+  memcpy(out1024, c->icp_trace_host + 1024, 2048 * 8);
+  return SB_OK;
+}
+
 // debugging aid: %globaltimer stamps of the last sb_icp_minimize (16 iterations x 16 slots), see sb_icp.cu SB_TR
 int sb_debug_icp_trace(sb_ctx* c, uint64_t* out256) {
   if (!c || !out256 || !c->icp_trace) return SB_ERR_STATE;
@@ -1480,7 +1493,7 @@ int sb_comm_init(sb_ctx* c, int rank, int nranks, const uint8_t* handles, int ro
   SB_CUDA(c, cudaMemset(c->comm_epoch, 0, 64));
   c->row_begin = row_begin;
   c->row_end = row_end;
-  c->comm_on = nranks > 1;
+  c->comm_on = nranks > 1 || getenv("SUMA_B200_SELF_COMM") != nullptr;  // 1-rank loop-back: exercises the exchange on one GPU
   return SB_OK;
 }
 

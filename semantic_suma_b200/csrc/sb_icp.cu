@@ -614,6 +614,8 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_icp_persistent(KParams kp, I
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                             \
     trace[it * 16 + (slot)] = t__;                                                      \
   }
+#define SB_BS(phase)                                                              \
+  if (trace && threadIdx.x == 0) ((volatile unsigned long long*)trace)[1024 + blockIdx.x] = (unsigned long long)(it * 16u + (phase));
   __shared__ GnShared sh;
   __shared__ bool is_last;
   __shared__ double s_pose[16];
@@ -626,18 +628,26 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_icp_persistent(KParams kp, I
     if (warp == 0) {
       if (it > 0) {
         if (lane == 0) {
+          if (trace) ((volatile unsigned long long*)trace)[2048 + blockIdx.x] = (unsigned long long)(it * 16u + 9u);
           while (*(volatile unsigned int*)epoch_flag != it) {
           }
+          if (trace) ((volatile unsigned long long*)trace)[2048 + blockIdx.x] = (unsigned long long)(it * 16u + 10u);
           __threadfence();
+          if (trace) ((volatile unsigned long long*)trace)[2048 + blockIdx.x] = (unsigned long long)(it * 16u + 11u);
         }
         __syncwarp();
       }
       if (lane < 16) s_pose[lane] = *(volatile double*)&st->pose[lane];
       if (lane == 16) s_k = *(volatile int*)&st->k;
       if (lane == 17) s_done = *(volatile int*)&st->done;
+      if (trace && lane == 0) ((volatile unsigned long long*)trace)[2048 + blockIdx.x] = (unsigned long long)(it * 16u + 12u);
     }
     __syncthreads();
-    if (s_done) break;
+    if (s_done) {
+      SB_BS(15)
+      break;
+    }
+    SB_BS(1)
     SB_TR(0)
     float M[16];
 #pragma unroll
@@ -646,9 +656,11 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_icp_persistent(KParams kp, I
     Acc acc;
     icp_accumulate(kp, a, M, k, acc);
     __syncthreads();
+    SB_BS(2)
     SB_TR(1)
     block_reduce_to_replica(acc, slots);
     __syncthreads();
+    SB_BS(3)
     SB_TR(2)
     if (threadIdx.x == 0) {
       __threadfence();  // cumulative: orders this block's slot stores (observed through the barrier) before the ticket
@@ -656,6 +668,7 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_icp_persistent(KParams kp, I
       is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
+    SB_BS(4)
     SB_TR(3)
     if (is_last && warp == 0) {
       SB_TR(8)
@@ -665,7 +678,9 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_icp_persistent(KParams kp, I
       double last_error = 0.0;
       if (lane == 16) last_error = *(volatile double*)&st->last_error;
       last_error = __shfl_sync(0xffffffffu, last_error, 16);
-      if (cd.nranks > 1) raw = comm_allreduce32_warp(cd, raw, lane, trace);
+      SB_BS(5)
+      if (cd.epoch) raw = comm_allreduce32_warp(cd, raw, lane, trace);
+      SB_BS(6)
       if (lane < 16) sh.P[lane] = s_pose[lane];
       int hl = (int)it;  // one pose has been pushed per completed iteration
       if (lane < 16) st->history[hl * 16 + lane] = s_pose[lane];  // history_.push_back(Tk_)
@@ -696,10 +711,16 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_icp_persistent(KParams kp, I
       __threadfence();
       __syncwarp();
       if (lane == 0) atomicExch(epoch_flag, it + 1u);
+      SB_BS(8)
       SB_TR(11)
     }
+    // The last block's other warps wait for the step HERE, not at the loop-top barrier: with a peer exchange in the step
+    // (tens of microseconds) the version that let them run ahead to the next iteration's barrier deadlocked on a
+    // 2-GPU box; is_last is block-uniform, so this barrier is too.
+    if (is_last) __syncthreads();
   }
 #undef SB_TR
+#undef SB_BS
 }
 
 int icp_persistent_max_blocks(int sm_count) {

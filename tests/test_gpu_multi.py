@@ -1,8 +1,10 @@
 """Row-striped Jacobian reduction over two ranks (BASELINE.json configs[3]): every rank reduces its rows,
 the 32 int64 sums are all-reduced, and every rank must end with exactly the pose a single GPU computes.
 
-With two GPUs the ranks use one GPU each and NCCL; on a one-GPU box both ranks share the GPU and exchange over gloo
-(the host-callback exchange has no in-kernel waiting, so two processes can share a device)."""
+Two exchanges are covered: the host-callback baseline (torch.distributed all-reduce once per iteration; on a one-GPU
+box both ranks share the GPU and use gloo, as there is no in-kernel waiting) and the fused one, where the last block of
+the persistent Gauss-Newton kernel exchanges the sums over CUDA-IPC peer memory (needs two GPUs: the kernels of the two
+ranks must run at the same time)."""
 import os
 import socket
 import sys
@@ -21,7 +23,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q, two_gpus):
+def _worker(rank, world, port, q, two_gpus, fused, size, n_scans, iters):
     try:
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -37,8 +39,8 @@ def _worker(rank, world, port, q, two_gpus):
             dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
         else:
             dist.init_process_group("gloo", rank=rank, world_size=world)
-        pp = api.default_params(**sized(900), max_iterations=8, stopping_threshold=0.0, delta=0.0)
-        sc, _ = scans(900, n=4)
+        pp = api.default_params(**sized(size), max_iterations=iters, stopping_threshold=0.0, delta=0.0)
+        sc, _ = scans(size, n=n_scans)
         solo = api.SurfelMapping(pp, device=dev)
         for s in sc:
             solo.processScan(*s)
@@ -46,7 +48,7 @@ def _worker(rank, world, port, q, two_gpus):
         ref_n = solo.getMap().size()
         solo.ctx.close()
         sl = api.SurfelMapping(pp, device=dev)
-        r0, r1 = stripes.setup_comm(sl.ctx, dist, fused=False)
+        r0, r1 = stripes.setup_comm(sl.ctx, dist, fused=fused)
         for s in sc:
             sl.processScan(*s)
         pose = sl.getCurrentPose()
@@ -60,15 +62,12 @@ def _worker(rank, world, port, q, two_gpus):
         raise
 
 
-@pytest.mark.gpu
-def test_two_rank_striped_icp_is_bit_identical():
-    from semantic_suma_b200 import api
-    two_gpus = api.lib().sb_device_count() >= 2
+def _run_two_ranks(fused, two_gpus, size=900, n_scans=4, iters=8):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, two_gpus)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, two_gpus, fused, size, n_scans, iters)) for r in range(2)]
     for p in procs:
         p.start()
     try:
@@ -85,3 +84,18 @@ def test_two_rank_striped_icp_is_bit_identical():
     assert got[0][1] and got[1][1], "striped result differs from the single-GPU result: %r %r" % (got[0][2], got[1][2])
     assert got[0][3] == got[1][3]
     assert got[0][2] == (0, 32) and got[1][2] == (32, 64)
+
+
+@pytest.mark.gpu
+def test_two_rank_striped_icp_is_bit_identical():
+    from semantic_suma_b200 import api
+    _run_two_ranks(fused=False, two_gpus=api.lib().sb_device_count() >= 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size,n_scans,iters", [(900, 4, 8), (2048, 6, 10)])
+def test_two_gpu_fused_peer_allreduce_is_bit_identical(size, n_scans, iters):
+    from semantic_suma_b200 import api
+    if api.lib().sb_device_count() < 2:
+        pytest.skip("the in-kernel peer exchange needs two GPUs")
+    _run_two_ranks(fused=True, two_gpus=True, size=size, n_scans=n_scans, iters=iters)
