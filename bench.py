@@ -155,7 +155,7 @@ def run_native(args, w, rank, world, local_rank):
     ctx = slam.ctx
     if dist is not None and args.striped:
         from semantic_suma_b200 import stripes
-        stripes.setup_comm(ctx, dist)
+        stripes.setup_comm(ctx, dist, fused=(args.comm == "fused"))
     stream = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     sem = w["semantic"]
@@ -221,7 +221,7 @@ def run_native(args, w, rank, world, local_rank):
     # per-kernel device time with CUDA events on the launching stream, over the same timed frames
     roofline = None
     kernel_table = {}
-    if rank == 0 and not args.no_profile:
+    if (rank == 0 or args.striped) and not args.no_profile:  # striped: every rank must walk the same scans
         slam.reset()
         for f in range(args.warmup):
             p, l, q = dev[f]
@@ -274,7 +274,8 @@ def run_native(args, w, rank, world, local_rank):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "range_image": "%dx%d" % (w["height"], w["width"]),
                        "icp_iterations": w["iters"], "semantic": sem, "sequences": 1 if args.striped else world,
-                       "parallelism": ("k5-row-stripes-x%d (peer-memory all-reduce in-kernel)" % world) if args.striped
+                       "parallelism": ("k5-row-stripes-x%d (%s)" % (world, "peer-memory all-reduce in-kernel" if args.comm == "fused"
+                                                                   else "torch.distributed all-reduce per iteration")) if args.striped
                        else "one sequence per GPU",
                        "surfels_end": int(surfels), "pose_drift_m": round(drift, 4),
                        "l2": "flushed between timed steps (256 MiB memset, untimed)",
@@ -297,8 +298,9 @@ def run_native(args, w, rank, world, local_rank):
 
 
 def cpu_baseline(w, scans, budget_s=15.0, max_frames=None):
-    """the CPU restatement of the reference (oracle/, single thread) on a bounded sample of the same scans"""
+    """the CPU restatement of the reference (oracle/, OpenMP over all host cores) on a bounded sample of the same scans"""
     from oracle import oracle as O
+    threads = O.set_threads(0)
     po = O.default_params(**param_kwargs(w))
     sl = O.Slam(po)
     t0 = time.time()
@@ -309,19 +311,20 @@ def cpu_baseline(w, scans, budget_s=15.0, max_frames=None):
         if time.time() - t0 > budget_s or (max_frames and n >= max_frames):
             break
     dt = time.time() - t0
-    return {"value": round(n / dt, 3), "unit": "scans/s", "cores": 1, "kind": "port",
-            "sample": "first %d scans of the same synthetic sequence (map grows from empty), oracle/ C port, 1 thread"
-                      % n, "seconds": round(dt, 2), "host_cpus": os.cpu_count()}
+    return {"value": round(n / dt, 3), "unit": "scans/s", "cores": threads, "kind": "port",
+            "sample": "first %d scans of the same synthetic sequence (map grows from empty), oracle/ C port, "
+                      "%d OpenMP threads" % (n, threads), "seconds": round(dt, 2), "host_cpus": os.cpu_count()}
 
 
 def run_reference(args, w, rank, world):
     """--impl reference: the reference has no CPU (or buildable GL) path in this environment; the arm times the
-    oracle's restatement of it on the host cores (single-threaded C) on the same workload."""
+    oracle's restatement of it on all host cores (C + OpenMP, thread-count independent results) on the same workload."""
     if rank != 0:
         return None
     n_frames = args.warmup + args.steps
     scans = generate_scans(w, n_frames, seed=1337)
     from oracle import oracle as O
+    threads = O.set_threads(0)
     po = O.default_params(**param_kwargs(w))
     sl = O.Slam(po)
     for f in range(args.warmup):
@@ -343,8 +346,8 @@ def run_reference(args, w, rank, world):
                    "icp_iterations": w["iters"], "semantic": w["semantic"],
                    "note": "reference OpenGL path not runnable here (no GL/EGL, glow/gtsam/rangenet_lib absent); "
                            "this is the CPU restatement in oracle/ (kind=port)"},
-        "cpu_baseline": {"value": round(v, 3), "unit": "scans/s", "cores": 1, "kind": "port",
-                         "sample": "%d scans after %d warm-up scans, single thread" % (done, args.warmup),
+        "cpu_baseline": {"value": round(v, 3), "unit": "scans/s", "cores": threads, "kind": "port",
+                         "sample": "%d scans after %d warm-up scans, %d OpenMP threads" % (done, args.warmup, threads),
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": round(v, 3), "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -362,6 +365,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="hdl64_2048_geometric", choices=sorted(WORKLOADS))
+    ap.add_argument("--comm", choices=["fused", "callback"], default="fused",
+                    help="--striped exchange: in-kernel over peer memory (default) or the torch.distributed baseline")
     ap.add_argument("--striped", action="store_true",
                     help="N > 1: all ranks process the SAME sequence, the K5 reduction is striped over image rows and "
                          "all-reduced inside the kernel over peer memory (BASELINE.json configs[3]); strong scaling")

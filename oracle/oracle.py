@@ -81,7 +81,13 @@ def lib():
         L.orc_slam_timestamp.restype = C.c_uint32
         L.orc_icp_minimize.restype = C.c_int
         L.orc_gn_step.restype = C.c_int
+        L.orc_set_threads.restype = C.c_int; L.orc_set_threads.argtypes = [C.c_int]
     return _lib
+
+
+def set_threads(n=0):
+    """host threads for the oracle's loops (0 = all cores, capped at 64); results do not depend on it"""
+    return int(lib().orc_set_threads(int(n)))
 
 
 def _p(a, t=C.c_float):

@@ -66,6 +66,9 @@ typedef struct orc_surfel {
 } orc_surfel;
 
 void orc_default_params(orc_params* p); /* config/default.xml */
+/* host threads used by the oracle's loops (OpenMP); 0 = all the machine offers (capped at 64). Results are
+ * bit-identical for every thread count. Returns the count now in effect. */
+int orc_set_threads(int n);
 
 /* ---- scalar functions exported for unit tests ---- */
 float orc_t_atan2f(float y, float x);

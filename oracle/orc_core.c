@@ -7,6 +7,29 @@
 #include <stdlib.h>
 
 /* config/default.xml:7-83 */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+static int g_orc_threads = 0; /* 0 = not chosen yet */
+int orc_threads(void) {
+  if (g_orc_threads <= 0) orc_set_threads(0);
+  return g_orc_threads;
+}
+int orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n <= 0) {
+    const char* e = getenv("ORC_THREADS");
+    n = e ? atoi(e) : omp_get_num_procs();
+  }
+  if (n < 1) n = 1;
+  if (n > 64) n = 64;
+#else
+  n = 1;
+#endif
+  g_orc_threads = n;
+  return n;
+}
+
 void orc_default_params(orc_params* p) {
   memset(p, 0, sizeof(*p));
   p->data_width = 900; p->data_height = 64;
@@ -55,19 +78,13 @@ static void orc_k1_project(const orc_params* p, const float* pts4, const float* 
   memset(vertex_map, 0, P * 4 * sizeof(float));
   memset(semantic_map, 0, P * 4 * sizeof(float));
 
+  /* phase 1 (all host threads): the per-point projection; phase 2 (buffer order): the depth test and the writes */
+  int32_t* ppix = (int32_t*)malloc((size_t)(n ? n : 1) * sizeof(int32_t));
+  uint32_t* pd24 = (uint32_t*)malloc((size_t)(n ? n : 1) * sizeof(uint32_t));
+#pragma omp parallel for schedule(static) num_threads(orc_threads())
   for (uint32_t i = 0; i < n; ++i) {
     orc_v3 pos = orc_mk3(pts4[4 * i + 0], pts4[4 * i + 1], pts4[4 * i + 2]);
-    /* Q1: attribute pointers start 16 / 20 bytes into the stride-4 label / prob buffers (Preprocessing.cpp:142-145);
-     * reads past the end return 0 (robust buffer access). */
-    float label = 0.0f, prob = 0.0f;
-    if (labels) {
-      uint32_t li = p->label_offset_quirk ? i + 4 : i;
-      if (li < n) label = labels[li];
-    }
-    if (probs) {
-      uint32_t pi = p->label_offset_quirk ? i + 5 : i;
-      if (pi < n) prob = probs[pi];
-    }
+    ppix[i] = -1;
     float d = orc_len3(pos);
     float yaw = orc_atan2f(pos.y, pos.x);
     float pitch = -orc_asinf(pos.z / d);
@@ -78,21 +95,39 @@ static void orc_k1_project(const orc_params* p, const float* pts4, const float* 
     float fy = floorf((0.5f * (y + 1.0f)) * (float)H);                       /* .vert:89 */
     if (!(fx >= 0.0f && fx < (float)W && fy >= 0.0f && fy < (float)H)) continue; /* clipped */
     if (!(z >= -1.0f && z <= 1.0f)) continue;
-    uint32_t d24 = orc_depth24(0.5f * z + 0.5f);
-    size_t pix = (size_t)(int)fy * W + (size_t)(int)fx;
+    pd24[i] = orc_depth24(0.5f * z + 0.5f);
+    ppix[i] = (int32_t)((size_t)(int)fy * W + (size_t)(int)fx);
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    if (ppix[i] < 0) continue;
+    const size_t pix = (size_t)ppix[i];
+    const uint32_t d24 = pd24[i];
     if (d24 < depth[pix]) { /* GL_LESS, primitives in buffer order */
       depth[pix] = d24;
+      /* Q1: attribute pointers start 16 / 20 bytes into the stride-4 label / prob buffers (Preprocessing.cpp:142-145);
+       * reads past the end return 0 (robust buffer access). */
+      float label = 0.0f, prob = 0.0f;
+      if (labels) {
+        uint32_t li = p->label_offset_quirk ? i + 4 : i;
+        if (li < n) label = labels[li];
+      }
+      if (probs) {
+        uint32_t pi = p->label_offset_quirk ? i + 5 : i;
+        if (pi < n) prob = probs[pi];
+      }
       float* v = vertex_map + 4 * pix;
       if (isfirst && orc_is_movable(label)) { /* .vert:95-102 */
         v[0] = v[1] = v[2] = v[3] = 0.0f;
       } else {
-        v[0] = pos.x; v[1] = pos.y; v[2] = pos.z; v[3] = 1.0f;
+        v[0] = pts4[4 * i + 0]; v[1] = pts4[4 * i + 1]; v[2] = pts4[4 * i + 2]; v[3] = 1.0f;
       }
-      float* s = semantic_map + 4 * pix;
+      float* sm = semantic_map + 4 * pix;
       float l = label / 255.0f; /* .frag:20 */
-      s[0] = l; s[1] = l; s[2] = l; s[3] = prob;
+      sm[0] = l; sm[1] = l; sm[2] = l; sm[3] = prob;
     }
   }
+  free(ppix);
+  free(pd24);
   free(depth);
 }
 
@@ -109,6 +144,7 @@ static inline const float* orc_tex_wrapx(const float* img, int W, int H, int x, 
 static void orc_k2_normals(const orc_params* p, const float* vertex_map, const float* sem_in, float* normal_map,
                            float* eroded) {
   const int W = p->data_width, H = p->data_height;
+#pragma omp parallel for collapse(2) schedule(static) num_threads(orc_threads())
   for (int y = 0; y < H; ++y)
     for (int x = 0; x < W; ++x) {
       size_t pix = (size_t)y * W + x;
@@ -156,6 +192,7 @@ static void orc_k2_normals(const orc_params* p, const float* vertex_map, const f
 static void orc_k3_floodfill(const orc_params* p, const float* vertex_map, const float* eroded, float* semantic_map) {
   const int W = p->data_width, H = p->data_height;
   static const int dx[4] = {1, 0, -1, 0}, dy[4] = {0, 1, 0, -1};
+#pragma omp parallel for collapse(2) schedule(static) num_threads(orc_threads())
   for (int y = 0; y < H; ++y)
     for (int x = 0; x < W; ++x) {
       size_t pix = (size_t)y * W + x;
@@ -341,9 +378,11 @@ void orc_icp_jacobian(const orc_params* p, const float* data_v, const float* dat
   int64_t acc[32];
   memset(acc, 0, sizeof(acc));
   const int W = p->data_width;
-  orc_k5_terms t;
+  /* integer (Q33.30) sums: the reduction order does not matter */
+#pragma omp parallel for collapse(2) schedule(static) reduction(+ : acc[:32]) num_threads(orc_threads())
   for (int y = row_begin; y < row_end; ++y)
     for (int x = 0; x < W; ++x) {
+      orc_k5_terms t;
       if (!orc_k5_pixel(p, Mf, data_v, data_n, data_s, model_v, model_n, model_s, x, y, iteration, dthr, athr, &t)) {
         acc[31] += 1; /* invalid, .geom:198 */
         continue;

@@ -40,4 +40,9 @@ static inline float orc_pack_rgb(float r, float g, float b) {
   return (float)rgb;
 }
 
+/* Host threads (OpenMP). Every parallel loop of the oracle is written so that its result does not depend on the
+ * thread count: integer sums, per-pixel / per-surfel independent work, and depth-tested rasterisation into per-thread
+ * targets that are merged in buffer order (orc_map.c). orc_set_threads(1) runs the plain sequential code. */
+int orc_threads(void);
+
 #endif

@@ -6,6 +6,9 @@
 
 #include <stdio.h>
 #include <stdlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define ORC_MAX_SURFELS (2048u * 2048u) /* SurfelMap.h:87 */
 #define ORC_MAX_POSES 10000u            /* SurfelMap.h:205 */
@@ -38,6 +41,13 @@ struct orc_map {
   uint32_t n_extraction, cap_extraction;
   orc_tile* tiles;
   uint32_t n_tiles, cap_tiles;
+  /* per-thread raster targets + chunk bookkeeping of the multi-threaded passes (see render_pass / chunked_compact) */
+  int mt_threads;
+  size_t mt_pixels;
+  uint32_t** mt_depth;
+  uint32_t** mt_index;
+  orc_frame* mt_frame;
+  orc_surfel* scratch2;
   /* derived parameters (SurfelMap.cpp:336-457) */
   float pixel_size, p_unstable, log_prior, log_unstable, radconf_angle_thresh, update_angle_thresh;
 };
@@ -49,7 +59,11 @@ static void frame_alloc(orc_frame* f, size_t P) {
 }
 static void frame_free(orc_frame* f) { free(f->v); free(f->n); free(f->s); }
 static void frame_clear(orc_frame* f, size_t P) {
-  memset(f->v, 0, P * 16); memset(f->n, 0, P * 16); memset(f->s, 0, P * 16);
+#pragma omp parallel for schedule(static) num_threads(orc_threads())
+  for (size_t r = 0; r < 64; ++r) {
+    size_t b = P * 16 * r / 64, e = P * 16 * (r + 1) / 64;
+    memset((char*)f->v + b, 0, e - b); memset((char*)f->n + b, 0, e - b); memset((char*)f->s + b, 0, e - b);
+  }
 }
 
 static float deg2rad_f(float d) { return d * (float)(3.14159265358979323846 / 180.0); }
@@ -100,6 +114,8 @@ void orc_map_destroy(orc_map* m) {
   free(m->surfels); free(m->scratch); free(m->poses); free(m->poses_inv);
   frame_free(&m->oldf); frame_free(&m->newf); frame_free(&m->compf);
   free(m->rdepth); free(m->idepth); free(m->index_map); free(m->radius_map); free(m->integrated);
+  for (int t = 0; t < m->mt_threads; ++t) { free(m->mt_depth[t]); free(m->mt_index[t]); frame_free(&m->mt_frame[t]); }
+  free(m->mt_depth); free(m->mt_index); free(m->mt_frame); free(m->scratch2);
   free(m);
 }
 
@@ -234,15 +250,15 @@ static void raster_tri(orc_rctx* rc, orc_rvert A, orc_rvert B, orc_rvert C) {
 }
 
 /* one glDrawArrays(GL_POINTS, surfels_) with the render program */
-static void render_pass(orc_map* m, const float inv_pose[16], float conf_thr, int t_thr, int render_old, int lequal,
-                        uint32_t* depth, orc_frame* out) {
+static void render_range(orc_map* m, uint32_t k_begin, uint32_t k_end, const float inv_pose[16], float conf_thr,
+                         int t_thr, int render_old, int lequal, uint32_t* depth, orc_frame* out) {
   const orc_params* p = &m->p;
   const int W = p->model_width, H = p->model_height;
   const float fov_up = fabsf(p->model_fov_up), fov = fabsf(p->model_fov_up) + fabsf(p->model_fov_down);
   const float mind = p->model_min_depth, maxd = p->model_max_depth;
   orc_rctx rc;
   rc.m = m; rc.depth = depth; rc.out = out; rc.lequal = lequal;
-  for (uint32_t k = 0; k < m->n; ++k) {
+  for (uint32_t k = k_begin; k < k_end; ++k) {
     const orc_surfel* s = &m->surfels[k];
     int c = surfel_pose_index(s);
     float T[16];
@@ -290,12 +306,77 @@ static void render_pass(orc_map* m, const float inv_pose[16], float conf_thr, in
 
 static void depth_clear(uint32_t* d, size_t P) { for (size_t i = 0; i < P; ++i) d[i] = ORC_DEPTH_CLEAR; }
 
+/* per-thread raster targets, (re)allocated for the larger of the two image sizes */
+static void mt_prepare(orc_map* m, int T) {
+  size_t Pm = (size_t)m->p.model_width * m->p.model_height, Pd = (size_t)m->p.data_width * m->p.data_height;
+  size_t P = Pm > Pd ? Pm : Pd;
+  if (m->mt_threads >= T && m->mt_pixels >= P) return;
+  for (int t = 0; t < m->mt_threads; ++t) { free(m->mt_depth[t]); free(m->mt_index[t]); frame_free(&m->mt_frame[t]); }
+  free(m->mt_depth); free(m->mt_index); free(m->mt_frame);
+  m->mt_depth = (uint32_t**)calloc((size_t)T, sizeof(uint32_t*));
+  m->mt_index = (uint32_t**)calloc((size_t)T, sizeof(uint32_t*));
+  m->mt_frame = (orc_frame*)calloc((size_t)T, sizeof(orc_frame));
+  for (int t = 0; t < T; ++t) {
+    m->mt_depth[t] = (uint32_t*)malloc(P * 4);
+    m->mt_index[t] = (uint32_t*)malloc(P * 4);
+    frame_alloc(&m->mt_frame[t], P);
+  }
+  m->mt_threads = T;
+  m->mt_pixels = P;
+}
+static inline void chunk_of(uint32_t n, int T, int t, uint32_t* b, uint32_t* e) {
+  *b = (uint32_t)(((uint64_t)n * (uint64_t)t) / (uint64_t)T);
+  *e = (uint32_t)(((uint64_t)n * (uint64_t)(t + 1)) / (uint64_t)T);
+}
+
+/* One draw call. With T host threads the surfel buffer is cut into T contiguous chunks; every chunk is rasterised in
+ * buffer order into its own depth/attribute target (cleared above every 24-bit depth), and the targets are merged into
+ * the real one in chunk order with the SAME depth comparison. Because "first (GL_LESS) / last (GL_LEQUAL) fragment of
+ * minimal depth in buffer order" is associative over contiguous chunks, the result is the sequential one bit for bit. */
+static void render_pass(orc_map* m, const float inv_pose[16], float conf_thr, int t_thr, int render_old, int lequal,
+                        uint32_t* depth, orc_frame* out) {
+  const int T = orc_threads();
+  if (T <= 1 || m->n < 4096u) {
+    render_range(m, 0, m->n, inv_pose, conf_thr, t_thr, render_old, lequal, depth, out);
+    return;
+  }
+  const size_t P = (size_t)m->p.model_width * m->p.model_height;
+  mt_prepare(m, T);
+#pragma omp parallel num_threads(T)
+  {
+#ifdef _OPENMP
+    const int t = omp_get_thread_num();
+#else
+    const int t = 0;
+#endif
+    uint32_t b, e;
+    chunk_of(m->n, T, t, &b, &e);
+    memset(m->mt_depth[t], 0xFF, P * 4); /* 0xFFFFFFFF: above every depth24, so "untouched" is recognisable */
+    render_range(m, b, e, inv_pose, conf_thr, t_thr, render_old, lequal, m->mt_depth[t], &m->mt_frame[t]);
+#pragma omp barrier
+#pragma omp for schedule(static)
+    for (size_t pix = 0; pix < P; ++pix) {
+      for (int c = 0; c < T; ++c) {
+        uint32_t d = m->mt_depth[c][pix];
+        if (d == 0xFFFFFFFFu) continue;
+        if (lequal ? (d <= depth[pix]) : (d < depth[pix])) {
+          depth[pix] = d;
+          memcpy(out->v + 4 * pix, m->mt_frame[c].v + 4 * pix, 16);
+          memcpy(out->n + 4 * pix, m->mt_frame[c].n + 4 * pix, 16);
+          memcpy(out->s + 4 * pix, m->mt_frame[c].s + 4 * pix, 16);
+        }
+      }
+    }
+  }
+}
+
 static int t_threshold(const orc_map* m) { return (int)(m->timestamp - ORC_COMPOSE_AGE); } /* SurfelMap.cpp:873 (Q9) */
 
 /* render_compose.frag:26-48 */
 static void compose(const orc_map* m, float* fv, float* fn, float* fs) {
   size_t P = (size_t)m->p.model_width * m->p.model_height;
   const float maxdist = m->p.max_loop_closure_distance;
+#pragma omp parallel for schedule(static) num_threads(orc_threads())
   for (size_t i = 0; i < P; ++i) {
     const float* nv = m->newf.v + 4 * i; const float* nn = m->newf.n + 4 * i; const float* ns = m->newf.s + 4 * i;
     const float* ov = m->oldf.v + 4 * i; const float* on = m->oldf.n + 4 * i; const float* os = m->oldf.s + 4 * i;
@@ -386,14 +467,12 @@ static inline void data_tex(const float* img, int W, int H, float fx, float fy, 
 }
 
 /* K6a gen_indexmap.vert:62-81 */
-static void k6a_indexmap(orc_map* m, const float inv_pose[16]) {
+static void k6a_range(orc_map* m, uint32_t k_begin, uint32_t k_end, const float inv_pose[16], uint32_t* idepth,
+                      uint32_t* index_map) {
   const orc_params* p = &m->p;
   const int W = p->data_width, H = p->data_height;
-  const size_t P = (size_t)W * H;
   const float fov_up = fabsf(p->data_fov_up), fov = fabsf(p->data_fov_up) + fabsf(p->data_fov_down);
-  depth_clear(m->idepth, P);
-  memset(m->index_map, 0, P * 4);
-  for (uint32_t k = 0; k < m->n; ++k) {
+  for (uint32_t k = k_begin; k < k_end; ++k) {
     const orc_surfel* s = &m->surfels[k];
     float T[16];
     orc_mat4_mul_f(inv_pose, m->poses + 16 * surfel_pose_index(s), T);
@@ -408,10 +487,43 @@ static void k6a_indexmap(orc_map* m, const float inv_pose[16]) {
     if (!(zn >= -1.0f && zn <= 1.0f)) continue;
     uint32_t d24 = orc_depth24(0.5f * zn + 0.5f);
     size_t pix = (size_t)(int)fy * W + (size_t)(int)fx;
-    if (d24 < m->idepth[pix]) {
-      m->idepth[pix] = d24;
-      m->index_map[pix] = k + 1;
+    if (d24 < idepth[pix]) {
+      idepth[pix] = d24;
+      index_map[pix] = k + 1;
     }
+  }
+}
+static void k6a_indexmap(orc_map* m, const float inv_pose[16]) {
+  const size_t P = (size_t)m->p.data_width * m->p.data_height;
+  const int T = orc_threads();
+  depth_clear(m->idepth, P);
+  memset(m->index_map, 0, P * 4);
+  if (T <= 1 || m->n < 4096u) {
+    k6a_range(m, 0, m->n, inv_pose, m->idepth, m->index_map);
+    return;
+  }
+  mt_prepare(m, T); /* chunks in buffer order, merged with GL_LESS in chunk order: see render_pass */
+#pragma omp parallel num_threads(T)
+  {
+#ifdef _OPENMP
+    const int t = omp_get_thread_num();
+#else
+    const int t = 0;
+#endif
+    uint32_t b, e;
+    chunk_of(m->n, T, t, &b, &e);
+    memset(m->mt_depth[t], 0xFF, P * 4);
+    k6a_range(m, b, e, inv_pose, m->mt_depth[t], m->mt_index[t]);
+#pragma omp barrier
+#pragma omp for schedule(static)
+    for (size_t pix = 0; pix < P; ++pix)
+      for (int c = 0; c < T; ++c) {
+        uint32_t d = m->mt_depth[c][pix];
+        if (d != 0xFFFFFFFFu && d < m->idepth[pix]) {
+          m->idepth[pix] = d;
+          m->index_map[pix] = m->mt_index[c][pix];
+        }
+      }
   }
 }
 
@@ -419,6 +531,7 @@ static void k6a_indexmap(orc_map* m, const float inv_pose[16]) {
 static void k6b_radius(orc_map* m, const float* fv, const float* fn) {
   const orc_params* p = &m->p;
   const size_t P = (size_t)p->data_width * p->data_height;
+#pragma omp parallel for schedule(static) num_threads(orc_threads())
   for (size_t i = 0; i < P; ++i) {
     const float* V = fv + 4 * i; const float* N = fn + 4 * i;
     float* o = m->radius_map + 4 * i;
@@ -497,7 +610,7 @@ static int k6c_surfel(orc_map* m, uint32_t k, const float pose[16], const float 
       /* :219 integrated flag: a point at (pixel, 2z-1) through clipping + depth test GL_LESS */
       float zn = 2.0f * z - 1.0f;
       if (zn >= -1.0f && zn <= 1.0f && orc_depth24(0.5f * zn + 0.5f) < ORC_DEPTH_CLEAR)
-        m->integrated[(size_t)(int)iy * W + (size_t)(int)ix] = 1;
+        __atomic_store_n(&m->integrated[(size_t)(int)iy * W + (size_t)(int)ix], (uint8_t)1, __ATOMIC_RELAXED);
       float confidence = old_conf + new_conf;
       out->confidence = confidence;
       out->timestamp = (uint32_t)timestamp;
@@ -669,25 +782,64 @@ void orc_map_update(orc_map* m, const float pose[16], const float* fv, const flo
   /* K6c */
   memset(m->integrated, 0, P);
   uint32_t nu = 0;
-  for (uint32_t k = 0; k < m->n; ++k) {
-    orc_surfel o;
-    if (k6c_surfel(m, k, pose, inv_pose, fv, fn, fs, &o)) m->scratch[nu++] = o;
+  const int T = orc_threads();
+  if (T <= 1 || m->n < 4096u) {
+    for (uint32_t k = 0; k < m->n; ++k) {
+      orc_surfel o;
+      if (k6c_surfel(m, k, pose, inv_pose, fv, fn, fs, &o)) m->scratch[nu++] = o;
+    }
+  } else {
+    /* ordered stream compaction (transform feedback order): every thread packs its contiguous chunk in place in a
+     * second buffer, the chunk counts are prefix-summed, the chunks are copied behind one another */
+    uint32_t cnt[64], off[65];
+    if (!m->scratch2) m->scratch2 = (orc_surfel*)malloc(sizeof(orc_surfel) * ORC_MAX_SURFELS);
+#pragma omp parallel num_threads(T)
+    {
+#ifdef _OPENMP
+      const int t = omp_get_thread_num();
+#else
+      const int t = 0;
+#endif
+      uint32_t b, e, c = 0;
+      chunk_of(m->n, T, t, &b, &e);
+      for (uint32_t k = b; k < e; ++k) {
+        orc_surfel o;
+        if (k6c_surfel(m, k, pose, inv_pose, fv, fn, fs, &o)) m->scratch2[b + c++] = o;
+      }
+      cnt[t] = c;
+#pragma omp barrier
+#pragma omp single
+      {
+        off[0] = 0;
+        for (int i = 0; i < T; ++i) off[i + 1] = off[i] + cnt[i];
+      }
+      memcpy(m->scratch + off[t], m->scratch2 + b, sizeof(orc_surfel) * (size_t)c);
+    }
+    nu = off[T];
   }
   m->n_updated = nu;
   /* K6d gen_surfels.vert:38-52 + .geom:109-145, pixels in x-major order (SurfelMap.cpp:88-92) */
   uint32_t nn = 0;
   const int timestamp = (int)m->timestamp;
+  /* phase 1 (all host threads): which pixels emit a surfel; phase 2: emission in x-major order */
+  uint8_t* emit = (uint8_t*)malloc(P);
+#pragma omp parallel for schedule(static) num_threads(orc_threads())
+  for (size_t pix = 0; pix < P; ++pix) {
+    const float* V = fv + 4 * pix; const float* N = fn + 4 * pix; const float* R = m->radius_map + 4 * pix;
+    int invalid = (V[3] < 1.0f) || (N[3] < 1.0f);
+    invalid = invalid || (R[3] < 0.5f);
+    int integrated = m->integrated[pix] != 0;
+    orc_v3 v = orc_mk3(V[0], V[1], V[2]), n = orc_mk3(N[0], N[1], N[2]);
+    orc_v3 view_dir = orc_divs3(orc_neg3(v), orc_len3(v));
+    emit[pix] = (uint8_t)(!invalid && !integrated && (orc_dot3(n, view_dir) > 0.01f));
+  }
   for (int x = 0; x < W; ++x)
     for (int y = 0; y < H; ++y) {
       size_t pix = (size_t)y * W + x;
-      const float* V = fv + 4 * pix; const float* N = fn + 4 * pix; const float* R = m->radius_map + 4 * pix;
-      int invalid = (V[3] < 1.0f) || (N[3] < 1.0f);
-      invalid = invalid || (R[3] < 0.5f);
-      int integrated = m->integrated[pix] != 0;
-      orc_v3 v = orc_mk3(V[0], V[1], V[2]), n = orc_mk3(N[0], N[1], N[2]);
-      orc_v3 view_dir = orc_divs3(orc_neg3(v), orc_len3(v));
-      if (!(!invalid && !integrated && (orc_dot3(n, view_dir) > 0.01f))) continue;
+      if (!emit[pix]) continue;
       if (nu + nn >= ORC_MAX_SURFELS) continue;
+      const float* V = fv + 4 * pix; const float* N = fn + 4 * pix; const float* R = m->radius_map + 4 * pix;
+      orc_v3 v = orc_mk3(V[0], V[1], V[2]), n = orc_mk3(N[0], N[1], N[2]);
       orc_surfel* o = &m->scratch[nu + nn];
       orc_v3 ng = orc_normalize3(n);
       o->x = v.x; o->y = v.y; o->z = v.z; o->radius = R[0];
@@ -699,14 +851,42 @@ void orc_map_update(orc_map* m, const float pose[16], const float* fv, const flo
       if (orc_is_movable(S[0] * 255.0f)) o->confidence = m->log_prior - 0.5f; /* .geom:135-140 */
       ++nn;
     }
+  free(emit);
   m->n_new = nn;
   /* K6e copySurfels, SurfelMap.cpp:667-698 */
   float cx = (float)(2.0 * m->origin_i * p->submap_extent), cy = (float)(2.0 * m->origin_j * p->submap_extent);
   float extent = 2.0f * p->submap_dimension * p->submap_extent + p->submap_extent;
   if (p->partial_extraction && m->n_extraction > 0) extent += 2.0f * p->submap_extent;
   uint32_t no = 0;
-  for (uint32_t k = 0; k < nu + nn; ++k)
-    if (k6e_keep(m, &m->scratch[k], cx, cy, extent)) m->surfels[no++] = m->scratch[k];
+  if (T <= 1 || nu + nn < 4096u) {
+    for (uint32_t k = 0; k < nu + nn; ++k)
+      if (k6e_keep(m, &m->scratch[k], cx, cy, extent)) m->surfels[no++] = m->scratch[k];
+  } else {
+    uint32_t cnt[64], off[65];
+    const uint32_t total = nu + nn;
+    if (!m->scratch2) m->scratch2 = (orc_surfel*)malloc(sizeof(orc_surfel) * ORC_MAX_SURFELS);
+#pragma omp parallel num_threads(T)
+    {
+#ifdef _OPENMP
+      const int t = omp_get_thread_num();
+#else
+      const int t = 0;
+#endif
+      uint32_t b, e, c = 0;
+      chunk_of(total, T, t, &b, &e);
+      for (uint32_t k = b; k < e; ++k)
+        if (k6e_keep(m, &m->scratch[k], cx, cy, extent)) m->scratch2[b + c++] = m->scratch[k];
+      cnt[t] = c;
+#pragma omp barrier
+#pragma omp single
+      {
+        off[0] = 0;
+        for (int i = 0; i < T; ++i) off[i + 1] = off[i] + cnt[i];
+      }
+      memcpy(m->surfels + off[t], m->scratch2 + b, sizeof(orc_surfel) * (size_t)c);
+    }
+    no = off[T];
+  }
   m->n = no;
   update_active_submaps(m, pose);
   m->timestamp += 1;

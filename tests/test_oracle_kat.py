@@ -203,3 +203,34 @@ def test_submap_shift_and_extraction():
     m.update(T, fr[0])
     oi, oj, pending = m.submap_origin()
     assert (oi, oj) == (1, 0) and pending == 8    # 9 tiles queued, one extracted per update (partial extraction)
+
+
+def test_oracle_results_do_not_depend_on_the_thread_count():
+    """The oracle's OpenMP loops (integer sums, per-thread raster targets merged in buffer order, ordered chunk
+    compaction) must reproduce the sequential result bit for bit: it is the checker for the CUDA path and the timed
+    CPU arm of bench.py at the same time."""
+    import hashlib
+    from helpers import scans, sized
+    pp = O.default_params(**sized(450))
+    sc, _ = scans(450, n=6)
+
+    def digest(threads):
+        O.set_threads(threads)
+        s = O.Slam(pp)
+        h = hashlib.sha256()
+        for a in sc:
+            s.process_scan(*a)
+            h.update(s.pose().tobytes())
+        m = O.Map(pp, handle=O.lib().orc_slam_map(s.h))
+        h.update(m.download().tobytes())
+        for k in (0, 1):
+            for img in s.frame(k):
+                h.update(img.tobytes())
+        return h.hexdigest()
+
+    try:
+        ref = digest(1)
+        assert digest(2) == ref
+        assert digest(5) == ref
+    finally:
+        O.set_threads(0)
