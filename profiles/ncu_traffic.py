@@ -1,0 +1,42 @@
+"""Turn `ncu -i <rep> --page raw --csv --print-units base` output into profiles/dram_traffic.json
+(per kernel: launches captured, mean duration, mean DRAM bytes read+written per launch) -- the `roofline.traffic`
+source of bench.py.  Usage: python profiles/ncu_traffic.py raw.csv profiles/dram_traffic.json "<capture command>" """
+import csv, json, re, sys
+
+ALIAS = {"k_icp_persistent": "icp_fused", "k_gen_compact": "gen_surfels"}
+
+
+def main(src, dst, note):
+    rows = list(csv.reader(open(src, newline="")))
+    hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    names = rows[hdr]
+    col = {n: i for i, n in enumerate(names)}
+    out = {}
+    for r in rows[hdr + 2:]:
+        if len(r) < len(names):
+            continue
+        kn = re.sub(r"\(.*", "", r[col["Kernel Name"]]).split("::")[-1]
+        key = ALIAS.get(kn, kn[2:] if kn.startswith("k_") else kn)
+
+        def f(name):
+            try:
+                return float(r[col[name]].replace(",", ""))
+            except (KeyError, ValueError):
+                return float("nan")
+        e = out.setdefault(key, {"kernel": kn, "launches": 0, "ns": 0.0, "rd": 0.0, "wr": 0.0})
+        e["launches"] += 1
+        e["ns"] += f("gpu__time_duration.sum")
+        e["rd"] += f("dram__bytes_read.sum")
+        e["wr"] += f("dram__bytes_write.sum")
+    res = {"source": note, "kernels": {}}
+    for k, e in out.items():
+        n = e["launches"]
+        res["kernels"][k] = {"kernel": e["kernel"], "launches_captured": n, "avg_us_under_ncu": round(e["ns"] / n / 1e3, 2),
+                             "dram_bytes_read_per_launch": round(e["rd"] / n), "dram_bytes_write_per_launch": round(e["wr"] / n),
+                             "dram_bytes_per_launch": round((e["rd"] + e["wr"]) / n)}
+    json.dump(res, open(dst, "w"), indent=1)
+    print(json.dumps(res["kernels"], indent=1))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")

@@ -32,16 +32,17 @@ ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int64))
 def setup_comm(ctx, dist, height=None, fused=None):
     """Row-stripe the K5 reduction of `ctx` over the ranks of `dist`.
 
-    fused=False (default): baseline -- the library calls back once per Gauss-Newton iteration and the 32 int64 sums are
-    all-reduced with torch.distributed (NCCL for CUDA tensors, gloo on the CPU). Exact either way.
-    fused=True (SUMA_B200_FUSED_COMM=1): the exchange runs inside the persistent GN kernel over CUDA-IPC peer memory
-    (sb_comm_init). EXPERIMENTAL in round 1: it deadlocks on a 2-GPU box after a few iterations.
+    fused=True (default with the nccl backend, i.e. one GPU per rank): the exchange runs inside the persistent
+    Gauss-Newton kernel -- its last block stores the 32 int64 sums into every peer's CUDA-IPC mailbox over NVLink and
+    spins on the peers' stamps (sb_comm_init); no host round trip per iteration.
+    fused=False (SUMA_B200_FUSED_COMM=0, and the only choice when ranks share a GPU): baseline -- the library calls back
+    once per iteration and the sums are all-reduced with torch.distributed. Both are exact (integer sums).
     """
     import os
     import torch
     from . import api
     if fused is None:
-        fused = os.environ.get("SUMA_B200_FUSED_COMM", "0") == "1"
+        fused = os.environ.get("SUMA_B200_FUSED_COMM", "1" if dist.get_backend() == "nccl" else "0") == "1"
     rank, world = dist.get_rank(), dist.get_world_size()
     H = ctx.params.data_height if height is None else height
     if not fused:
