@@ -23,13 +23,16 @@ def main(src, dst, note):
                 return float(r[col[name]].replace(",", ""))
             except (KeyError, ValueError):
                 return float("nan")
-        e = out.setdefault(key, {"kernel": kn, "launches": 0, "ns": 0.0, "rd": 0.0, "wr": 0.0})
-        e["launches"] += 1
-        e["ns"] += f("gpu__time_duration.sum")
-        e["rd"] += f("dram__bytes_read.sum")
-        e["wr"] += f("dram__bytes_write.sum")
-    res = {"source": note, "kernels": {}}
+        e = out.setdefault(key, {"kernel": kn, "rows": []})
+        e["rows"].append((f("gpu__time_duration.sum"), f("dram__bytes_read.sum"), f("dram__bytes_write.sum")))
+    res = {"source": note, "filter": "launches shorter than 25% of the kernel's longest captured launch are dropped "
+                                     "(early-exit launches, e.g. the fallback Gauss-Newton launch that finds done=1)",
+           "kernels": {}}
     for k, e in out.items():
+        longest = max(r[0] for r in e["rows"])
+        keep = [r for r in e["rows"] if r[0] >= 0.25 * longest]
+        e["launches"] = len(keep)
+        e["ns"], e["rd"], e["wr"] = (sum(r[i] for r in keep) for i in range(3))
         n = e["launches"]
         res["kernels"][k] = {"kernel": e["kernel"], "launches_captured": n, "avg_us_under_ncu": round(e["ns"] / n / 1e3, 2),
                              "dram_bytes_read_per_launch": round(e["rd"] / n), "dram_bytes_write_per_launch": round(e["wr"] / n),
