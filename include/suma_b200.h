@@ -161,6 +161,7 @@ int sb_map_submap_origin(sb_ctx* ctx, int32_t* i, int32_t* j, uint32_t* pending)
 int sb_process_scan(sb_ctx* ctx, const float* pts4, const float* labels, const float* probs, uint32_t n,
                     int pts_on_device);
 int sb_get_pose(sb_ctx* ctx, double pose[16]);     /* getCurrentPose */
+int sb_get_last_pose(sb_ctx* ctx, double pose[16]); /* getLastPose, core/SurfelMapping.h:63 (pose before the last processScan) */
 int sb_timestamp(sb_ctx* ctx, uint32_t* t);        /* timestamp() */
 int sb_slam_frame(sb_ctx* ctx, int which, sb_frame** out); /* getCurrentFrame / LastFrame / *ModelFrame (borrowed) */
 /* stats[16]: [0] icp iterations [1] F [2] inlier [3] outlier [4] invalid [5] inlier_residual [6] track losses

@@ -223,6 +223,9 @@ class Preprocessing {
  public:
   explicit Preprocessing(const ContextPtr& ctx) : ctx_(ctx) {}
   void setParameters(const ParameterList& params) { ctx_->setParameters(params); }
+  /** Preprocessing.cpp:341 stores the calibration "for semantic map"; no pass of the hot path reads it */
+  template <class Calibration>
+  void setCalibration(const Calibration&) {}
   /** Preprocessing::process(points, frame, labels, probs, timestamp), Preprocessing.cpp:120 */
   void process(const std::vector<float>& points, Frame& frame, const std::vector<float>& labels,
                const std::vector<float>& probs, uint32_t timestamp) {
@@ -389,6 +392,9 @@ class SurfelMap {
  public:
   explicit SurfelMap(const ContextPtr& ctx) : ctx_(ctx) {}
   void setParameters(const ParameterList& params) { ctx_->setParameters(params); }
+  /** colours are a display concern (SurfelMap::setColorMap feeds draw_surfels.*): accepted and ignored */
+  template <class ColorMap>
+  void setColorMap(const ColorMap&) {}
   void reset() { check(sb_reset(ctx_->get()), ctx_->get(), "SurfelMap::reset"); }
   void update(const Matrix4f& pose, Frame& frame) {
     check(sb_map_update(ctx_->get(), pose.m, frame.handle()), ctx_->get(), "SurfelMap::update");
@@ -441,13 +447,34 @@ class SurfelMapping {
   explicit SurfelMapping(const ParameterList& params, int device = 0)
       : ctx_(std::make_shared<Context>(params, device)), map_(std::make_shared<SurfelMap>(ctx_)) {}
   void setParameters(const ParameterList& params) { ctx_->setParameters(params); }
-  void reset() { check(sb_reset(ctx_->get()), ctx_->get(), "SurfelMapping::reset"); }
+  void reset() {
+    check(sb_reset(ctx_->get()), ctx_->get(), "SurfelMapping::reset");
+    trajectory_.clear();
+  }
   /** processScan(scan), SurfelMapping.cpp:175-210 */
   void processScan(const Laserscan& scan) {
     check(sb_process_scan(ctx_->get(), scan.points.data(), scan.labels_float.empty() ? nullptr : scan.labels_float.data(),
                           scan.labels_prob.empty() ? nullptr : scan.labels_prob.data(), scan.size(), 0),
           ctx_->get(), "SurfelMapping::processScan");
+    trajectory_.push_back(getCurrentPose());
   }
+  /** SurfelMapping.cpp:904-907 hands the KITTI calibration to the preprocessor, whose shaders never read it: accepted, unused */
+  template <class Calibration>
+  void setCalibration(const Calibration&) {}
+  template <class ColorMap>
+  void setColorMap(const ColorMap& c) { map_->setColorMap(c); }
+  Matrix4d getLastPose() const {
+    Matrix4d p;
+    sb_get_last_pose(ctx_->get(), p.m);
+    return p;
+  }
+  Frame::Ptr getOldSurfelMap() { return map_->oldMapFrame(); }  // SurfelMapping.h:73
+  Frame::Ptr getNewSurfelMap() { return map_->newMapFrame(); }  // SurfelMapping.h:74
+  /** loop closure and the pose graph stay with the caller: this object never finds or uses a
+   * candidate, and the "optimized" poses are the odometry poses */
+  bool foundLoopClosureCandidate() const { return false; }
+  bool useLoopClosureCandidate() const { return false; }
+  std::vector<Matrix4d> getOptimizedPoses() const { return trajectory_; }
   uint32_t timestamp() const {
     uint32_t t = 0;
     sb_timestamp(ctx_->get(), &t);
@@ -489,6 +516,7 @@ class SurfelMapping {
   }
   ContextPtr ctx_;
   std::shared_ptr<SurfelMap> map_;
+  std::vector<Matrix4d> trajectory_;
 };
 
 }  // namespace suma

@@ -116,7 +116,7 @@ def lib(build_if_missing=True):
         "sb_map_update_debug": [vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32)],
         "sb_map_submap_origin": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(u32)],
         "sb_process_scan": [vp, vp, vp, vp, u32, C.c_int],
-        "sb_get_pose": [vp, pd], "sb_timestamp": [vp, C.POINTER(u32)], "sb_slam_frame": [vp, C.c_int, pv],
+        "sb_get_pose": [vp, pd], "sb_get_last_pose": [vp, pd], "sb_timestamp": [vp, C.POINTER(u32)], "sb_slam_frame": [vp, C.c_int, pv],
         "sb_get_statistics": [vp, pd],
         "sb_comm_export": [vp, vp], "sb_comm_init": [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int],
         "sb_comm_shutdown": [vp],
@@ -147,7 +147,7 @@ EXPORTED_SYMBOLS = [
     "sb_map_render_inactive", "sb_map_render_composed", "sb_map_frame", "sb_icp_jacobian", "sb_icp_unpack",
     "sb_icp_minimize", "sb_se3_exp", "sb_se3_log", "sb_ldlt_solve6", "sb_gn_step", "sb_map_update",
     "sb_map_update_poses", "sb_map_size", "sb_map_timestamp", "sb_map_download", "sb_map_upload", "sb_map_set_pose",
-    "sb_map_update_debug", "sb_map_submap_origin", "sb_process_scan", "sb_get_pose", "sb_timestamp", "sb_slam_frame",
+    "sb_map_update_debug", "sb_map_submap_origin", "sb_process_scan", "sb_get_pose", "sb_get_last_pose", "sb_timestamp", "sb_slam_frame",
     "sb_get_statistics", "sb_comm_export", "sb_comm_init", "sb_comm_shutdown", "sb_comm_set_callback",
     "sb_profile_enable",
     "sb_profile_kernels", "sb_profile_name", "sb_profile_collect",
@@ -531,6 +531,11 @@ class SurfelMapping:
     def getCurrentPose(self):
         a = np.zeros(16)
         lib().sb_get_pose(self.ctx.h, _dp(a))
+        return from_colmajor(a)
+
+    def getLastPose(self):
+        a = np.zeros(16)
+        lib().sb_get_last_pose(self.ctx.h, _dp(a))
         return from_colmajor(a)
 
     def timestamp(self):

@@ -1385,6 +1385,11 @@ int sb_get_pose(sb_ctx* c, double pose[16]) {
   memcpy(pose, c->currentPose, sizeof(c->currentPose));
   return SB_OK;
 }
+int sb_get_last_pose(sb_ctx* c, double pose[16]) {
+  if (!c || !pose) return SB_ERR_INVALID;
+  memcpy(pose, c->lastPose, sizeof(c->lastPose));
+  return SB_OK;
+}
 int sb_timestamp(sb_ctx* c, uint32_t* t) {
   if (!c || !t) return SB_ERR_INVALID;
   *t = c->timestamp;

@@ -74,3 +74,23 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in txt.replace("CPU oracle", "").replace("the oracle", "").lower() or f == "build.py", f
+
+
+def test_cpp_mirror_has_the_reference_class_surface():
+    """include/suma_b200.hpp must offer every hot-path method of the reference's four classes:
+    tests/cpp/mirror_surface.cpp names them all; it only has to compile (and link against the library)."""
+    import shutil
+    import subprocess
+    import tempfile
+    from semantic_suma_b200 import build
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    so = build.build()
+    with tempfile.TemporaryDirectory() as td:
+        obj = os.path.join(td, "mirror_surface.o")
+        subprocess.check_call([gxx, "-std=c++17", "-fPIC", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-c",
+                               os.path.join(ROOT, "tests", "cpp", "mirror_surface.cpp"), "-o", obj])
+        # link into a shared object against the library: every sb_* the header uses must resolve
+        subprocess.check_call([gxx, "-shared", "-o", os.path.join(td, "libsurface.so"), obj, "-L" + os.path.dirname(so),
+                               "-lsuma_b200", "-Wl,--no-undefined"])
