@@ -234,3 +234,53 @@ def test_oracle_results_do_not_depend_on_the_thread_count():
         assert digest(5) == ref
     finally:
         O.set_threads(0)
+
+
+def _ground_plane_frame(p, W, H, height=2.0):
+    """range image of the plane z = -height seen from the origin, built from the pixel-centre beam directions (the
+    inverse of the shaders' projection: x = 0.5 (1 - yaw/pi), y = 1 - (pitch_deg + fov_up) / fov, pitch = -asin(z/d))"""
+    fov_up = abs(p.data_fov_up)
+    fov = fov_up + abs(p.data_fov_down)
+    xs = (np.arange(W) + 0.5) / W
+    ys = (np.arange(H) + 0.5) / H
+    yaw = -(2 * xs - 1) * np.pi
+    elev = -np.deg2rad((1 - ys) * fov - fov_up)
+    YAW, EL = np.meshgrid(yaw, elev)
+    d = np.stack([np.cos(EL) * np.cos(YAW), np.cos(EL) * np.sin(YAW), np.sin(EL)], -1)
+    r = np.where(EL < -0.02, height / np.maximum(-np.sin(EL), 1e-9), 0.0)
+    valid = (r > p.min_depth) & (r < p.max_depth)
+    V = np.zeros((H, W, 4), np.float32)
+    N = np.zeros((H, W, 4), np.float32)
+    V[..., :3] = d * r[..., None]
+    V[..., 3] = 1
+    N[..., 2] = 1
+    N[..., 3] = 1
+    V[~valid] = 0
+    N[~valid] = 0
+    return (V, N, np.zeros((H, W, 4), np.float32)), int(valid.sum())
+
+
+@pytest.mark.parametrize("dz", [0.01, -0.02])
+def test_icp_point_to_plane_terms_on_a_plane_are_the_analytic_ones(dz):
+    """Closed form for K5: data = model = a horizontal plane with normal (0,0,1), pose = pure z translation dz.
+    Whatever pixel a point is associated with, its point-to-plane residual is n.(T p - q) = dz, its translational
+    Jacobian row is n = (0,0,1): F = n dz^2, (JtJ)_zz = n, (Jtf)_z = n dz, no x/y terms, and the Gauss-Newton step
+    solves to exactly -dz (Frame2Model_jacobians.geom:150-185, LieGaussNewton.cpp:60-68)."""
+    W, H = 900, 64
+    p = O.default_params(**sized(W), weighting=0, bilinear_sampling=0)
+    frame, n_px = _ground_plane_frame(p, W, H)
+    T = np.eye(4)
+    T[2, 3] = dz
+    o48, _ = O.icp_jacobian(p, frame, frame, T)
+    n_valid, n_out, n_invalid = o48[42], o48[44], o48[46]
+    assert n_valid + n_invalid == W * H and n_out == 0
+    assert 0.9 * n_px <= n_valid <= n_px          # a band of rows leaves the image when the plane moves
+    JtJ = o48[:36].reshape(6, 6)
+    assert JtJ[2, 2] == n_valid                   # sum of n_z^2 with unit weights
+    assert abs(o48[43] - n_valid * dz * dz) <= 1e-4 * n_valid * dz * dz
+    assert abs(o48[45] - o48[43]) == 0            # every valid pixel is an inlier
+    assert abs(o48[38] - n_valid * dz) <= 1e-4 * abs(n_valid * dz)
+    assert np.abs(JtJ[:2, :]).max() == 0 and np.abs(o48[36:38]).max() == 0    # no x / y translation terms
+    assert JtJ[5, 5] == 0 and o48[41] == 0                                     # rotation about z is unobservable
+    step = O.ldlt_solve6(JtJ, -o48[36:42])
+    assert abs(step[2] + dz) < 1e-5 * abs(dz) + 1e-7 and np.abs(np.delete(step, 2)).max() < 1e-6
