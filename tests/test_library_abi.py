@@ -94,3 +94,31 @@ def test_cpp_mirror_has_the_reference_class_surface():
         # link into a shared object against the library: every sb_* the header uses must resolve
         subprocess.check_call([gxx, "-shared", "-o", os.path.join(td, "libsurface.so"), obj, "-L" + os.path.dirname(so),
                                "-lsuma_b200", "-Wl,--no-undefined"])
+
+
+def test_default_parameters_equal_the_reference_config():
+    """tests/golden/reference_default_xml.json is the reference's config/default.xml (made by
+    tests/golden/make_reference_params_fixture.py). Every XML key the C++ mirror's ParameterList maps onto sb_params
+    must default -- in the library AND in the oracle -- to the reference's value."""
+    import json
+    from oracle import oracle as O
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_default_xml.json")))["params"]
+    hpp = open(os.path.join(ROOT, "include", "suma_b200.hpp")).read()
+    keys = dict(re.findall(r'SUMA_F\("([^"]+)",\s*([a-z_0-9]+),', hpp))
+    assert len(keys) >= 45
+    lib_p, orc_p = api.default_params(), O.default_params()
+    not_in_xml = sorted(k for k in keys if k not in fx)
+    # code-side defaults (SurfelMap.cpp:265-273) and the two switches this implementation adds
+    assert not_in_xml == ["active_timestamps", "label_offset_quirk", "max_weight", "render_after_update"]
+    for key, field in keys.items():
+        if key not in fx:
+            continue
+        want = fx[key]["value"]
+        got, got_o = getattr(lib_p, field), getattr(orc_p, field)
+        if fx[key]["type"] == "float" and isinstance(got, float):
+            assert got in (want, float(np.float32(want))), (key, want, got)
+        else:
+            assert got == int(want), (key, want, got)
+        assert got == got_o, (key, got, got_o)
+    weights = {"none": 0, "huber": 1, "turkey": 2, "stability": 3}   # Frame2Model.cpp:69-80
+    assert lib_p.weighting == orc_p.weighting == weights[fx["weighting"]["value"]]
