@@ -122,3 +122,23 @@ def test_default_parameters_equal_the_reference_config():
         assert got == got_o, (key, got, got_o)
     weights = {"none": 0, "huber": 1, "turkey": 2, "stability": 3}   # Frame2Model.cpp:69-80
     assert lib_p.weighting == orc_p.weighting == weights[fx["weighting"]["value"]]
+
+
+def test_surfel_record_is_the_reference_struct():
+    """core/Surfel.h of the reference (fixture: tests/golden/reference_surfel_layout.json) fixes the 64-byte record of
+    getAllSurfels(): sb_surfel in the header, the numpy dtype of the mirror and the oracle's dtype must have the same
+    members, types and order."""
+    import json
+    from oracle import oracle as O
+    fields = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_surfel_layout.json")))["fields"]
+    assert len(fields) == 16
+    src = open(os.path.join(ROOT, "include", "suma_b200.h")).read()
+    body = re.search(r"typedef struct sb_surfel\s*\{(.*?)\}\s*sb_surfel;", src, flags=re.S).group(1)
+    mine = [[n.strip(), t] for t, names in re.findall(r"\b(float|uint32_t|int32_t)\s+([^;]+);", body)
+            for n in names.split(",")]
+    assert mine == fields
+    np_type = {"float": np.dtype(np.float32), "uint32_t": np.dtype(np.uint32)}
+    for dt in (api.SURFEL_DTYPE, O.SURFEL_DTYPE):
+        assert dt.itemsize == 64
+        assert [[n, dt.fields[n][0]] for n in dt.names] == [[n, np_type[t]] for n, t in fields]
+        assert [dt.fields[n][1] for n in dt.names] == [4 * i for i in range(16)]

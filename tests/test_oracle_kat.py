@@ -284,3 +284,43 @@ def test_icp_point_to_plane_terms_on_a_plane_are_the_analytic_ones(dz):
     assert JtJ[5, 5] == 0 and o48[41] == 0                                     # rotation about z is unobservable
     step = O.ldlt_solve6(JtJ, -o48[36:42])
     assert abs(step[2] + dz) < 1e-5 * abs(dz) + 1e-7 and np.abs(np.delete(step, 2)).max() < 1e-6
+
+
+def test_movable_label_set_is_the_reference_shaders():
+    """tests/golden/reference_movable_labels.json is parsed out of the reference's shaders (generator beside it): the
+    label ids gen_vertexmap.vert removes during the first ten scans, update_surfels.vert penalises and gen_surfels.geom
+    starts with a lower confidence. The oracle's K1 must remove exactly those; the CUDA predicate is the same literal
+    list (checked in the source, the GPU parity tests then compare behaviour)."""
+    import json
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fx = json.load(open(os.path.join(root, "tests", "golden", "reference_movable_labels.json")))["passes"]
+    sets = [set(v["movable"]) for v in fx.values()]
+    assert len(sets) == 3 and sets[0] == sets[1] == sets[2] and len(sets[0]) == 9
+    movable = sets[0]
+    # one point per label value 0..259, each in its own pixel column of the middle row
+    W, H = 900, 64
+    p = O.default_params(**sized(W), label_offset_quirk=0)
+    n = 260
+    az = -np.pi + (np.arange(n) * 3 + 1.5) * (2 * np.pi / W)
+    el = np.deg2rad(-11.0)
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, 0] = 10 * np.cos(el) * np.cos(az)
+    pts[:, 1] = 10 * np.cos(el) * np.sin(az)
+    pts[:, 2] = 10 * np.sin(el)
+    lab = np.arange(n, dtype=np.float32)
+    prb = np.full(n, 0.9, np.float32)
+    v_first, _, _ = O.preprocess(p, pts, lab, prb, timestamp=0)
+    v_later, _, s_later = O.preprocess(p, pts, lab, prb, timestamp=10)
+    assert int((v_later[..., 3] > 0).sum()) == n                 # every point owns a pixel
+    kept_first = (v_first[..., 3] > 0)
+    labels_kept = set(np.rint(s_later[kept_first][:, 0] * 255.0).astype(int).tolist())
+    labels_all = set(np.rint(s_later[v_later[..., 3] > 0][:, 0] * 255.0).astype(int).tolist())
+    assert labels_all == set(range(n))
+    assert labels_all - labels_kept == {int(m) for m in movable}
+    # the CUDA predicate and the oracle predicate are the same literal list
+    for path in ("semantic_suma_b200/csrc/sb_math.cuh", "oracle/orc_internal.h"):
+        src = open(os.path.join(root, path)).read()
+        body = re.search(r"is_movable\(float l\)\s*\{(.*?)\}", src, flags=re.S).group(1)
+        assert {float(x) for x in re.findall(r"l == ([\d.]+)f", body)} == movable, path
