@@ -723,6 +723,115 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_icp_persistent(KParams kp, I
 #undef SB_BS
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (opt-in: SUMA_B200_ICP_VARIANT=1, single GPU only, not measured yet -- DESIGN.md section 8).
+// Same iteration, no "last block": the ticket is a grid barrier, after which EVERY block's warp 0 sums the replicas and
+// performs the identical 6x6 step redundantly (deterministic code on identical integers => identical poses), so the
+// publish-through-an-epoch-flag hop and the re-load of the pose from L2 disappear from the critical path of each
+// iteration. The replica accumulators are cumulative and double buffered by iteration parity (never cleared inside the
+// kernel): iteration i adds into buffer i&1 and reads it after barrier i; the buffer is next written in iteration i+2,
+// which no block enters before every block has arrived at barrier i+1, i.e. after every block finished reading it.
+// Block 0 alone mirrors the state into GnState for the host and the kernels that follow.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kIcpThreads, 2) k_icp_persistent_all(KParams kp, IcpArgs a, GnState* __restrict__ st,
+                                                                    long long* __restrict__ cum, unsigned int* ticket,
+                                                                    int max_iter, double eps, double delta) {
+  __shared__ GnShared sh;
+  __shared__ double s_pose[16];
+  __shared__ double s_last_error;
+  __shared__ int s_k, s_done;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int hl = 0;
+  if (warp == 0) {
+    if (lane < 16) s_pose[lane] = st->pose[lane];
+    if (lane == 16) s_k = st->k;
+    if (lane == 17) s_done = st->done;
+    if (lane == 18) s_last_error = st->last_error;
+    hl = st->history_len;
+  }
+  long long prev0 = 0, prev1 = 0;  // lanes of warp 0: the cumulative totals already consumed, per buffer
+  __syncthreads();
+  for (unsigned int it = 0;; ++it) {
+    if (s_done) break;
+    float M[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) M[i] = (float)s_pose[i];  // pose_.cast<float>(), Frame2Model.cpp:194
+    const int k = s_k;
+    Acc acc;
+    icp_accumulate(kp, a, M, k, acc);
+    __syncthreads();
+    long long* buf = cum + (size_t)(it & 1u) * kAccReplicas * 32;
+    block_reduce_to_replica(acc, buf);
+    __syncthreads();
+    if (warp == 0) {
+      if (lane == 0) {
+        __threadfence();  // cumulative: orders this block's REDs (observed through the barrier) before the ticket
+        atomicAdd(ticket, 1u);
+        const unsigned int target = gridDim.x * (it + 1u);
+        while (*(volatile unsigned int*)ticket < target) {
+        }
+        __threadfence();
+      }
+      __syncwarp();
+      long long tot = 0;
+#pragma unroll
+      for (int r = 0; r < kAccReplicas; ++r) tot += *(volatile long long*)(buf + (size_t)r * 32 + lane);
+      long long raw;
+      if (it & 1u) {
+        raw = tot - prev1;
+        prev1 = tot;
+      } else {
+        raw = tot - prev0;
+        prev0 = tot;
+      }
+      const double last_error = s_last_error;
+      const bool writer = blockIdx.x == 0;
+      if (lane < 16) sh.P[lane] = s_pose[lane];
+      if (writer && lane < 16) st->history[hl * 16 + lane] = s_pose[lane];  // history_.push_back(Tk_)
+      ++hl;
+      __syncwarp();
+      gn_step_warp(sh, raw, lane, last_error, eps, delta, nullptr);
+      int kk = k, done = 0;
+      if (sh.result == 0) {
+        done = 1;
+      } else {
+        ++kk;
+        if (kk >= max_iter) {  // the loop pushes the pose once more and leaves (LieGaussNewton.cpp:24-27)
+          if (writer && lane < 16) st->history[hl * 16 + lane] = sh.P[lane];
+          ++hl;
+          done = 1;
+        }
+      }
+      if (lane < 16) s_pose[lane] = sh.P[lane];
+      if (lane == 0) {
+        s_k = kk;
+        s_done = done;
+        s_last_error = sh.O[43];
+      }
+      if (writer) {
+        if (lane < 16) st->pose[lane] = sh.P[lane];
+        for (int i = lane; i < 48; i += 32) st->out48[i] = sh.O[i];
+        if (lane == 0) {
+          st->last_error = sh.O[43];
+          st->k = kk;
+          st->history_len = hl;
+          st->done = done;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static int icp_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SUMA_B200_ICP_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 int icp_persistent_max_blocks(int sm_count) {
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_persistent, kIcpThreads, 0) != cudaSuccess) return 0;
@@ -741,6 +850,17 @@ int launch_icp_persistent(const Launch& L, const KParams& kp, const IcpArgs& a, 
   }
   KParams kpv = kp;
   IcpArgs av = a;
+  if (icp_variant() == 1 && !comm) {  // experimental all-blocks-solve kernel; its accumulators live behind the others
+    long long* cum = slots + (size_t)512 * 32;
+    if (cudaMemsetAsync(cum, 0, sizeof(long long) * 2 * kAccReplicas * 32, L.stream) != cudaSuccess) return -1;
+    void* args2[] = {&kpv, &av, &st, &cum, &ticket, &max_iter, &eps, &delta};
+    cudaError_t e2;
+    {
+      ScopedKernel sk(L, K_ICP_FUSED);
+      e2 = cudaLaunchCooperativeKernel((void*)k_icp_persistent_all, dim3(blocks), dim3(kIcpThreads), args2, 0, L.stream);
+    }
+    return e2 == cudaSuccess ? 0 : -1;
+  }
   void* args[] = {&kpv, &av, &st, &slots, &ticket, &epoch_flag, &max_iter, &eps, &delta, &cd, &trace};
   cudaError_t e;
   {

@@ -367,14 +367,220 @@ __global__ void __launch_bounds__(kRenderThreads) k_render_scatter(KParams kp, S
   raster_balanced(wt, ntris, total, rt, kp.Wm, lane);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (opt-in: SUMA_B200_RENDER_VARIANT=1|2, not measured yet -- DESIGN.md section 8): the same kernel with a
+// leaner per-warp triangle store, so that more blocks fit on an SM. ncu on the default kernel shows 51 % issue-slot use
+// at 25 % occupancy (86 registers, 36.9 KB shared memory per block). Here the x/y edge steps are kept as int32 (they
+// are 256 * a vertex-coordinate difference of one quad, |.| <= 2^28), the texture coordinates as six sign bits (they
+// are +-1), the bounding box in two packed words: 21.5 KB per block. Arithmetic and results are identical.
+// ------------------------------------------------------------------------------------------------------------
+struct WarpTrisLite {
+  long long e[3][kTrisPerWarp];
+  int sx[3][kTrisPerWarp], sy[3][kTrisPerWarp];
+  float farea[kTrisPerWarp], z[3][kTrisPerWarp];
+  uint32_t boxx[kTrisPerWarp], boxy[kTrisPerWarp];  // i0 | ni << 16, j0 | nj << 16
+  uint32_t k[kTrisPerWarp];
+  uint32_t meta[kTrisPerWarp];  // bits 0-2 ties, 3-5 flags, 6-8 tx sign of A,B,C (set = +1), 9-11 ty sign of A,B,C
+  int prefix[kTrisPerWarp + 1];
+};
+
+__device__ __forceinline__ void tris_store_lite(WarpTrisLite& w, int slot, const TriSetup& t, const Emit& e) {
+  w.e[0][slot] = t.eA; w.e[1][slot] = t.eB; w.e[2][slot] = t.eC;
+  w.sx[0][slot] = (int)t.sxA; w.sx[1][slot] = (int)t.sxB; w.sx[2][slot] = (int)t.sxC;
+  w.sy[0][slot] = (int)t.syA; w.sy[1][slot] = (int)t.syB; w.sy[2][slot] = (int)t.syC;
+  w.farea[slot] = t.farea;
+  w.z[0][slot] = t.zA; w.z[1][slot] = t.zB; w.z[2][slot] = t.zC;
+  w.boxx[slot] = (uint32_t)t.i0 | ((uint32_t)t.ni << 16);
+  w.boxy[slot] = (uint32_t)t.j0 | ((uint32_t)t.nj << 16);
+  w.k[slot] = e.k;
+  w.meta[slot] = (t.ties & 7u) | ((e.flags & 7u) << 3) | ((t.txA > 0.0f ? 1u : 0u) << 6) | ((t.txB > 0.0f ? 1u : 0u) << 7) |
+                 ((t.txC > 0.0f ? 1u : 0u) << 8) | ((t.tyA > 0.0f ? 1u : 0u) << 9) | ((t.tyB > 0.0f ? 1u : 0u) << 10) |
+                 ((t.tyC > 0.0f ? 1u : 0u) << 11);
+  w.prefix[slot + 1] = (t.ni + 1) * (t.nj + 1);
+}
+__device__ __forceinline__ void tris_load_lite(const WarpTrisLite& w, int slot, TriSetup& t, Emit& e) {
+  t.eA = w.e[0][slot]; t.eB = w.e[1][slot]; t.eC = w.e[2][slot];
+  t.sxA = (long long)w.sx[0][slot]; t.sxB = (long long)w.sx[1][slot]; t.sxC = (long long)w.sx[2][slot];
+  t.syA = (long long)w.sy[0][slot]; t.syB = (long long)w.sy[1][slot]; t.syC = (long long)w.sy[2][slot];
+  t.farea = w.farea[slot];
+  t.zA = w.z[0][slot]; t.zB = w.z[1][slot]; t.zC = w.z[2][slot];
+  const uint32_t m = w.meta[slot], bx = w.boxx[slot], by = w.boxy[slot];
+  t.txA = (m & (1u << 6)) ? 1.0f : -1.0f; t.txB = (m & (1u << 7)) ? 1.0f : -1.0f; t.txC = (m & (1u << 8)) ? 1.0f : -1.0f;
+  t.tyA = (m & (1u << 9)) ? 1.0f : -1.0f; t.tyB = (m & (1u << 10)) ? 1.0f : -1.0f; t.tyC = (m & (1u << 11)) ? 1.0f : -1.0f;
+  t.i0 = (int)(bx & 0xffffu); t.ni = (int)(bx >> 16);
+  t.j0 = (int)(by & 0xffffu); t.nj = (int)(by >> 16);
+  t.ties = m & 7u; t.valid = 1;
+  e.k = w.k[slot]; e.flags = (m >> 3) & 7u;
+}
+
+// raster_balanced over the lean store (same walk, same arithmetic)
+__device__ __forceinline__ void raster_balanced_lite(const WarpTrisLite& w, int ntris, int total, const RenderTargets& rt,
+                                                     int W, int lane) {
+  const int ch = (total + 31) >> 5;
+  int item = lane * ch;
+  const int end = min(item + ch, total);
+  if (item >= end) return;
+  int lo = 0, hi = ntris;  // largest j with prefix[j] <= item
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (w.prefix[mid] <= item) lo = mid; else hi = mid;
+  }
+  int j = lo;
+  while (item < end) {
+    TriSetup t;
+    Emit e;
+    tris_load_lite(w, j, t, e);
+    const int first = w.prefix[j], cnt = w.prefix[j + 1] - first;
+    const int local = item - first;
+    const int wd = t.ni + 1;
+    int dj = local / wd, di = local - dj * wd;
+    int n_here = min(end - item, cnt - local);
+    const bool tieA = t.ties & 1u, tieB = t.ties & 2u, tieC = t.ties & 4u;
+    long long rowA = t.eA + (long long)dj * t.syA, rowB = t.eB + (long long)dj * t.syB, rowC = t.eC + (long long)dj * t.syC;
+    long long wA = rowA + (long long)di * t.sxA, wB = rowB + (long long)di * t.sxB, wC = rowC + (long long)di * t.sxC;
+    for (int q = 0; q < n_here; ++q) {
+      bool in = (wA > 0 || (wA == 0 && tieA)) && (wB > 0 || (wB == 0 && tieB)) && (wC > 0 || (wC == 0 && tieC));
+      if (in) tri_fragment(t, e, rt, W, wB, wC, di, dj);
+      if (++di > t.ni) {
+        di = 0;
+        ++dj;
+        rowA += t.syA; rowB += t.syB; rowC += t.syC;
+        wA = rowA; wB = rowB; wC = rowC;
+      } else {
+        wA += t.sxA; wB += t.sxB; wC += t.sxC;
+      }
+    }
+    item += n_here;
+    ++j;
+  }
+}
+
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(kRenderThreads, MIN_BLOCKS)
+    k_render_scatter_lite(KParams kp, SurfelPlanes s, const uint32_t* __restrict__ n_dev, const float* __restrict__ Mtab,
+                          float conf_thr, int t_thr, int emit_old, int emit_new, int lequal, RenderTargets rt) {
+  __shared__ WarpTrisLite s_tris[kRenderThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpTrisLite& wt = s_tris[warp];
+  wt.prefix[2 * lane + 1] = 0;
+  wt.prefix[2 * lane + 2] = 0;
+  if (lane == 0) wt.prefix[0] = 0;
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  bool alive = k < *n_dev;
+  float4 p0, p1, p2;
+  bool is_old = false, is_new = false;
+  if (alive) {
+    p2 = __ldg(s.p2 + k);
+    p1 = __ldg(s.p1 + k);
+    alive = !kp.use_stability || p1.w > conf_thr;  // .geom:87 (cheap test first)
+  }
+  if (alive) {
+    int creation = (int)p2.w, ts = (int)__float_as_uint(p2.x);
+    is_old = emit_old && (creation < t_thr);                  // .geom:90
+    is_new = emit_new && (creation >= t_thr || ts >= t_thr);  // .geom:91
+    alive = is_old || is_new;
+  }
+  TriSetup t0, t1;
+  t0.valid = t1.valid = 0;
+  if (alive) {
+    p0 = __ldg(s.p0 + k);
+    float M[16];
+    load_mat(Mtab, pose_index(p2.w), M);
+    V3 pp = xform_point(M, mk3(p0.x, p0.y, p0.z));
+    V3 nn = xform_dir(M, mk3(p1.x, p1.y, p1.z));
+    float r = p0.w;
+    bool visible = dot3(nn, divs3(neg3(pp), len3(pp))) > 0.01f;  // .geom:84
+    float cx, cy, cz;
+    project01(pp, kp.m_fov_up, kp.m_fov, kp.m_min_depth, kp.m_max_depth, cx, cy, cz);
+    if (visible && cx >= 0.0f && cy >= 0.0f && cz >= 0.0f && cx < 1.0f && cy < 1.0f && cz < 1.0f) {
+      V3 u = normalize3(mk3(nn.y - nn.z, -nn.x, nn.x));
+      V3 v = normalize3(cross3(nn, u));
+      V3 ru = scale3(r, u), rv = scale3(r, v);
+      V3 corner[4];
+      corner[0] = sub3(sub3(pp, ru), rv);
+      corner[1] = sub3(add3(pp, ru), rv);
+      corner[2] = add3(sub3(pp, ru), rv);
+      corner[3] = add3(add3(pp, ru), rv);
+      RVert q[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float x, y, z;
+        project01(corner[i], kp.m_fov_up, kp.m_fov, kp.m_min_depth, kp.m_max_depth, x, y, z);
+        if (cx - x > 0.5f) x += 1.0f;  // .geom:68
+        if (x - cx > 0.5f) x -= 1.0f;  // .geom:69
+        float xw = (0.5f * (2.0f * x - 1.0f) + 0.5f) * (float)kp.Wm;
+        float yw = (0.5f * (2.0f * y - 1.0f) + 0.5f) * (float)kp.Hm;
+        q[i].z = 0.5f * (2.0f * z - 1.0f) + 0.5f;
+        q[i].X = __float2ll_rn(xw * 256.0f);
+        q[i].Y = __float2ll_rn(yw * 256.0f);
+        q[i].tx = (i & 1) ? 1.0f : -1.0f;
+        q[i].ty = (i & 2) ? 1.0f : -1.0f;
+      }
+      t0 = tri_prepare(q[0], q[1], q[2], kp.Wm, kp.Hm);
+      t1 = tri_prepare(q[1], q[2], q[3], kp.Wm, kp.Hm);
+    }
+  }
+  const int cnt = (int)t0.valid + (int)t1.valid;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int ntris = __shfl_sync(0xffffffffu, incl, 31);
+  if (ntris == 0) return;
+  __syncwarp();
+  if (cnt) {
+    Emit e;
+    e.k = k;
+    e.flags = (is_old ? 1u : 0u) | (is_new ? 2u : 0u) | (lequal ? 4u : 0u);
+    int slot = incl - cnt;
+    if (t0.valid) tris_store_lite(wt, slot++, t0, e);
+    if (t1.valid) tris_store_lite(wt, slot, t1, e);
+  }
+  __syncwarp();
+  int a = wt.prefix[2 * lane + 1], b = wt.prefix[2 * lane + 2];
+  int sum = a + b, isum = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, isum, o);
+    if (lane >= o) isum += v;
+  }
+  const int total = __shfl_sync(0xffffffffu, isum, 31);
+  __syncwarp();
+  wt.prefix[2 * lane + 1] = isum - sum + a;
+  wt.prefix[2 * lane + 2] = isum;
+  __syncwarp();
+  raster_balanced_lite(wt, ntris, total, rt, kp.Wm, lane);
+}
+
+static int render_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SUMA_B200_RENDER_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 void launch_render_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, const uint32_t* n_dev, uint32_t n_upper,
                            const float* M, float conf_thr, int t_thr, int emit_old, int emit_new, int lequal,
                            RenderTargets t) {
   if (n_upper == 0) return;
   {
     ScopedKernel sk(L, K_RENDER_SCATTER);
-    k_render_scatter<<<(n_upper + kRenderThreads - 1) / kRenderThreads, kRenderThreads, 0, L.stream>>>(
-        kp, s, n_dev, M, conf_thr, t_thr, emit_old, emit_new, lequal, t);
+    const unsigned grid = (n_upper + kRenderThreads - 1) / kRenderThreads;
+    const int variant = render_variant();
+    if (variant == 1) {  // lean triangle store, up to 6 blocks per SM without spills
+      k_render_scatter_lite<6><<<grid, kRenderThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr, emit_old,
+                                                                      emit_new, lequal, t);
+    } else if (variant == 2) {  // lean triangle store, 8 blocks per SM (64 registers, a few spills)
+      k_render_scatter_lite<8><<<grid, kRenderThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr, emit_old,
+                                                                      emit_new, lequal, t);
+    } else {
+      k_render_scatter<<<grid, kRenderThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr, emit_old, emit_new,
+                                                              lequal, t);
+    }
   }
 }
 
