@@ -1,0 +1,17 @@
+#!/bin/bash
+# First GPU call of the next round (1 GPU, ~6 min): is the tree still green, and what do the opt-in variants buy?
+#   gpurun --timeout 900 -- ./scratch/round2_first.sh
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+echo "== render variants (digest must equal the default's)"
+timeout 400 python scratch/variant_parity.py SUMA_B200_RENDER_VARIANT 1 2 2>&1 | tail -4
+echo "== Gauss-Newton variant"
+timeout 300 python scratch/variant_parity.py SUMA_B200_ICP_VARIANT 1 2>&1 | tail -3
+for v in "" "SUMA_B200_RENDER_VARIANT=1" "SUMA_B200_RENDER_VARIANT=2" "SUMA_B200_ICP_VARIANT=1"; do
+  echo "== bench $v"
+  env $v timeout 300 python bench.py --no-cpu-baseline 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1])
+k = d.get('kernels', {})
+print(d['value'], d['e2e']['value'], {n: (v['avg_us'], v['share']) for n, v in list(k.items())[:4]})"
+done
