@@ -6,10 +6,18 @@ import os
 import sys
 import xml.etree.ElementTree as ET
 
+import re
+
 SRC = sys.argv[1] if len(sys.argv) > 1 else "/root/reference/config/default.xml"
+HERE = os.path.dirname(os.path.abspath(__file__))
+# only the keys the hot path reads: the ones suma::ParameterList maps onto sb_params, plus the weighting string
+hpp = open(os.path.join(HERE, "..", "..", "include", "suma_b200.hpp")).read()
+wanted = set(re.findall(r'SUMA_F\("([^"]+)"', hpp)) | {"weighting"}
 out = {}
 for prm in ET.parse(SRC).getroot().findall("param"):
     name, typ, txt = prm.get("name"), prm.get("type"), (prm.text or "").strip()
+    if name not in wanted:
+        continue
     if typ == "integer":
         val = int(txt)
     elif typ == "float":
