@@ -157,7 +157,7 @@ def test_sequence_runner_on_the_gpu_matches_the_oracle_run(tmp_path):
     from semantic_suma_b200 import api, run_kitti
     from helpers import sized
     seq = str(tmp_path / "seq")
-    run_kitti.make_synthetic_sequence(seq, 8, width=450, semantic=True)
+    run_kitti.make_synthetic_sequence(seq, 8, width=900, semantic=True)
 
     class OracleEngine:
         def __init__(self, params):
@@ -169,8 +169,8 @@ def test_sequence_runner_on_the_gpu_matches_the_oracle_run(tmp_path):
         def getCurrentPose(self):
             return self.s.pose()
 
-    ref = run_kitti.run_sequence(seq, O.default_params(**sized(450)), make_engine=OracleEngine, semantic=True)
-    got = run_kitti.run_sequence(seq, api.default_params(**sized(450)), semantic=True)
+    ref = run_kitti.run_sequence(seq, O.default_params(**sized(900)), make_engine=OracleEngine, semantic=True)
+    got = run_kitti.run_sequence(seq, api.default_params(**sized(900)), semantic=True)
     assert got["scans"] == 8
     for a, b in zip(got["poses"], ref["poses"]):
         assert np.array_equal(a, b)
