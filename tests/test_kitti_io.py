@@ -176,3 +176,52 @@ def test_sequence_runner_on_the_gpu_matches_the_oracle_run(tmp_path):
         assert np.array_equal(a, b)
     ev = run_kitti.evaluate_against_ground_truth(seq, got["poses"])
     assert ev["end_point_error_m"] < 0.15
+
+
+def test_cpp_reader_and_metrics_agree_with_the_python_ones(tmp_path):
+    """include/suma_b200_io.hpp (KITTIReader, KITTICalibration, KITTI::Odometry) against semantic_suma_b200/kitti.py on
+    the same files: scan/label contents, pose files and the devkit errors of a drifting estimate."""
+    import os
+    import shutil
+    import subprocess
+    from semantic_suma_b200 import kitti as K, run_kitti
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "kitti_io_example")
+    subprocess.check_call([gxx, "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "kitti_io_example.cpp"), "-o", exe])
+    seq = str(tmp_path / "seq")
+    n = 130
+    # tiny scans (the content is irrelevant for the metrics), long trajectory so that 100 m segments exist
+    run_kitti.make_synthetic_sequence(seq, 3, width=90, semantic=True)
+    Tr = K.read_calibration(seq + "/calib.txt")["Tr"]
+    gt_velo = [np.linalg.inv(synth.trajectory(1)[0]) @ p for p in synth.trajectory(n)]
+    K.save_poses(seq + "/poses.txt", gt_velo, Tr=Tr)
+    est_velo = []
+    for i, p in enumerate(gt_velo):
+        q = p @ _yaw(0.004 * i)
+        q[:3, 3] *= 1.01
+        est_velo.append(q)
+    est_file = str(tmp_path / "est.txt")
+    K.save_poses(est_file, est_velo, Tr=Tr)
+    out = subprocess.check_output([exe, seq, est_file], text=True).split()
+    count, n_scans, n_points = int(out[0]), int(out[1]), int(out[2])
+    files = run_kitti.list_scans(seq)
+    scans = [K.read_scan(f) for f in files]
+    labels = [K.read_labels(f.replace("velodyne", "labels").replace(".bin", ".label"))[0] for f in files]
+    assert count == n_scans == 3 and n_points == sum(s[0].shape[0] for s in scans)
+    assert abs(float(out[3]) - sum(float(s[0].astype(np.float64).sum()) for s in scans)) < 1e-3
+    assert float(out[4]) == sum(float(l.sum()) for l in labels)
+    assert abs(float(out[5]) - sum(float(s[1].astype(np.float64).sum()) for s in scans)) < 1e-2
+    assert int(out[6]) == 1 and int(float(out[10])) == scans[1][0].shape[0]
+    errs = K.calc_sequence_errors(K.load_poses(seq + "/poses.txt"), K.load_poses(est_file))
+    t_py, r_py = K.sequence_stats(errs)
+    assert int(out[7]) == len(errs) > 0
+    assert abs(float(out[8]) - t_py) < 1e-5 * max(1.0, abs(t_py)) + 1e-6
+    assert abs(float(out[9]) - r_py) < 1e-5 * max(1.0, abs(r_py)) + 1e-7
+    # savePoses(velodyne poses, Tr) reproduces the camera-frame file it was derived from
+    again = K.load_poses(est_file + ".roundtrip")
+    for a, b in zip(again, K.load_poses(est_file)):
+        assert np.allclose(a, b, atol=2e-4)
