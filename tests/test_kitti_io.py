@@ -225,3 +225,34 @@ def test_cpp_reader_and_metrics_agree_with_the_python_ones(tmp_path):
     again = K.load_poses(est_file + ".roundtrip")
     for a, b in zip(again, K.load_poses(est_file)):
         assert np.allclose(a, b, atol=2e-4)
+
+
+@pytest.mark.gpu
+def test_cpp_end_to_end_example_matches_the_python_runner(tmp_path):
+    """tests/cpp/run_sequence_example.cpp (KITTIReader -> SurfelMapping::processScan -> savePoses) and
+    semantic_suma_b200.run_kitti over the same directory: the same trajectory file up to float32 text round-off."""
+    import os
+    import subprocess
+    from semantic_suma_b200 import api, kitti as K, run_kitti
+    from helpers import sized
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "semantic_suma_b200", "lib")
+    api.lib()
+    exe = str(tmp_path / "run_sequence_example")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "run_sequence_example.cpp"), "-o", exe, "-L" + libdir,
+                           "-lsuma_b200", "-Wl,-rpath," + libdir])
+    seq = str(tmp_path / "seq")
+    run_kitti.make_synthetic_sequence(seq, 6, width=900, semantic=False)
+    out_cpp = str(tmp_path / "cpp.txt")
+    log = subprocess.check_output([exe, seq, out_cpp, "900"], text=True)
+    assert "scan 5:" in log
+    res = run_kitti.run_sequence(seq, api.default_params(**sized(900)))
+    Tr = K.read_calibration(seq + "/calib.txt")["Tr"]
+    out_py = str(tmp_path / "py.txt")
+    K.save_poses(out_py, res["poses"], Tr=Tr)
+    a, b = K.load_poses(out_cpp), K.load_poses(out_py)
+    assert len(a) == len(b) == 6
+    for x, y in zip(a, b):
+        assert np.allclose(x, y, atol=2e-4)
+    assert abs(a[-1][2, 3] - 5.0) < 0.2          # five 1 m steps, forward = +z in the camera frame

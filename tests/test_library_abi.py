@@ -94,6 +94,16 @@ def test_cpp_mirror_has_the_reference_class_surface():
         # link into a shared object against the library: every sb_* the header uses must resolve
         subprocess.check_call([gxx, "-shared", "-o", os.path.join(td, "libsurface.so"), obj, "-L" + os.path.dirname(so),
                                "-lsuma_b200", "-Wl,--no-undefined"])
+        # the end-to-end example (reader -> processScan -> pose export) builds into an executable; without a GPU it must
+        # fail loudly (exit code 1 from the std::runtime_error), never fall back to anything
+        exe = os.path.join(td, "run_sequence_example")
+        subprocess.check_call([gxx, "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                               os.path.join(ROOT, "tests", "cpp", "run_sequence_example.cpp"), "-o", exe,
+                               "-L" + os.path.dirname(so), "-lsuma_b200", "-Wl,-rpath," + os.path.dirname(so)])
+        if api.lib().sb_device_count() == 0:
+            os.makedirs(os.path.join(td, "seq", "velodyne"))
+            r = subprocess.run([exe, os.path.join(td, "seq"), os.path.join(td, "out.txt")], capture_output=True, text=True)
+            assert r.returncode == 1 and "sb_create failed" in r.stderr
 
 
 def test_default_parameters_equal_the_reference_config():
