@@ -160,6 +160,10 @@ int sb_map_submap_origin(sb_ctx* ctx, int32_t* i, int32_t* j, uint32_t* pending)
 /* ---- SurfelMapping::processScan, SurfelMapping.cpp:175-210 (loop closure off) ---------------------------------- */
 int sb_process_scan(sb_ctx* ctx, const float* pts4, const float* labels, const float* probs, uint32_t n,
                     int pts_on_device);
+/* Optional input double buffering (no counterpart in the reference, which uploads inside processScan,
+ * SurfelMapping.cpp:325-331): start the host-to-device copy of the NEXT scan on a separate copy stream; a following
+ * sb_process_scan with the same host pointers / count (on_device = 0) uses the staged copy. At most two scans staged. */
+int sb_prefetch_scan(sb_ctx* ctx, const float* pts4, const float* labels, const float* probs, uint32_t n);
 int sb_get_pose(sb_ctx* ctx, double pose[16]);     /* getCurrentPose */
 int sb_get_last_pose(sb_ctx* ctx, double pose[16]); /* getLastPose, core/SurfelMapping.h:63 (pose before the last processScan) */
 int sb_timestamp(sb_ctx* ctx, uint32_t* t);        /* timestamp() */

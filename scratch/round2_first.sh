@@ -7,6 +7,7 @@ echo "== render variants (digest must equal the default's)"
 timeout 400 python scratch/variant_parity.py SUMA_B200_RENDER_VARIANT 1 2 2>&1 | tail -4
 echo "== Gauss-Newton variant"
 timeout 300 python scratch/variant_parity.py SUMA_B200_ICP_VARIANT 1 2>&1 | tail -3
+echo "== bench --prefetch (e2e)"; timeout 300 python bench.py --no-cpu-baseline --no-profile --prefetch 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['e2e'])"
 for v in "" "SUMA_B200_RENDER_VARIANT=1" "SUMA_B200_RENDER_VARIANT=2" "SUMA_B200_ICP_VARIANT=1"; do
   echo "== bench $v"
   env $v timeout 300 python bench.py --no-cpu-baseline 2>/dev/null | python -c "

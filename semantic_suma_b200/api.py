@@ -115,7 +115,7 @@ def lib(build_if_missing=True):
         "sb_map_download": [vp, vp, u32, C.POINTER(u32)], "sb_map_upload": [vp, vp, u32, u32],
         "sb_map_update_debug": [vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32)],
         "sb_map_submap_origin": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(u32)],
-        "sb_process_scan": [vp, vp, vp, vp, u32, C.c_int],
+        "sb_process_scan": [vp, vp, vp, vp, u32, C.c_int], "sb_prefetch_scan": [vp, vp, vp, vp, u32],
         "sb_get_pose": [vp, pd], "sb_get_last_pose": [vp, pd], "sb_timestamp": [vp, C.POINTER(u32)], "sb_slam_frame": [vp, C.c_int, pv],
         "sb_get_statistics": [vp, pd],
         "sb_comm_export": [vp, vp], "sb_comm_init": [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int],
@@ -147,7 +147,7 @@ EXPORTED_SYMBOLS = [
     "sb_map_render_inactive", "sb_map_render_composed", "sb_map_frame", "sb_icp_jacobian", "sb_icp_unpack",
     "sb_icp_minimize", "sb_se3_exp", "sb_se3_log", "sb_ldlt_solve6", "sb_gn_step", "sb_map_update",
     "sb_map_update_poses", "sb_map_size", "sb_map_timestamp", "sb_map_download", "sb_map_upload", "sb_map_set_pose",
-    "sb_map_update_debug", "sb_map_submap_origin", "sb_process_scan", "sb_get_pose", "sb_get_last_pose", "sb_timestamp", "sb_slam_frame",
+    "sb_map_update_debug", "sb_map_submap_origin", "sb_process_scan", "sb_prefetch_scan", "sb_get_pose", "sb_get_last_pose", "sb_timestamp", "sb_slam_frame",
     "sb_get_statistics", "sb_comm_export", "sb_comm_init", "sb_comm_shutdown", "sb_comm_set_callback",
     "sb_profile_enable",
     "sb_profile_kernels", "sb_profile_name", "sb_profile_collect",
@@ -527,6 +527,13 @@ class SurfelMapping:
         rc = lib().sb_process_scan(self.ctx.h, C.c_void_p(ptr_pts), C.c_void_p(ptr_labels) if ptr_labels else None,
                                    C.c_void_p(ptr_probs) if ptr_probs else None, n, 1 if on_device else 0)
         self.ctx.check(rc, "process_scan")
+
+    def prefetch_scan_raw(self, ptr_pts, ptr_labels, ptr_probs, n):
+        """stage the NEXT scan's (pinned) host buffers on the copy stream; process_scan_raw(..., on_device=False) with
+        the same pointers then skips its own copy (sb_prefetch_scan)"""
+        rc = lib().sb_prefetch_scan(self.ctx.h, C.c_void_p(ptr_pts), C.c_void_p(ptr_labels) if ptr_labels else None,
+                                    C.c_void_p(ptr_probs) if ptr_probs else None, n)
+        self.ctx.check(rc, "prefetch_scan")
 
     def getCurrentPose(self):
         a = np.zeros(16)

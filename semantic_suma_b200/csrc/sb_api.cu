@@ -47,6 +47,21 @@ struct sb_ctx {
   float* d_labels = nullptr;
   float* d_probs = nullptr;
   size_t pts_cap = 0;
+  // optional input prefetch (sb_prefetch_scan): a ring of staging buffers filled on a copy stream while the previous
+  // scan is being processed; created on first use, the default path never touches it
+  struct PrefetchSlot {
+    float4* pts = nullptr;
+    float* labels = nullptr;
+    float* probs = nullptr;
+    const float* host_pts = nullptr;
+    uint32_t n = 0;
+    bool has_labels = false, has_probs = false, valid = false, in_use = false;
+    cudaEvent_t done = nullptr;      // copy finished (recorded on the copy stream)
+    cudaEvent_t released = nullptr;  // every kernel that read the slot has been enqueued before this (compute stream)
+    bool has_released = false;
+  };
+  PrefetchSlot prefetch[3];
+  cudaStream_t copy_stream = nullptr;
 
   // ---- ICP
   GnState* gn = nullptr;
@@ -793,6 +808,26 @@ int upload_scan(sb_ctx* c, const float* pts4, const float* labels, const float* 
     return SB_OK;
   }
   if (n > c->pts_cap) return fail(c, SB_ERR_CAPACITY, "scan larger than 2 * data_width * data_height points");
+  if (c->copy_stream) {  // was this scan prefetched (same host buffer, same size, same optional arrays)?
+    for (auto& sl : c->prefetch)
+      if (sl.in_use) {  // the work that read this slot is already in the compute stream: mark the point after it
+        SB_CUDA(c, cudaEventRecord(sl.released, c->stream));
+        sl.has_released = true;
+        sl.in_use = false;
+      }
+    for (auto& sl : c->prefetch) {
+      if (!sl.valid || sl.host_pts != pts4 || sl.n != n || sl.has_labels != (labels != nullptr) ||
+          sl.has_probs != (probs != nullptr))
+        continue;
+      SB_CUDA(c, cudaStreamWaitEvent(c->stream, sl.done, 0));
+      sl.valid = false;
+      sl.in_use = true;
+      *d_pts = sl.pts;
+      *d_labels = labels ? sl.labels : nullptr;
+      *d_probs = probs ? sl.probs : nullptr;
+      return SB_OK;
+    }
+  }
   if (n) SB_CUDA(c, cudaMemcpyAsync(c->d_pts, pts4, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
   if (labels && n) SB_CUDA(c, cudaMemcpyAsync(c->d_labels, labels, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
   if (probs && n) SB_CUDA(c, cudaMemcpyAsync(c->d_probs, probs, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
@@ -980,6 +1015,12 @@ int sb_destroy(sb_ctx* c) {
   cudaStreamSynchronize(c->stream);
   sb_comm_shutdown(c);
   release_buffers(c);
+  for (auto& sl : c->prefetch) {
+    cudaFree(sl.pts); cudaFree(sl.labels); cudaFree(sl.probs);
+    if (sl.done) cudaEventDestroy(sl.done);
+    if (sl.released) cudaEventDestroy(sl.released);
+  }
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
   return SB_OK;
@@ -1377,6 +1418,44 @@ int sb_process_scan(sb_ctx* c, const float* pts4, const float* labels, const flo
   c->stats[11] = now_s() - t_all;
   c->stats[8] = c->stats[9] = c->stats[10] = 0.0;  // stages overlap on the stream; only complete-time is meaningful
   c->timestamp += 1;
+  return SB_OK;
+}
+
+// Optional: start copying the NEXT scan's host buffers to the device on a separate copy stream while the current scan
+// is being processed. A later sb_process_scan(..., on_device = 0) with the same host pointers and count uses the staged
+// copy instead of copying again. (The reference uploads inside processScan, SurfelMapping.cpp:325-331; this is the usual
+// double buffering of a sensor driver.) Buffers must stay unchanged until that sb_process_scan; pinned memory overlaps.
+int sb_prefetch_scan(sb_ctx* c, const float* pts4, const float* labels, const float* probs, uint32_t n) {
+  if (!c || (!pts4 && n)) return fail(c, SB_ERR_INVALID, "prefetch_scan: null argument");
+  if (n > c->pts_cap) return fail(c, SB_ERR_CAPACITY, "scan larger than 2 * data_width * data_height points");
+  cudaSetDevice(c->device);
+  if (!c->copy_stream) {
+    SB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (auto& sl : c->prefetch) {
+      SB_CUDA(c, cudaMalloc(&sl.pts, c->pts_cap * 16));
+      SB_CUDA(c, cudaMalloc(&sl.labels, c->pts_cap * 4));
+      SB_CUDA(c, cudaMalloc(&sl.probs, c->pts_cap * 4));
+      SB_CUDA(c, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+      SB_CUDA(c, cudaEventCreateWithFlags(&sl.released, cudaEventDisableTiming));
+    }
+  }
+  sb_ctx::PrefetchSlot* slot = nullptr;
+  for (auto& sl : c->prefetch)  // a slot that neither holds an unconsumed scan nor feeds the scan in flight
+    if (!sl.valid && !sl.in_use) {
+      slot = &sl;
+      break;
+    }
+  if (!slot) return fail(c, SB_ERR_STATE, "prefetch_scan: two scans are already staged");
+  if (slot->has_released) SB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, slot->released, 0));  // readers are done first
+  if (n) SB_CUDA(c, cudaMemcpyAsync(slot->pts, pts4, (size_t)n * 16, cudaMemcpyHostToDevice, c->copy_stream));
+  if (labels && n) SB_CUDA(c, cudaMemcpyAsync(slot->labels, labels, (size_t)n * 4, cudaMemcpyHostToDevice, c->copy_stream));
+  if (probs && n) SB_CUDA(c, cudaMemcpyAsync(slot->probs, probs, (size_t)n * 4, cudaMemcpyHostToDevice, c->copy_stream));
+  SB_CUDA(c, cudaEventRecord(slot->done, c->copy_stream));
+  slot->host_pts = pts4;
+  slot->n = n;
+  slot->has_labels = labels != nullptr;
+  slot->has_probs = probs != nullptr;
+  slot->valid = true;
   return SB_OK;
 }
 
