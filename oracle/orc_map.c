@@ -590,6 +590,7 @@ static int k6c_surfel(orc_map* m, uint32_t k, const float pose[16], const float 
   int inside = (ix < (float)W && iy < (float)H && z < 1.0f) && !(ix < 0.0f && iy < 0.0f && z < 0.0f); /* :174 (Q7) */
   float penalty = 0.0f;
   float update_conf = m->log_prior;
+  int64_t integrated_pix = -1;
   if (valid && inside && visible) {
     float St[4], Rt[4];
     data_tex(fs, W, H, ix, iy, St);
@@ -607,10 +608,11 @@ static int k6c_surfel(orc_map* m, uint32_t k, const float pose[16], const float 
     float angle = orc_len3(orc_cross3(n_global, old_normal));                       /* :211 */
     float new_radius = Rt[0], new_conf = Rt[1];
     if (distance < p->map_max_distance && angle < m->update_angle_thresh) { /* :217 */
-      /* :219 integrated flag: a point at (pixel, 2z-1) through clipping + depth test GL_LESS */
+      /* :219 integrated flag: a point at (pixel, 2z-1) through clipping + depth test GL_LESS -- drawn only if the
+       * geometry shader emits the surfel, i.e. if it is still valid at the end (update_surfels.geom:35-48); see below */
       float zn = 2.0f * z - 1.0f;
       if (zn >= -1.0f && zn <= 1.0f && orc_depth24(0.5f * zn + 0.5f) < ORC_DEPTH_CLEAR)
-        __atomic_store_n(&m->integrated[(size_t)(int)iy * W + (size_t)(int)ix], (uint8_t)1, __ATOMIC_RELAXED);
+        integrated_pix = (int64_t)((size_t)(int)iy * W + (size_t)(int)ix);
       float confidence = old_conf + new_conf;
       out->confidence = confidence;
       out->timestamp = (uint32_t)timestamp;
@@ -677,6 +679,11 @@ static int k6c_surfel(orc_map* m, uint32_t k, const float pose[16], const float 
     out->confidence = old_conf;
   }
   if (out->confidence < m->log_unstable && p->use_stability) valid_out = 0; /* :332 */
+  /* update_surfels.geom:35: `if(gs_in[0].valid)` -- a surfel that matched its measurement but is removed in the same
+   * pass (penalty / negative confidence) emits no vertex, so its pixel is NOT marked integrated and gen_surfels creates
+   * a new surfel there. (Found by oracle/_ref, the transpiled reference shaders; round 1 set the flag unconditionally.) */
+  if (valid_out && integrated_pix >= 0)
+    __atomic_store_n(&m->integrated[(size_t)integrated_pix], (uint8_t)1, __ATOMIC_RELAXED);
   return valid_out;
 }
 

@@ -16,3 +16,8 @@ d = json.loads(sys.stdin.read().strip().splitlines()[-1])
 k = d.get('kernels', {})
 print(d['value'], d['e2e']['value'], {n: (v['avg_us'], v['share']) for n, v in list(k.items())[:4]})"
 done
+echo "== microbench S=1e6"
+timeout 400 python microbench.py 2>gpurun_out/r02_micro.err | tee gpurun_out/r02_microbench_first.json | cut -c1-1500
+echo "== self comm loop-back"
+REPS=3 timeout 120 python scratch/self_comm.py 900 2>&1 | tail -3
+nvidia-smi topo -m > gpurun_out/r02_topo.txt 2>&1; lscpu | head -30 >> gpurun_out/r02_topo.txt; numactl -H >> gpurun_out/r02_topo.txt 2>&1

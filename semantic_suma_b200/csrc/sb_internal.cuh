@@ -202,12 +202,6 @@ void launch_gen_surfels(const Launch& L, const KParams& kp, FrameDev frame, cons
                         const uint8_t* integrated, const float* poses, int timestamp, float2 submap_center,
                         float submap_extent, SurfelPlanes tmp, uint8_t* keep, uint32_t* block_counts);
 // single-pass update / generate with in-place ordered compaction (decoupled look-back)
-void launch_update_compact(const Launch& L, const KParams& kp, SurfelPlanes map, const uint32_t* n_dev, uint32_t n_upper,
-                           const Mat4& pose, const Mat4& inv_pose, const Mat4* pose_dev, const Mat4* inv_pose_dev,
-                           const float* poses, const float* poses_inv, const unsigned long long* index_keys,
-                           const float4* radius_map, FrameDev frame, int timestamp, float2 submap_center,
-                           float submap_extent, uint8_t* integrated, unsigned long long* desc, uint32_t* ticket,
-                           uint32_t gen, uint32_t cap, uint32_t* counts);
 void launch_gen_compact(const Launch& L, const KParams& kp, FrameDev frame, const float4* radius_map,
                         const uint8_t* integrated, const float* poses, int timestamp, float2 submap_center,
                         float submap_extent, SurfelPlanes map, unsigned long long* desc, uint32_t* ticket, uint32_t gen,

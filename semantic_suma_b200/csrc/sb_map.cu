@@ -912,6 +912,8 @@ __global__ void __launch_bounds__(kThreads) k_update_surfels(KParams kp, SurfelP
     bool inside = (ix < (float)W && iy < (float)H && z < 1.0f) && !(ix < 0.0f && iy < 0.0f && z < 0.0f);
     float penalty = 0.0f;
     float update_conf = kp.log_prior;
+    size_t dpix = 0;
+    bool mark_integrated = false;
     if (valid && inside && visible) {
       float4 St = data_tex(f.semantic, W, H, ix, iy);
       float4 Rt = data_tex(ua.radius_map, W, H, ix, iy);
@@ -926,10 +928,12 @@ __global__ void __launch_bounds__(kThreads) k_update_surfels(KParams kp, SurfelP
       float distance = fabsf(dot3(old_normal, sub3(v_global, old_position)));
       float angle = len3(cross3(n_global, old_normal));
       float new_radius = Rt.x, new_conf = Rt.y;
-      size_t dpix = (size_t)(int)iy * W + (size_t)(int)ix;
+      dpix = (size_t)(int)iy * W + (size_t)(int)ix;
       if (distance < kp.map_max_distance && angle < kp.update_angle_thresh) {
+        // the "measurement integrated" point is drawn only if the geometry stage emits this surfel, i.e. if it is
+        // still valid at the end of the pass (update_surfels.geom:35-48): decided below
         float zn = 2.0f * z - 1.0f;
-        if (zn >= -1.0f && zn <= 1.0f && depth24(0.5f * zn + 0.5f) < kDepthClear) integrated[dpix] = 1;
+        mark_integrated = zn >= -1.0f && zn <= 1.0f && depth24(0.5f * zn + 0.5f) < kDepthClear;
         float confidence = old_conf + new_conf;
         o1.w = confidence;
         o2.x = __uint_as_float((uint32_t)timestamp);
@@ -998,6 +1002,7 @@ __global__ void __launch_bounds__(kThreads) k_update_surfels(KParams kp, SurfelP
       o1.w = old_conf;
     }
     if (o1.w < kp.log_unstable && kp.use_stability) valid_out = false;
+    if (valid_out && mark_integrated) integrated[dpix] = 1;
     kept = valid_out && submap_keep(ua.poses, o0, o2, ua.submap_center, ua.submap_extent);
     tmp.p0[k] = o0;
     tmp.p1[k] = o1;
@@ -1007,158 +1012,6 @@ __global__ void __launch_bounds__(kThreads) k_update_surfels(KParams kp, SurfelP
   }
   int cnt = __syncthreads_count(kept ? 1 : 0);
   if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)cnt;
-}
-
-// K6c + K6e in ONE pass: update every surfel, decide keep / kill / outside-the-submap, and write the survivors in order
-// to the front of the SAME lanes (in-place: a block learns its output offset only after every earlier block has read
-// its input; later blocks read behind everything this block writes).
-constexpr int kUpdThreads = 128;  // small blocks: a block holds its SM slot while it waits for its output offset
-__global__ void __launch_bounds__(kUpdThreads) k_update_compact(KParams kp, SurfelPlanes src, const uint32_t* __restrict__ n_dev,
-                                                            UpdateArgs ua, FrameDev f, uint8_t* __restrict__ integrated,
-                                                            Lookback lb, uint32_t cap, uint32_t* __restrict__ counts) {
-  const uint32_t vb = block_ticket(lb);
-  uint32_t k = vb * blockDim.x + threadIdx.x;
-  bool kept = false;
-  float4 o0, o1, o2, o3;
-  o0 = o1 = o2 = o3 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (k < *n_dev) {
-    const int W = kp.W, H = kp.H;
-    // plain (coherent) loads: the same lanes are written in place by later blocks of this kernel
-    float4 p0 = src.p0[k], p1 = src.p1[k], p2 = src.p2[k], p3 = src.p3[k];
-    const int timestamp = ua.timestamp;
-    int s_ts = (int)__float_as_uint(p2.x);
-    int surfel_age = timestamp - s_ts;
-    int creation = (int)p2.w;
-    int ci = pose_index(p2.w);
-    float SP[16];
-    load_mat(ua.poses, ci, SP);
-    const float* POSE = ua.pose_dev ? ua.pose_dev->m : ua.pose.m;
-    const float* INV = ua.inv_pose_dev ? ua.inv_pose_dev->m : ua.inv_pose.m;
-    V3 old_position = xform_point(SP, mk3(p0.x, p0.y, p0.z));
-    V3 old_normal = xform_dir(SP, mk3(p1.x, p1.y, p1.z));
-    float old_radius = p0.w, old_conf = p1.w, old_weight = p2.z;
-    bool valid_out = true;
-    if (old_conf < kp.confidence_threshold && kp.use_stability) valid_out = surfel_age < kp.unstable_age;
-    o0 = p0; o1 = p1; o2 = p2; o3 = p3;
-    o2.y = pack_rgb(0.3f, 0.3f, 0.3f);
-    V3 vertex = xform_point(INV, old_position);
-    V3 normal = normalize3(xform_dir(INV, old_normal));
-    bool visible = dot3(normal, divs3(neg3(vertex), len3(vertex))) > 0.0f;
-    float x, y, z;
-    project01(vertex, kp.fov_up, kp.fov, kp.min_depth, kp.max_depth, x, y, z);
-    float ix = floorf(x * (float)W) + 0.5f, iy = floorf(y * (float)H) + 0.5f;
-    float4 Vt = data_tex(f.vertex, W, H, ix, iy);
-    float4 Nt = data_tex(f.normal, W, H, ix, iy);
-    bool valid = (Vt.w > 0.5f) && (Nt.w > 0.5f);
-    bool inside = (ix < (float)W && iy < (float)H && z < 1.0f) && !(ix < 0.0f && iy < 0.0f && z < 0.0f);
-    float penalty = 0.0f;
-    float update_conf = kp.log_prior;
-    if (valid && inside && visible) {
-      float4 St = data_tex(f.semantic, W, H, ix, iy);
-      float4 Rt = data_tex(ua.radius_map, W, H, ix, iy);
-      float data_label = St.x * 255.0f, data_prob = St.w;
-      float model_label = p3.x * 255.0f, model_prob = p3.w;
-      bool label_diff = roundf_(data_label) != roundf_(model_label);
-      if (label_diff && is_movable(model_label)) penalty = 1.0f;
-      V3 v = mk3(Vt.x, Vt.y, Vt.z), n = mk3(Nt.x, Nt.y, Nt.z);
-      V3 v_global = xform_point(POSE, v);
-      V3 n_global = normalize3(xform_dir(POSE, n));
-      V3 view_dir = divs3(neg3(v), len3(v));
-      float distance = fabsf(dot3(old_normal, sub3(v_global, old_position)));
-      float angle = len3(cross3(n_global, old_normal));
-      float new_radius = Rt.x, new_conf = Rt.y;
-      size_t dpix = (size_t)(int)iy * W + (size_t)(int)ix;
-      if (distance < kp.map_max_distance && angle < kp.update_angle_thresh) {
-        float zn = 2.0f * z - 1.0f;
-        if (zn >= -1.0f && zn <= 1.0f && depth24(0.5f * zn + 0.5f) < kDepthClear) integrated[dpix] = 1;
-        float confidence = old_conf + new_conf;
-        o1.w = confidence;
-        o2.x = __uint_as_float((uint32_t)timestamp);
-        float avg_radius = new_radius < old_radius ? new_radius : old_radius;
-        avg_radius = avg_radius > 0.0f ? avg_radius : 0.0f;  // update program's min_radius uniform is 0 (SurfelMap.cpp:422)
-        o0.w = avg_radius;
-        valid_out = true;
-        o2.y = pack_rgb(0.0f, 0.7f, 0.0f);
-        o2.w = (float)creation;
-        float a = angle, d = distance;
-        float pr = kp.p_stable;
-        if (kp.confidence_mode == 1 || kp.confidence_mode == 3)
-          pr = pr * expf_(((-a) * a) / (kp.sigma_angle * kp.sigma_angle));
-        if (kp.confidence_mode == 2 || kp.confidence_mode == 3)
-          pr = pr * expf_(((-d) * d) / (kp.sigma_distance * kp.sigma_distance));
-        pr = pr > kp.p_unstable ? pr : kp.p_unstable;
-        pr = pr < 1.0f ? pr : 1.0f;
-        update_conf = logf_(pr / (1.0f - pr));
-        if ((new_radius < old_radius && timestamp - creation < kp.active_timestamps) || kp.update_always) {
-          float w1 = 0.9f, w2 = 0.1f;
-          if (kp.weighting_scheme > 0) {
-            w1 = old_weight;
-            w2 = 1.0f;
-            if (kp.weighting_scheme == 2) w2 = dot3(n, view_dir);
-            float sw = w1 + w2;
-            o2.z = kp.max_weight < sw ? kp.max_weight : sw;
-            float sum = w1 + w2;
-            w1 = w1 / sum;
-            w2 = w2 / sum;
-          }
-          V3 avg_position = add3(scale3(w1, old_position), scale3(w2, v_global));
-          V3 avg_normal = slerp(old_normal, n_global, w1);
-          float avg_prob;
-          if (label_diff)
-            avg_prob = w1 * model_prob + w2 * (1.0f - data_prob);
-          else
-            avg_prob = w1 * model_prob + w2 * data_prob;
-          o3.w = avg_prob;
-          if (kp.averaging_scheme == 1) {
-            avg_position = add3(old_position, scale3(w2 * distance, old_normal));
-            avg_normal = slerp(old_normal, n_global, w1);
-          }
-          avg_normal = normalize3(avg_normal);
-          float SPI[16];
-          load_mat(ua.poses_inv, ci, SPI);
-          avg_position = xform_point(SPI, avg_position);
-          avg_normal = xform_dir(SPI, avg_normal);
-          o0 = make_float4(avg_position.x, avg_position.y, avg_position.z, avg_radius);
-          o1 = make_float4(avg_normal.x, avg_normal.y, avg_normal.z, confidence);
-          o2.y = pack_rgb(1.0f, 0.0f, 1.0f);
-        }
-      } else {
-        unsigned long long key = ua.index_keys[dpix];
-        int idx = (key == ~0ull) ? -1 : (int)(uint32_t)(key & 0xffffffffull);
-        if (idx == (int)k) {  // closest visible surfel of that pixel
-          update_conf = logf_(kp.p_unstable / (1.0f - kp.p_unstable));
-          o2.y = pack_rgb(0.0f, 1.0f, 1.0f);
-        }
-      }
-    }
-    update_conf = update_conf - penalty;
-    if (kp.use_stability) {
-      float c = (old_conf + update_conf) - kp.log_prior;
-      o1.w = c < 20.0f ? c : 20.0f;
-    } else {
-      o1.w = old_conf;
-    }
-    if (o1.w < kp.log_unstable && kp.use_stability) valid_out = false;
-    kept = valid_out && submap_keep(ua.poses, o0, o2, ua.submap_center, ua.submap_extent);
-  }
-  uint32_t block_count;
-  const uint32_t rank = block_rank<kUpdThreads>(kept, block_count);
-  const uint32_t excl = lookback_exclusive(lb, vb, block_count);
-  if (kept) {
-    uint32_t d = excl + rank;
-    if (d < cap) {  // transform feedback drops what does not fit
-      src.p0[d] = o0;
-      src.p1[d] = o1;
-      src.p2[d] = o2;
-      src.p3[d] = o3;
-    }
-  }
-  if (vb == gridDim.x - 1 && threadIdx.x == 0) {
-    uint32_t total = excl + block_count;
-    counts[1] = total < cap ? total : cap;  // S': base of the new surfels
-    counts[2] = total;                      // kept updated surfels
-    *lb.ticket = 0;
-  }
 }
 
 // K6d: gen_surfels.vert:38-52 + .geom:109-145; thread t <-> pixel (x = t / H, y = t % H): x-major order
@@ -1423,23 +1276,6 @@ void launch_gen_surfels(const Launch& L, const KParams& kp, FrameDev frame, cons
     k_gen_surfels<<<(P + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, frame, radius_map, integrated, poses,
                                                                          timestamp, submap_center, submap_extent, tmp,
                                                                          keep, block_counts);
-  }
-}
-
-void launch_update_compact(const Launch& L, const KParams& kp, SurfelPlanes map, const uint32_t* n_dev, uint32_t n_upper,
-                           const Mat4& pose, const Mat4& inv_pose, const Mat4* pose_dev, const Mat4* inv_pose_dev,
-                           const float* poses, const float* poses_inv, const unsigned long long* index_keys,
-                           const float4* radius_map, FrameDev frame, int timestamp, float2 submap_center,
-                           float submap_extent, uint8_t* integrated, unsigned long long* desc, uint32_t* ticket,
-                           uint32_t gen, uint32_t cap, uint32_t* counts) {
-  UpdateArgs ua{pose, inv_pose, pose_dev, inv_pose_dev, poses, poses_inv, index_keys, radius_map, timestamp,
-                submap_center, submap_extent};
-  Lookback lb{desc, ticket, gen};
-  uint32_t blocks = (n_upper + kUpdThreads - 1) / kUpdThreads;
-  if (blocks == 0) blocks = 1;  // the last block also publishes the (zero) totals
-  {
-    ScopedKernel sk(L, K_UPDATE_SURFELS);
-    k_update_compact<<<blocks, kUpdThreads, 0, L.stream>>>(kp, map, n_dev, ua, frame, integrated, lb, cap, counts);
   }
 }
 
