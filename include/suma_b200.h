@@ -133,7 +133,9 @@ void sb_icp_unpack(const int64_t raw32[32], double out48[48]);
 
 /* ---- LieGaussNewton::minimize, LieGaussNewton.cpp:13-37 (+ step :53-79, Objective::increment Objective.h:45) ----
  * The whole Gauss-Newton loop runs on the device (K5 + 6x6 LDLT + SE3 exp per iteration, no host round trip).
- * history (optional): (max_iter+1)*16 doubles; history_len receives the number of poses pushed.
+ * history (optional): (max_iter+1)*16 doubles; history_len receives the number of poses pushed. max_iter <= 0 (the
+ * reference's "no limit") or > 256 runs at most 256 iterations and is only accepted with history == NULL
+ * (SB_ERR_INVALID otherwise).
  * Returns the iteration count k_ in *iters. */
 int sb_icp_minimize(sb_ctx* ctx, const sb_frame* data, const sb_frame* model, const double T0[16], int max_iter,
                     double eps, double delta, float max_distance, float max_angle_deg, double pose_out[16],

@@ -374,10 +374,13 @@ class LieGaussNewton:
     def minimize(self, F, T0):
         T0c = colmajor(T0, np.float64)
         pose = np.zeros(16); out48 = np.zeros(48); it = C.c_int(0); hl = C.c_int(0)
-        hist = np.zeros((max(self.maxIter, 1) + 2) * 16 if self.maxIter > 0 else 258 * 16)
+        bounded = 1 <= self.maxIter <= 256   # a history buffer is only accepted with an explicit iteration limit
+        hist = np.zeros((self.maxIter + 1) * 16 if bounded else 16)
         self.ctx.check(lib().sb_icp_minimize(self.ctx.h, F.current.h, F.last.h, _dp(T0c), self.maxIter, self.epsilon,
                                              self.delta, F.max_distance, F.max_angle, _dp(pose), _dp(out48),
-                                             C.byref(it), _dp(hist), C.byref(hl)), "icp_minimize")
+                                             C.byref(it), _dp(hist) if bounded else None, C.byref(hl)), "icp_minimize")
+        if not bounded:
+            hl.value = 0
         self.Tk_ = from_colmajor(pose)
         self.k_ = it.value
         self.out48 = out48

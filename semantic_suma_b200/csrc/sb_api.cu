@@ -490,6 +490,7 @@ IcpArgs icp_args(sb_ctx* c, const sb_frame* data, const sb_frame* model, float m
   a.angle_thresh = (float)cos((double)max_angle_deg * 3.14159265358979323846 / 180.0);  // Frame2Model.cpp:66
   a.row_begin = row_begin; a.row_end = row_end;
   a.has_semantics = semantics ? 1 : 0;
+  a.Wm = model->d.W; a.Hm = model->d.H;
   {  // stride ~ 0.618 * rows, coprime to rows
     int rows = row_end - row_begin;
     int step = (int)(rows * 0.6180339887) | 1;
@@ -503,7 +504,10 @@ IcpArgs icp_args(sb_ctx* c, const sb_frame* data, const sb_frame* model, float m
 
 int icp_check(sb_ctx* c, const sb_frame* data, const sb_frame* model) {
   if (!c || !data || !model) return fail(c, SB_ERR_INVALID, "icp: null argument");
-  if (data->d.W != c->kp.W || data->d.H != c->kp.H || model->d.W != c->kp.Wm || model->d.H != c->kp.Hm)
+  // the model may be a rendered model frame or another data frame (frame-to-frame objective, SurfelMapping.cpp:442):
+  // its own size is what the kernel samples with (textureSize(vertex_model))
+  const bool model_ok = (model->d.W == c->kp.Wm && model->d.H == c->kp.Hm) || (model->d.W == c->kp.W && model->d.H == c->kp.H);
+  if (data->d.W != c->kp.W || data->d.H != c->kp.H || !model_ok)
     return fail(c, SB_ERR_INVALID, "icp: frame size does not match data_/model_ width/height");
   return SB_OK;
 }
@@ -799,6 +803,30 @@ float conf_threshold(const sb_ctx* c) {  // SurfelMapping.cpp:333-340, time_init
   return ct;
 }
 
+// staging buffers for host-pointer scans grow with the largest scan seen (the projection itself only needs W*H pixels)
+int grow_point_buffers(sb_ctx* c, size_t n) {
+  if (n <= c->pts_cap) return SB_OK;
+  size_t cap = n + n / 4 + 1024;
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->copy_stream) SB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+  float4* np = nullptr; float* nl = nullptr; float* nq = nullptr;
+  if (cudaMalloc(&np, cap * 16) != cudaSuccess || cudaMalloc(&nl, cap * 4) != cudaSuccess ||
+      cudaMalloc(&nq, cap * 4) != cudaSuccess) {
+    cudaFree(np); cudaFree(nl); cudaFree(nq);
+    cudaGetLastError();
+    return fail(c, SB_ERR_CAPACITY, "out of device memory for the scan staging buffers");
+  }
+  cudaFree(c->d_pts); cudaFree(c->d_labels); cudaFree(c->d_probs);
+  c->d_pts = np; c->d_labels = nl; c->d_probs = nq;
+  for (auto& sl : c->prefetch) {  // prefetch slots are re-allocated lazily at the new capacity
+    cudaFree(sl.pts); cudaFree(sl.labels); cudaFree(sl.probs);
+    sl.pts = nullptr; sl.labels = nullptr; sl.probs = nullptr;
+    sl.valid = false; sl.in_use = false; sl.has_released = false;
+  }
+  c->pts_cap = cap;
+  return SB_OK;
+}
+
 int upload_scan(sb_ctx* c, const float* pts4, const float* labels, const float* probs, uint32_t n, int on_device,
                 const float4** d_pts, const float** d_labels, const float** d_probs) {
   if (on_device) {
@@ -807,7 +835,8 @@ int upload_scan(sb_ctx* c, const float* pts4, const float* labels, const float* 
     *d_probs = probs;
     return SB_OK;
   }
-  if (n > c->pts_cap) return fail(c, SB_ERR_CAPACITY, "scan larger than 2 * data_width * data_height points");
+  int rg = grow_point_buffers(c, n);  // GlBuffer::assign resizes (SurfelMapping.cpp:327-330): no cap on the scan size
+  if (rg) return rg;
   if (c->copy_stream) {  // was this scan prefetched (same host buffer, same size, same optional arrays)?
     for (auto& sl : c->prefetch)
       if (sl.in_use) {  // the work that read this slot is already in the compute stream: mark the point after it
@@ -1189,6 +1218,10 @@ int sb_icp_minimize(sb_ctx* c, const sb_frame* data, const sb_frame* model, cons
   int r = icp_check(c, data, model);
   if (r) return r;
   if (!T0) return fail(c, SB_ERR_INVALID, "icp_minimize: null T0");
+  // max_iter <= 0 is the reference's "no limit" (LieGaussNewton.cpp:24); the device loop stops after kMaxGnIter = 256
+  // iterations at the latest. A caller-sized history buffer ((max_iter+1)*16 doubles) is only safe for 1..256.
+  if (history && (max_iter <= 0 || max_iter > kMaxGnIter))
+    return fail(c, SB_ERR_INVALID, "icp_minimize: with a history buffer max_iter must be in [1, 256]");
   cudaSetDevice(c->device);
   if ((r = icp_minimize_enqueue(c, data, model, T0, max_iter, eps, delta, max_distance, max_angle_deg, true))) return r;
   if ((r = icp_minimize_fetch(c, pose_out, out48, iters, history, history_len))) return r;
@@ -1328,6 +1361,10 @@ int sb_process_scan(sb_ctx* c, const float* pts4, const float* labels, const flo
   const sb_params& p = c->p;
   Launch L = L_(c);
   double t_all = now_s();
+  // the upload can fail (out of memory for a larger scan): do it before any state of the context changes
+  const float4* dp; const float* dl; const float* dq;
+  int r = upload_scan(c, pts4, labels, probs, n, on_device, &dp, &dl, &dq);
+  if (r) return r;
   // initialize(), SurfelMapping.cpp:323-331
   std::swap(c->cur, c->last);
   std::swap(c->cur_model, c->last_model);
@@ -1335,9 +1372,6 @@ int sb_process_scan(sb_ctx* c, const float* pts4, const float* labels, const flo
   c->cur_has_semantics = labels != nullptr;
   // ---- everything below is enqueued on the stream without a host round trip; ONE synchronisation at the end ----
   // preprocess(), :342-358
-  const float4* dp; const float* dl; const float* dq;
-  int r = upload_scan(c, pts4, labels, probs, n, on_device, &dp, &dl, &dq);
-  if (r) return r;
   launch_preprocess(L, c->kp, dp, dl, dq, n, c->timestamp, c->keys_data, c->sem_raw, c->eroded, c->cur->d);
   float ct = conf_threshold(c);
   float Pold[16], Pnew[16];
@@ -1427,18 +1461,22 @@ int sb_process_scan(sb_ctx* c, const float* pts4, const float* labels, const flo
 // double buffering of a sensor driver.) Buffers must stay unchanged until that sb_process_scan; pinned memory overlaps.
 int sb_prefetch_scan(sb_ctx* c, const float* pts4, const float* labels, const float* probs, uint32_t n) {
   if (!c || (!pts4 && n)) return fail(c, SB_ERR_INVALID, "prefetch_scan: null argument");
-  if (n > c->pts_cap) return fail(c, SB_ERR_CAPACITY, "scan larger than 2 * data_width * data_height points");
   cudaSetDevice(c->device);
+  int rg = grow_point_buffers(c, n);
+  if (rg) return rg;
   if (!c->copy_stream) {
     SB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (auto& sl : c->prefetch) {
-      SB_CUDA(c, cudaMalloc(&sl.pts, c->pts_cap * 16));
-      SB_CUDA(c, cudaMalloc(&sl.labels, c->pts_cap * 4));
-      SB_CUDA(c, cudaMalloc(&sl.probs, c->pts_cap * 4));
       SB_CUDA(c, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
       SB_CUDA(c, cudaEventCreateWithFlags(&sl.released, cudaEventDisableTiming));
     }
   }
+  for (auto& sl : c->prefetch)
+    if (!sl.pts) {  // first use, or the staging capacity grew
+      SB_CUDA(c, cudaMalloc(&sl.pts, c->pts_cap * 16));
+      SB_CUDA(c, cudaMalloc(&sl.labels, c->pts_cap * 4));
+      SB_CUDA(c, cudaMalloc(&sl.probs, c->pts_cap * 4));
+    }
   sb_ctx::PrefetchSlot* slot = nullptr;
   for (auto& sl : c->prefetch)  // a slot that neither holds an unconsumed scan nor feeds the scan in flight
     if (!sl.valid && !sl.in_use) {

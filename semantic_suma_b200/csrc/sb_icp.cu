@@ -91,8 +91,8 @@ __device__ __forceinline__ void icp_pixel(const KParams& kp, const IcpArgs& a, c
   float pitch = -asinf_(v_d.z / depth);
   float px = 0.5f * ((-yaw * kInvPi) + 1.0f);
   float py = 1.0f - (kRad2Deg * pitch + kp.fov_up) / kp.fov;
-  float ix = px * (float)kp.Wm, iy = py * (float)kp.Hm;
-  if (!(ix >= 0.0f && ix < (float)kp.Wm && iy >= 0.0f && iy < (float)kp.Hm)) {
+  float ix = px * (float)a.Wm, iy = py * (float)a.Hm;
+  if (!(ix >= 0.0f && ix < (float)a.Wm && iy >= 0.0f && iy < (float)a.Hm)) {
     acc.n_invalid += 1;
     return;
   }
@@ -101,13 +101,13 @@ __device__ __forceinline__ void icp_pixel(const KParams& kp, const IcpArgs& a, c
   int tx = 0, ty = 0;
   if (kp.bilinear) {
     b = bilin_setup(ix, iy);
-    Vm = sample_bilin(a.model_v, kp.Wm, kp.Hm, b);
-    Nm = sample_bilin(a.model_n, kp.Wm, kp.Hm, b);
+    Vm = sample_bilin(a.model_v, a.Wm, a.Hm, b);
+    Nm = sample_bilin(a.model_n, a.Wm, a.Hm, b);
   } else {
     tx = (int)floorf(ix);
     ty = (int)floorf(iy);
-    Vm = tex_border(a.model_v, kp.Wm, kp.Hm, tx, ty);
-    Nm = tex_border(a.model_n, kp.Wm, kp.Hm, tx, ty);
+    Vm = tex_border(a.model_v, a.Wm, a.Hm, tx, ty);
+    Nm = tex_border(a.model_n, a.Wm, a.Hm, tx, ty);
   }
   float e_m = Vm.w + Nm.w;
   if (!(e_m > 1.5f)) {
@@ -133,7 +133,7 @@ __device__ __forceinline__ void icp_pixel(const KParams& kp, const IcpArgs& a, c
     }
   }
   if (a.has_semantics) {  // .geom:144-158
-    float4 Sm = kp.bilinear ? sample_bilin(a.model_s, kp.Wm, kp.Hm, b) : tex_border(a.model_s, kp.Wm, kp.Hm, tx, ty);
+    float4 Sm = kp.bilinear ? sample_bilin(a.model_s, a.Wm, a.Hm, b) : tex_border(a.model_s, a.Wm, a.Hm, tx, ty);
     float4 Sd = __ldg(a.data_s + pix);
     float data_label = Sd.x * 255.0f, data_prob = Sd.w, model_label = Sm.x * 255.0f;
     if (is_movable(model_label)) {

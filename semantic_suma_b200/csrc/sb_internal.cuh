@@ -74,6 +74,8 @@ struct IcpArgs {
   int row_begin, row_end;
   int has_semantics;
   int row_step;  // row permutation stride of the work distribution, coprime to (row_end - row_begin)
+  int Wm, Hm;    // size of the model images = textureSize(vertex_model) (Frame2Model_jacobians.geom:70): the rendered
+                 // model frame, or the last data frame in the frame-to-frame fallback (SurfelMapping.cpp:442)
 };
 
 // peer mailboxes for the multi-GPU one-shot all-reduce (fused into the Jacobian kernel's last block)
