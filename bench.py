@@ -124,7 +124,7 @@ class ClockSampler(threading.Thread):
 def algorithmic_bytes(kernel, P, S, N, semantic):
     """compulsory HBM bytes of one launch (DESIGN.md 'Kernels and their rooflines')"""
     t = {
-        "fill_u64": 8 * P, "project_scatter": 16 * N, "project_resolve": 8 * P + 16 * N + 32 * P,
+        "fill_u64": 8 * P, "project_scatter": 16 * N, "preprocess_tile": 8 * P + 16 * N + (48 + 16) * P,
         "normals_erode": 32 * P + 32 * P, "floodfill": 32 * P + 16 * P,
         "icp_fused": (96 if semantic else 64) * P, "icp_jacobian": (96 if semantic else 64) * P,
         "render_scatter": 48 * S, "render_resolve": 3 * 8 * P + 4 * 48 * P,

@@ -40,9 +40,8 @@ struct sb_ctx {
   Profiler prof;
 
   // ---- preprocessing scratch
-  unsigned long long* keys_data = nullptr;  // P_data
-  float4* sem_raw = nullptr;
-  float4* eroded = nullptr;
+  PrepKeys prep;            // two alternating z-buffer key images of the scan projection (+ TMA maps)
+  bool prepped_for_update = false;  // radius map / index keys / integrated flags of c->cur are ready (pipeline mode)
   float4* d_pts = nullptr;
   float* d_labels = nullptr;
   float* d_probs = nullptr;
@@ -244,7 +243,7 @@ int frame_create(sb_ctx* c, int w, int h, sb_frame** out) {
 }
 
 int release_buffers(sb_ctx* c) {
-  cudaFree(c->keys_data); cudaFree(c->sem_raw); cudaFree(c->eroded);
+  cudaFree(c->prep.img[0]); cudaFree(c->prep.img[1]);
   cudaFree(c->d_pts); cudaFree(c->d_labels); cudaFree(c->d_probs);
   cudaFree(c->gn); cudaFree(c->gn2); cudaFree(c->acc32); cudaFree(c->acc_slots); cudaFree(c->ticket);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -308,9 +307,14 @@ int reset_state(sb_ctx* c) {
 int alloc_buffers(sb_ctx* c) {
   const sb_params& p = c->p;
   size_t Pd = (size_t)p.data_width * p.data_height, Pm = (size_t)p.model_width * p.model_height;
-  SB_CUDA(c, cudaMalloc(&c->keys_data, Pd * 8));
-  SB_CUDA(c, cudaMalloc(&c->sem_raw, Pd * 16));
-  SB_CUDA(c, cudaMalloc(&c->eroded, Pd * 16));
+  const size_t Pk = preprocess_key_elems(p.data_width, p.data_height);
+  for (int i = 0; i < 2; ++i) {
+    SB_CUDA(c, cudaMalloc(&c->prep.img[i], Pk * 8));
+    c->prep.tmap_ok[i] = make_key_tensor_map(&c->prep.tmap[i], c->prep.img[i], p.data_width, p.data_height);
+  }
+  // TMA staging of the key tiles: default on for large range images, SUMA_B200_PREP_TMA=0/1 overrides
+  c->prep.use_tma = Pd >= (size_t)256 * 1024;
+  if (const char* e = getenv("SUMA_B200_PREP_TMA")) c->prep.use_tma = atoi(e) != 0;
   c->pts_cap = Pd * 2 + 1024;
   SB_CUDA(c, cudaMalloc(&c->d_pts, c->pts_cap * 16));
   SB_CUDA(c, cudaMalloc(&c->d_labels, c->pts_cap * 4));
@@ -350,7 +354,9 @@ int alloc_buffers(sb_ctx* c) {
   c->key_new = c->key_old + Pm;
   c->key_comp = c->key_old + 2 * Pm;
   SB_CUDA(c, cudaMemsetAsync(c->key_old, 0xff, Pm * 8 * 3, c->stream));
-  SB_CUDA(c, cudaMemsetAsync(c->keys_data, 0xff, Pd * 8, c->stream));
+  for (int i = 0; i < 2; ++i)
+    SB_CUDA(c, cudaMemsetAsync(c->prep.img[i], 0xff, preprocess_key_elems(c->p.data_width, c->p.data_height) * 8, c->stream));
+  c->prep.cur = 0;
   SB_CUDA(c, cudaMalloc(&c->key_index, Pd * 8));
   SB_CUDA(c, cudaMalloc(&c->radius_map, Pd * 16));
   SB_CUDA(c, cudaMalloc(&c->integrated, Pd));
@@ -752,12 +758,12 @@ int map_update(sb_ctx* c, const float* pose, const sb_frame* frame, const Mat4* 
   }
   // K6a
   launch_pose_products(L, mat4_from(inv_pose), inv_dev, c->poses, c->Mtab_old, pose_table_count(c));
-  launch_fill_u64(L, c->key_index, ~0ull, Pd);
+  // K6b (+ index keys re-armed, integrated flags cleared) -- already done by the tiled preprocessing pass of this scan
+  // when the frame is the one it produced
+  if (!(c->prepped_for_update && frame == c->cur)) launch_radius(L, kp, frame->d, c->radius_map, c->key_index, c->integrated);
+  c->prepped_for_update = false;
   launch_index_scatter(L, kp, c->A, c->d_counts, n_grid(c), c->Mtab_old, c->key_index);
-  // K6b
-  launch_radius(L, kp, frame->d, c->radius_map);
   // K6c + K6e predicate
-  SB_CUDA(c, cudaMemsetAsync(c->integrated, 0, Pd, c->stream));
   float2 ctr = submap_center(c, c->origin_i, c->origin_j);
   float extent = 2.0f * c->p.submap_dimension * c->p.submap_extent + c->p.submap_extent;  // :674
   if (c->p.partial_extraction && !c->extraction.empty()) extent += 2.0f * c->p.submap_extent;  // :677
@@ -1135,7 +1141,7 @@ int sb_preprocess(sb_ctx* c, const float* pts4, const float* labels, const float
   const float4* dp; const float* dl; const float* dq;
   int r = upload_scan(c, pts4, labels, probs, n, on_device, &dp, &dl, &dq);
   if (r) return r;
-  launch_preprocess(L_(c), c->kp, dp, dl, dq, n, timestamp, c->keys_data, c->sem_raw, c->eroded, out->d);
+  launch_preprocess(L_(c), c->kp, dp, dl, dq, n, timestamp, c->prep, out->d, nullptr, nullptr, nullptr);
   SB_CUDA(c, cudaGetLastError());
   return SB_OK;
 }
@@ -1372,7 +1378,8 @@ int sb_process_scan(sb_ctx* c, const float* pts4, const float* labels, const flo
   c->cur_has_semantics = labels != nullptr;
   // ---- everything below is enqueued on the stream without a host round trip; ONE synchronisation at the end ----
   // preprocess(), :342-358
-  launch_preprocess(L, c->kp, dp, dl, dq, n, c->timestamp, c->keys_data, c->sem_raw, c->eroded, c->cur->d);
+  launch_preprocess(L, c->kp, dp, dl, dq, n, c->timestamp, c->prep, c->cur->d, c->radius_map, c->key_index, c->integrated);
+  c->prepped_for_update = true;
   float ct = conf_threshold(c);
   float Pold[16], Pnew[16];
   cast_f(c->currentPose_old, Pold);

@@ -1,6 +1,7 @@
 // sb_internal.cuh -- internal declarations shared by the kernels and the C-ABI layer of libsuma_b200.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
@@ -108,7 +109,7 @@ struct PoseDev {
 
 // ---------------- kernel ids (launch accounting + the optional CUDA-event profiler) ----------------
 enum KernelId {
-  K_FILL = 0, K_PROJECT_SCATTER, K_PROJECT_RESOLVE, K_NORMALS_ERODE, K_FLOODFILL, K_ICP_JACOBIAN, K_GN_INIT,
+  K_FILL = 0, K_PROJECT_SCATTER, K_PREPROCESS_TILE, K_ICP_JACOBIAN, K_GN_INIT,
   K_ICP_FUSED, K_POSE_PRODUCTS, K_RENDER_SCATTER, K_RENDER_RESOLVE, K_INDEX_SCATTER, K_RADIUS, K_UPDATE_SURFELS,
   K_GEN_SURFELS, K_EXTRACT_FLAGS, K_SCAN_BLOCKS, K_COMPACT_SCATTER, K_AOS_TO_SOA, K_SOA_TO_AOS, K_COUNT
 };
@@ -151,9 +152,20 @@ struct ScopedKernel {
 };
 
 // sb_preprocess.cu
+// the two alternating z-buffer key images of the scan projection ([H][W+6] each, see sb_preprocess.cu) and their TMA maps
+struct PrepKeys {
+  unsigned long long* img[2] = {nullptr, nullptr};
+  int cur = 0;
+  bool use_tma = false;
+  bool tmap_ok[2] = {false, false};
+  CUtensorMap tmap[2];
+};
+size_t preprocess_key_elems(int W, int H);
+bool make_key_tensor_map(CUtensorMap* out, const unsigned long long* keys, int W, int H);
+// K1-K3 (+ optionally K6b radius map and the re-arming of the index-map keys / integrated flags for the map update)
 void launch_preprocess(const Launch& L, const KParams& kp, const float4* pts, const float* labels, const float* probs,
-                       uint32_t n, uint32_t timestamp, unsigned long long* keys, float4* sem_raw, float4* eroded,
-                       FrameDev out);
+                       uint32_t n, uint32_t timestamp, PrepKeys& keys, FrameDev out, float4* radius_map,
+                       unsigned long long* index_keys, uint8_t* integrated);
 
 // sb_icp.cu
 void launch_icp_jacobian(const Launch& L, const KParams& kp, const IcpArgs& a, const Mat4& pose, int iteration,
@@ -193,7 +205,8 @@ void launch_render_resolve(const Launch& L, const KParams& kp, SurfelPlanes s, c
                            int keep_semantic, int lequal);
 void launch_index_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, const uint32_t* n_dev, uint32_t n_upper,
                           const float* M, unsigned long long* keys);
-void launch_radius(const Launch& L, const KParams& kp, FrameDev frame, float4* radius_map);
+void launch_radius(const Launch& L, const KParams& kp, FrameDev frame, float4* radius_map, unsigned long long* index_keys,
+                   uint8_t* integrated);
 void launch_update_surfels(const Launch& L, const KParams& kp, SurfelPlanes src, SurfelPlanes tmp, const uint32_t* n_dev,
                            uint32_t n_upper, const Mat4& pose, const Mat4& inv_pose, const Mat4* pose_dev,
                            const Mat4* inv_pose_dev, const float* poses,

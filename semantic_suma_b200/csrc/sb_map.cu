@@ -21,7 +21,7 @@ using namespace sbm;
 constexpr int kThreads = 256;
 
 const char* kernel_name(int id) {
-  static const char* names[K_COUNT] = {"fill_u64", "project_scatter", "project_resolve", "normals_erode", "floodfill",
+  static const char* names[K_COUNT] = {"fill_u64", "project_scatter", "preprocess_tile",
                                        "icp_jacobian", "gn_init", "icp_fused", "pose_products", "render_scatter",
                                        "render_resolve", "index_scatter", "radius", "update_surfels", "gen_surfels",
                                        "extract_flags", "scan_blocks", "compact_scatter", "aos_to_soa", "soa_to_aos"};
@@ -718,9 +718,15 @@ void launch_index_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, co
 }
 
 // K6b: init_radiusConf.vert:41-68
-__global__ void __launch_bounds__(kThreads) k_radius(KParams kp, FrameDev f, float4* __restrict__ radius_map) {
+// (+ re-arms the index-map key image and clears the "measurement integrated" flags of the pixel: the prologue of a
+// stand-alone map update; in the per-scan pipeline the tiled preprocessing pass has already done all three)
+__global__ void __launch_bounds__(kThreads) k_radius(KParams kp, FrameDev f, float4* __restrict__ radius_map,
+                                                    unsigned long long* __restrict__ index_keys,
+                                                    uint8_t* __restrict__ integrated) {
   int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= kp.W * kp.H) return;
+  index_keys[pix] = ~0ull;
+  integrated[pix] = 0;
   float4 V = __ldg(f.vertex + pix), N = __ldg(f.normal + pix);
   float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
   V3 v = mk3(V.x, V.y, V.z), n = mk3(N.x, N.y, N.z);
@@ -738,11 +744,12 @@ __global__ void __launch_bounds__(kThreads) k_radius(KParams kp, FrameDev f, flo
   radius_map[pix] = o;
 }
 
-void launch_radius(const Launch& L, const KParams& kp, FrameDev frame, float4* radius_map) {
+void launch_radius(const Launch& L, const KParams& kp, FrameDev frame, float4* radius_map, unsigned long long* index_keys,
+                   uint8_t* integrated) {
   int P = kp.W * kp.H;
   {
     ScopedKernel sk(L, K_RADIUS);
-    k_radius<<<(P + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, frame, radius_map);
+    k_radius<<<(P + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, frame, radius_map, index_keys, integrated);
   }
 }
 
