@@ -71,8 +71,7 @@ struct sb_ctx {
   void* h_pinned = nullptr;  // pinned staging for small read-backs (64 KiB)
   int icp_blocks = 296;
   int icp_coop_blocks = 0;  // > 0: the persistent cooperative Gauss-Newton kernel is available
-  unsigned long long* icp_trace_host = nullptr;
-  unsigned long long* icp_trace = nullptr;  // optional %globaltimer stamps of the GN phases (SUMA_B200_ICP_TRACE=1)
+  unsigned int epoch_base = 0;  // epoch words of the persistent GN kernel: each launch owns a fresh range of values
 
   // ---- map
   SurfelPlanes A{}, T{}, G{}, X{};  // current surfels, updated (same index), generated (per pixel), extraction buffer
@@ -94,11 +93,13 @@ struct sb_ctx {
   unsigned long long* key_index = nullptr;
   float4* radius_map = nullptr;
   uint8_t* integrated = nullptr;
+  uint32_t* group_counts = nullptr;  // kGroupCounts totals of the update pass (64 blocks each)
   sb_frame* f_old = nullptr;
   sb_frame* f_new = nullptr;
   sb_frame* f_comp = nullptr;
   uint32_t n_host = 0;   // surfel count (exact; refreshed after every update)
   uint32_t n_upper = 0;  // upper bound used for grid sizing while the exact count is still in flight
+  char* result_block = nullptr;  // pd | acc32 | d_counts in one allocation (one device-to-host copy per scan)
   PoseDev* pd = nullptr; // device-resident pose bookkeeping of the pipeline
   uint32_t n_updated = 0, n_new = 0;
   uint32_t map_timestamp = 0;
@@ -245,14 +246,14 @@ int frame_create(sb_ctx* c, int w, int h, sb_frame** out) {
 int release_buffers(sb_ctx* c) {
   cudaFree(c->prep.img[0]); cudaFree(c->prep.img[1]);
   cudaFree(c->d_pts); cudaFree(c->d_labels); cudaFree(c->d_probs);
-  cudaFree(c->gn); cudaFree(c->gn2); cudaFree(c->acc32); cudaFree(c->acc_slots); cudaFree(c->ticket);
+  cudaFree(c->gn); cudaFree(c->gn2); cudaFree(c->acc_slots); cudaFree(c->ticket);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   free_planes(&c->A); free_planes(&c->T); free_planes(&c->G); free_planes(&c->X); free_planes(&c->pool);
   cudaFree(c->d_pool_top); cudaFree(c->d_tile_rec);
-  cudaFree(c->keep); cudaFree(c->block_counts); cudaFree(c->block_offsets); cudaFree(c->d_counts);
+  cudaFree(c->keep); cudaFree(c->block_counts); cudaFree(c->block_offsets);
   cudaFree(c->lb_desc); cudaFree(c->lb_ticket);
   cudaFree(c->poses); cudaFree(c->poses_inv); cudaFree(c->Mtab_old); cudaFree(c->Mtab_new);
-  cudaFree(c->key_old); cudaFree(c->key_index); cudaFree(c->radius_map); cudaFree(c->integrated);
+  cudaFree(c->key_old); cudaFree(c->key_index); cudaFree(c->radius_map); cudaFree(c->integrated); cudaFree(c->group_counts);
   sb_frame* fr[] = {c->f_old, c->f_new, c->f_comp, c->cur, c->last, c->cur_model, c->last_model};
   for (sb_frame* f : fr)
     if (f) {
@@ -261,7 +262,7 @@ int release_buffers(sb_ctx* c) {
     }
   cudaFree(c->mailbox);
   cudaFree(c->comm_epoch);
-  cudaFree(c->pd);
+  cudaFree(c->result_block);
   return SB_OK;
 }
 
@@ -307,13 +308,22 @@ int reset_state(sb_ctx* c) {
 int alloc_buffers(sb_ctx* c) {
   const sb_params& p = c->p;
   size_t Pd = (size_t)p.data_width * p.data_height, Pm = (size_t)p.model_width * p.model_height;
+  // the per-scan results live in ONE device block with the layout of the pinned host mirror, so that the end of a scan is
+  // a single device-to-host copy: [0] PoseDev, [4096] 64 int64 statistics sums, [8192] 16 uint32 surfel counts
+  static_assert(sizeof(PoseDev) <= 4096, "PoseDev must fit the first page of the result block");
+  SB_CUDA(c, cudaMalloc(&c->result_block, 8192 + 64));
+  SB_CUDA(c, cudaMemsetAsync(c->result_block, 0, 8192 + 64, c->stream));
+  c->pd = reinterpret_cast<PoseDev*>(c->result_block);
+  c->acc32 = reinterpret_cast<long long*>(c->result_block + 4096);
+  c->d_counts = reinterpret_cast<uint32_t*>(c->result_block + 8192);
   const size_t Pk = preprocess_key_elems(p.data_width, p.data_height);
   for (int i = 0; i < 2; ++i) {
     SB_CUDA(c, cudaMalloc(&c->prep.img[i], Pk * 8));
     c->prep.tmap_ok[i] = make_key_tensor_map(&c->prep.tmap[i], c->prep.img[i], p.data_width, p.data_height);
   }
-  // TMA staging of the key tiles: default on for large range images, SUMA_B200_PREP_TMA=0/1 overrides
-  c->prep.use_tma = Pd >= (size_t)256 * 1024;
+  // TMA staging of the key tiles: measured 2 % (64x2048) / 1.5 % (128x4096) faster than plain loads; SUMA_B200_PREP_TMA=0
+  // selects the plain-load instantiation
+  c->prep.use_tma = true;
   if (const char* e = getenv("SUMA_B200_PREP_TMA")) c->prep.use_tma = atoi(e) != 0;
   c->pts_cap = Pd * 2 + 1024;
   SB_CUDA(c, cudaMalloc(&c->d_pts, c->pts_cap * 16));
@@ -322,12 +332,10 @@ int alloc_buffers(sb_ctx* c) {
   SB_CUDA(c, cudaMalloc(&c->gn, sizeof(GnState)));
   SB_CUDA(c, cudaMalloc(&c->gn2, sizeof(GnState)));
   SB_CUDA(c, cudaMemsetAsync(c->gn2, 0, sizeof(GnState), c->stream));
-  SB_CUDA(c, cudaMalloc(&c->acc32, 64 * sizeof(long long)));
   SB_CUDA(c, cudaMalloc(&c->acc_slots, 1024 * 32 * sizeof(long long)));
   SB_CUDA(c, cudaMemsetAsync(c->acc_slots, 0, 1024 * 32 * sizeof(long long), c->stream));
   SB_CUDA(c, cudaMalloc(&c->ticket, 128));
   SB_CUDA(c, cudaMemsetAsync(c->ticket, 0, 128, c->stream));
-  SB_CUDA(c, cudaMemsetAsync(c->acc32, 0, 64 * sizeof(long long), c->stream));
   SB_CUDA(c, cudaMallocHost(&c->h_pinned, 65536));
   int r;
   if ((r = alloc_planes(c, &c->A, kMaxSurfels))) return r;
@@ -341,7 +349,6 @@ int alloc_buffers(sb_ctx* c) {
   size_t nb = (kMaxSurfels + 127) / 128 + 16;  // blocks of the finest-grained surfel kernel
   SB_CUDA(c, cudaMalloc(&c->block_counts, nb * 4));
   SB_CUDA(c, cudaMalloc(&c->block_offsets, nb * 4));
-  SB_CUDA(c, cudaMalloc(&c->d_counts, 16 * sizeof(uint32_t)));
   SB_CUDA(c, cudaMalloc(&c->lb_desc, (nb + 16) * 8));
   SB_CUDA(c, cudaMemsetAsync(c->lb_desc, 0, (nb + 16) * 8, c->stream));
   SB_CUDA(c, cudaMalloc(&c->lb_ticket, 64));
@@ -360,7 +367,8 @@ int alloc_buffers(sb_ctx* c) {
   SB_CUDA(c, cudaMalloc(&c->key_index, Pd * 8));
   SB_CUDA(c, cudaMalloc(&c->radius_map, Pd * 16));
   SB_CUDA(c, cudaMalloc(&c->integrated, Pd));
-  SB_CUDA(c, cudaMalloc(&c->pd, sizeof(PoseDev)));
+  SB_CUDA(c, cudaMalloc(&c->group_counts, kGroupCounts * 4));
+  SB_CUDA(c, cudaMemsetAsync(c->group_counts, 0, kGroupCounts * 4, c->stream));
   SB_CUDA(c, cudaMalloc(&c->comm_epoch, 64));
   SB_CUDA(c, cudaMemsetAsync(c->comm_epoch, 0, 64, c->stream));
   if ((r = frame_create(c, p.model_width, p.model_height, &c->f_old))) return r;
@@ -441,13 +449,13 @@ int render_full(sb_ctx* c, const float* pose_old, const float* pose_new, float c
       launch_render_scatter(L, kp, c->A, c->d_counts, n_grid(c), c->Mtab_old, conf_thr, thr, 1, 0, 0, to);
       launch_render_scatter(L, kp, c->A, c->d_counts, n_grid(c), Mnew, conf_thr, thr, 0, 1, 0, tn);
     }
-    launch_render_resolve(L, kp, c->A, c->Mtab_old, Mnew, t, c->f_old->d, c->f_new->d, c->f_comp->d, out->d, 0, 0);
+    launch_render_resolve(L, kp, c->A, c->Mtab_old, Mnew, t, c->f_old->d, c->f_new->d, c->f_comp->d, out->d, null_frame(), 0, 0);
   } else {
     // SurfelMap.cpp:977-1017: one view with render_old_surfels = false, timestamp_threshold = 0, copied to old and new
     RenderTargets t{nullptr, c->key_new, nullptr};
     launch_render_scatter(L, kp, c->A, c->d_counts, n_grid(c), c->Mtab_old, conf_thr, 0, 0, 1, 0, t);
     launch_render_resolve(L, kp, c->A, c->Mtab_old, c->Mtab_old, t, null_frame(), c->f_new->d, null_frame(), null_frame(),
-                          0, 0);
+                          null_frame(), 0, 0);
     SB_CUDA(c, cudaMemcpyAsync(c->f_old->base, c->f_new->base, Pm * 48, cudaMemcpyDeviceToDevice, c->stream));
     SB_CUDA(c, cudaMemcpyAsync(out->base, c->f_new->base, Pm * 48, cudaMemcpyDeviceToDevice, c->stream));
   }
@@ -467,26 +475,39 @@ int render_full(sb_ctx* c, const float* pose_old, const float* pose_new, float c
 }
 
 // which: 1 = active (new surfels into newMapFrame), 0 = inactive (old surfels into oldMapFrame); Q4: semantic map kept
-int render_single(sb_ctx* c, const float* pose, float conf_thr, int which, const Mat4* inv_dev = nullptr) {
+int render_single(sb_ctx* c, const float* pose, float conf_thr, int which, const Mat4* inv_dev = nullptr,
+                  bool table_ready = false, sb_frame* copy_to = nullptr) {
   c->rkey_valid = false;  // overwrites vertex / normal of the new (or old) map frame
   const KParams& kp = c->kp;
   Launch L = L_(c);
   size_t Pm = (size_t)kp.Wm * kp.Hm;
   float inv[16] = {0};
   if (pose) sbg::rigid_inverse_f(pose, inv);
-  launch_pose_products(L, mat4_from(inv), inv_dev, c->poses, c->Mtab_old, pose_table_count(c));
+  if (!table_ready) launch_pose_products(L, mat4_from(inv), inv_dev, c->poses, c->Mtab_old, pose_table_count(c));
   unsigned long long* key = which ? c->key_new : c->key_old;
   RenderTargets t{which ? nullptr : key, which ? key : nullptr, nullptr};
   launch_render_scatter(L, kp, c->A, c->d_counts, n_grid(c), c->Mtab_old, conf_thr, t_threshold(c), which ? 0 : 1,
                         which ? 1 : 0, 0, t);
-  launch_render_resolve(L, kp, c->A, c->Mtab_old, c->Mtab_old, t, c->f_old->d, c->f_new->d, null_frame(), null_frame(), 1,
-                        0);
+  // copy_to: lastModelFrame_->copy(*map_->newMapFrame()), SurfelMapping.cpp:407 (the semantic image is the stale one, Q4),
+  // written by the same resolve pass
+  launch_render_resolve(L, kp, c->A, c->Mtab_old, c->Mtab_old, t, c->f_old->d, c->f_new->d, null_frame(), null_frame(),
+                        (copy_to && which) ? copy_to->d : null_frame(), 1, 0);
+  if (copy_to && !which)
+    SB_CUDA(c, cudaMemcpyAsync(copy_to->base, c->f_old->base, Pm * 48, cudaMemcpyDeviceToDevice, c->stream));
   return SB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // ICP
 // ---------------------------------------------------------------------------------------------------------
+// every launch of the persistent Gauss-Newton kernel publishes epoch values base+1 .. base+max_iter+2: hand out disjoint
+// ranges so that the epoch word never has to be reset between launches
+unsigned int next_epoch_base(sb_ctx* c, int max_iter) {
+  unsigned int b = c->epoch_base;
+  c->epoch_base += (unsigned int)max_iter + 8u;
+  return b;
+}
+
 IcpArgs icp_args(sb_ctx* c, const sb_frame* data, const sb_frame* model, float max_distance, float max_angle_deg,
                  int row_begin, int row_end, bool semantics) {
   IcpArgs a;
@@ -535,7 +556,7 @@ struct GnHead {  // prefix of GnState copied back / uploaded
   double pose[16];
   double last_error;
   double out48[48];
-  int k, done, history_len, pad;
+  int k, done, history_len, error;
 };
 
 // Row-striped minimisation with a host-side all-reduce callback: LieGaussNewton::minimize driven from the host, one
@@ -543,7 +564,9 @@ struct GnHead {  // prefix of GnState copied back / uploaded
 // that the rest of the pipeline proceeds as after the device-resident loop.
 int icp_minimize_callback(sb_ctx* c, const sb_frame* data, const sb_frame* model, const double* T0, int max_iter,
                           double eps, double delta, float max_distance, float max_angle_deg, bool semantics) {
-  IcpArgs a = icp_args(c, data, model, max_distance, max_angle_deg, c->row_begin, c->row_end, semantics);
+  const bool striped = c->comm_cb != nullptr;
+  IcpArgs a = icp_args(c, data, model, max_distance, max_angle_deg, striped ? c->row_begin : 0, striped ? c->row_end : c->kp.H,
+                       semantics);
   std::vector<double> hist;
   GnHead h;
   memset(&h, 0, sizeof(h));
@@ -560,7 +583,7 @@ int icp_minimize_callback(sb_ctx* c, const sb_frame* data, const sb_frame* model
     SB_CUDA(c, cudaStreamSynchronize(c->stream));
     long long raw[32];
     memcpy(raw, c->h_pinned, sizeof(raw));
-    if (c->comm_cb(c->comm_cb_user, (int64_t*)raw) != 0) return fail(c, SB_ERR_STATE, "all-reduce callback failed");
+    if (c->comm_cb && c->comm_cb(c->comm_cb_user, (int64_t*)raw) != 0) return fail(c, SB_ERR_STATE, "all-reduce callback failed");
     sbg::unpack48(raw, h.out48);
     double dx[6];
     int result = sbg::gn_step(h.out48, h.last_error, eps, delta, h.pose, dx);
@@ -602,19 +625,26 @@ int icp_minimize_enqueue(sb_ctx* c, const sb_frame* data, const sb_frame* model,
   Mat4d T;
   memcpy(T.m, T0, sizeof(T.m));
   Launch L = L_(c);
-  launch_gn_init(L, c->gn, T, c->acc32, c->ticket, c->ticket + 8);
   if (c->icp_coop_blocks > 0) {
     // one cooperative launch for the whole minimisation
-    if (launch_icp_persistent(L, c->kp, a, c->gn, c->acc_slots, c->ticket, c->ticket + 8, max_iter, eps, delta,
-                              c->comm_on ? &c->comm : nullptr, c->icp_coop_blocks, c->icp_trace) == 0)
+    launch_gn_init(L, c->gn, T, c->acc32);
+    GnJob job;
+    memset(&job, 0, sizeof(job));
+    job.mode = GN_PLAIN;
+    job.a = a;
+    job.st = c->gn;
+    job.max_iter = max_iter;
+    job.eps = eps;
+    job.delta = delta;
+    job.epoch_base = next_epoch_base(c, max_iter);
+    if (launch_gn_persistent(L, c->kp, job, c->acc_slots, c->ticket, c->ticket + 8, c->comm_on ? &c->comm : nullptr,
+                             c->icp_coop_blocks) == 0)
       return SB_OK;
     cudaGetLastError();
-    c->icp_coop_blocks = 0;  // fall back to one launch per iteration
+    c->icp_coop_blocks = 0;  // no cooperative launch on this device / context: drive the loop from the host
   }
-  for (int i = 0; i < max_iter; ++i)
-    launch_icp_fused_iteration(L, c->kp, a, c->gn, c->acc32, c->ticket, max_iter, eps, delta,
-                               c->comm_on ? &c->comm : nullptr, c->icp_blocks);
-  return SB_OK;
+  if (c->comm_on) return fail(c, SB_ERR_STATE, "the fused peer exchange needs a cooperative launch");
+  return icp_minimize_callback(c, data, model, T0, max_iter, eps, delta, max_distance, max_angle_deg, semantics);
 }
 
 int icp_minimize_fetch(sb_ctx* c, double* pose_out, double* out48, int* iters, double* history, int* history_len) {
@@ -622,6 +652,7 @@ int icp_minimize_fetch(sb_ctx* c, double* pose_out, double* out48, int* iters, d
   SB_CUDA(c, cudaStreamSynchronize(c->stream));
   GnHead h;
   memcpy(&h, c->h_pinned, sizeof(h));
+  if (h.error) return fail(c, SB_ERR_STATE, "Gauss-Newton kernel timed out waiting for a block or a peer GPU");
   if (pose_out) memcpy(pose_out, h.pose, sizeof(h.pose));
   if (out48) memcpy(out48, h.out48, sizeof(h.out48));
   if (iters) *iters = h.k;
@@ -741,7 +772,7 @@ int update_active_submaps(sb_ctx* c, const float* pose) {  // SurfelMap.cpp:744-
 // pose_dev / inv_dev != nullptr: pipeline mode -- the pose (and its pose-table entry) already lives on the device,
 // nothing is read back here; the caller finishes with map_update_finish() after its end-of-scan synchronisation.
 int map_update(sb_ctx* c, const float* pose, const sb_frame* frame, const Mat4* pose_dev = nullptr,
-               const Mat4* inv_dev = nullptr) {
+               const Mat4* inv_dev = nullptr, bool table_ready = false) {
   c->map_version += 1;
   const KParams& kp = c->kp;
   Launch L = L_(c);
@@ -756,11 +787,11 @@ int map_update(sb_ctx* c, const float* pose, const sb_frame* frame, const Mat4* 
     sbg::rigid_inverse_f(pose, inv_pose);  // :497
     memcpy(pose_h, pose, 64);
   }
-  // K6a
-  launch_pose_products(L, mat4_from(inv_pose), inv_dev, c->poses, c->Mtab_old, pose_table_count(c));
+  // K6a (table_ready: the Gauss-Newton kernel of this scan has already filled inv(pose) * poses[t])
+  if (!table_ready) launch_pose_products(L, mat4_from(inv_pose), inv_dev, c->poses, c->Mtab_old, pose_table_count(c));
   // K6b (+ index keys re-armed, integrated flags cleared) -- already done by the tiled preprocessing pass of this scan
   // when the frame is the one it produced
-  if (!(c->prepped_for_update && frame == c->cur)) launch_radius(L, kp, frame->d, c->radius_map, c->key_index, c->integrated);
+  if (!(c->prepped_for_update && frame == c->cur)) launch_radius(L, kp, frame->d, c->radius_map, c->key_index, c->integrated, c->group_counts);
   c->prepped_for_update = false;
   launch_index_scatter(L, kp, c->A, c->d_counts, n_grid(c), c->Mtab_old, c->key_index);
   // K6c + K6e predicate
@@ -772,9 +803,9 @@ int map_update(sb_ctx* c, const float* pose, const sb_frame* frame, const Mat4* 
   // finish their heavy per-surfel work together and then resolve their offsets through a ~1000-block look-back chain.)
   launch_update_surfels(L, kp, c->A, c->T, c->d_counts, n_grid(c), mat4_from(pose_h), mat4_from(inv_pose), pose_dev,
                         inv_dev, c->poses, c->poses_inv, c->key_index, c->radius_map, frame->d, (int)c->map_timestamp,
-                        ctr, extent, c->integrated, c->keep, c->block_counts);
-  launch_compact(L, c->T, c->keep, c->block_counts, c->block_offsets, c->d_counts, n_grid(c), c->A, nullptr, kMaxSurfels,
-                 c->d_counts + 1, c->d_counts + 2);
+                        ctr, extent, c->integrated, c->keep, c->block_counts, c->group_counts);
+  launch_compact_update(L, c->T, c->keep, c->block_counts, c->group_counts, c->d_counts, n_grid(c), c->A, kMaxSurfels,
+                        c->d_counts + 1, c->d_counts + 2);
   // K6d + K6e: new surfels appended behind the updated ones; counts[0] = new map size, counts[3] = new surfels
   c->lb_gen = (c->lb_gen + 1) & 0x3fffffffu;
   if (c->lb_gen == 0) c->lb_gen = 1;
@@ -872,73 +903,106 @@ int upload_scan(sb_ctx* c, const float* pts4, const float* labels, const float* 
   return SB_OK;
 }
 
-// SurfelMapping::updatePose, SurfelMapping.cpp:372-476 -- enqueue only. The increment, the track-loss decision and the
-// pose chaining stay on the device (k_pose_after_icp / k_gn_init_fallback / k_pose_finalize).
-int update_pose_enqueue(sb_ctx* c) {
+// SurfelMapping::updatePose, SurfelMapping.cpp:372-476 -- enqueue only. The increment, the track-loss decision, the
+// recovery minimisation and the pose chaining stay on the device: two cooperative launches (GN_MAIN, GN_POST) around the
+// rendering of the active map at the new pose. Returns with *tables_ready = true when GN_POST has also written the pose
+// table entry of this scan and the table inv(P_cur) * poses[t] (Mtab_old) for the map update / model rendering.
+int update_pose_enqueue(sb_ctx* c, bool* tables_ready) {
   const sb_params& p = c->p;
+  const bool sem = c->cur_has_semantics;
+  *tables_ready = false;
+  int r;
+  Launch L = L_(c);
+  const uint32_t np = pose_table_count(c);
+  int max_iter = p.max_iterations;
+  if (max_iter <= 0 || max_iter > kMaxGnIter) max_iter = kMaxGnIter;
+  const int r0 = c->comm_on ? c->row_begin : 0, r1 = c->comm_on ? c->row_end : c->kp.H;
+  if (!c->comm_cb && c->icp_coop_blocks > 0) {
+    // ---- device-resident path ----
+    GnJob job;
+    memset(&job, 0, sizeof(job));
+    job.mode = GN_MAIN;  // objective_->setData(currentFrame_, map_->newMapFrame()); gn_->minimize(*objective_, T0)   :384-389
+    job.a = icp_args(c, c->cur, c->f_new, p.icp_max_distance, p.icp_max_angle, r0, r1, sem);
+    job.st = c->gn;
+    job.pd = c->pd;
+    job.Mtab = c->Mtab_old;
+    job.poses = c->poses;
+    job.n_poses = np;
+    job.initialize_identity = p.initialize_identity;
+    job.fallback_mode = p.fallback_mode;
+    job.timestamp = c->timestamp;
+    job.max_iter = max_iter;
+    job.eps = p.stopping_threshold;
+    job.delta = p.delta;
+    job.epoch_base = next_epoch_base(c, max_iter);
+    if (launch_gn_persistent(L, c->kp, job, c->acc_slots, c->ticket, c->ticket + 8, c->comm_on ? &c->comm : nullptr,
+                             c->icp_coop_blocks) != 0) {
+      cudaGetLastError();
+      return fail(c, SB_ERR_CUDA, "cooperative launch of the Gauss-Newton kernel failed");
+    }
+    // :405-413: render_active at the new pose (its product table is ready), copied into lastModelFrame_
+    if ((r = render_single(c, nullptr, conf_threshold(c), 1, &c->pd->invP_active, true, c->last_model))) return r;
+    // :414-449: statistics pass at identity, track-loss recovery, pose chaining, pose-table entry, table for the update
+    GnJob post;
+    memset(&post, 0, sizeof(post));
+    post.mode = GN_POST;
+    post.a = icp_args(c, c->cur, c->f_new, p.icp_max_distance, p.icp_max_angle, 0, c->kp.H, sem);
+    post.fb = icp_args(c, c->cur, c->last, p.fallback_max_distance, p.fallback_max_angle, r0, r1,
+                       sem && c->last_has_semantics);
+    post.st = c->gn2;
+    post.pd = c->pd;
+    post.stats32 = c->acc32;
+    post.poses = c->poses;
+    post.poses_inv = c->poses_inv;
+    post.t_map = c->map_timestamp;
+    post.Mtab = c->Mtab_old;
+    post.n_poses = np;
+    post.fallback_mode = p.fallback_mode;
+    post.timestamp = c->timestamp;
+    post.max_iter = max_iter;
+    post.eps = p.stopping_threshold;
+    post.delta = p.delta;
+    post.epoch_base = next_epoch_base(c, max_iter);
+    if (launch_gn_persistent(L, c->kp, post, c->acc_slots, c->ticket, c->ticket + 8, c->comm_on ? &c->comm : nullptr,
+                             c->icp_coop_blocks) != 0) {
+      cudaGetLastError();
+      return fail(c, SB_ERR_CUDA, "cooperative launch of the Gauss-Newton kernel failed");
+    }
+    *tables_ready = true;
+    return SB_OK;
+  }
+  // ---- host-driven path (all-reduce callback, or no cooperative launch): the round-1 sequence of small launches ----
   double T0[16];
   if (!p.initialize_identity) memcpy(T0, c->lastIncrement, sizeof(T0)); else ident_d(T0);
-  const bool sem = c->cur_has_semantics;
-  int r;
-  // objective_->setData(currentFrame_, map_->newMapFrame()); gn_->minimize(*objective_, T0)   :384-389
   if ((r = icp_minimize_enqueue(c, c->cur, c->f_new, T0, p.max_iterations, p.stopping_threshold, p.delta,
                                 p.icp_max_distance, p.icp_max_angle, sem)))
     return r;
-  Launch L = L_(c);
   Mat4d T0v;
   memcpy(T0v.m, T0, sizeof(T0v.m));
   launch_pose_after_icp(L, c->gn, c->pd, T0v, c->timestamp, p.fallback_mode);
-  // :405-413: render_active at the new pose, copy into lastModelFrame_, statistics pass at identity
-  if ((r = render_single(c, nullptr, conf_threshold(c), 1, &c->pd->invP_active))) return r;
-  size_t Pm = (size_t)c->kp.Wm * c->kp.Hm;
-  SB_CUDA(c, cudaMemcpyAsync(c->last_model->base, c->f_new->base, Pm * 48, cudaMemcpyDeviceToDevice, c->stream));
+  if ((r = render_single(c, nullptr, conf_threshold(c), 1, &c->pd->invP_active, false, c->last_model))) return r;
   {
     IcpArgs a = icp_args(c, c->cur, c->f_new, p.icp_max_distance, p.icp_max_angle, 0, c->kp.H, sem);
     Mat4 I;
     for (int i = 0; i < 16; ++i) I.m[i] = (i % 5 == 0) ? 1.0f : 0.0f;
     launch_icp_jacobian(L, c->kp, a, I, 0, c->acc32, c->acc_slots, c->ticket + 16, c->icp_blocks);
   }
-  // :430-449 track-loss test (on the device) and the frame-to-frame fallback, which returns at once unless needed
-  if (p.fallback_mode && c->comm_cb) {
-    // host-driven exchange: read the track-loss flag and run the recovery minimisation only when it is set
+  if (p.fallback_mode) {  // read the track-loss flag and run the recovery minimisation only when it is set
     int fb = 0;
     SB_CUDA(c, cudaMemcpyAsync(c->h_pinned, (const char*)c->pd + offsetof(PoseDev, fallback), sizeof(int),
                                cudaMemcpyDeviceToHost, c->stream));
     SB_CUDA(c, cudaStreamSynchronize(c->stream));
     memcpy(&fb, c->h_pinned, sizeof(int));
-    launch_gn_init_fallback(L, c->gn2, c->pd, c->acc32 + 32, c->ticket, c->ticket + 8);
     if (fb) {
       GnState* keep = c->gn;
       c->gn = c->gn2;  // icp_minimize_callback writes its result into c->gn
-      int rr = icp_minimize_callback(c, c->cur, c->last, T0, p.max_iterations > 0 ? p.max_iterations : kMaxGnIter,
-                                     p.stopping_threshold, p.delta, p.fallback_max_distance, p.fallback_max_angle,
-                                     sem && c->last_has_semantics);
+      int rr = icp_minimize_callback(c, c->cur, c->last, T0, max_iter, p.stopping_threshold, p.delta,
+                                     p.fallback_max_distance, p.fallback_max_angle, sem && c->last_has_semantics);
       c->gn = keep;
       if (rr) return rr;
     }
-  } else if (p.fallback_mode) {
-    int max_iter = p.max_iterations;
-    if (max_iter <= 0 || max_iter > kMaxGnIter) max_iter = kMaxGnIter;
-    int r0 = 0, r1 = c->kp.H;
-    if (c->comm_on) {
-      r0 = c->row_begin;
-      r1 = c->row_end;
-    }
-    IcpArgs a = icp_args(c, c->cur, c->last, p.fallback_max_distance, p.fallback_max_angle, r0, r1,
-                         sem && c->last_has_semantics);
-    launch_gn_init_fallback(L, c->gn2, c->pd, c->acc32 + 32, c->ticket, c->ticket + 8);
-    bool launched = false;
-    if (c->icp_coop_blocks > 0)
-      launched = launch_icp_persistent(L, c->kp, a, c->gn2, c->acc_slots, c->ticket, c->ticket + 8, max_iter,
-                                       p.stopping_threshold, p.delta, c->comm_on ? &c->comm : nullptr,
-                                       c->icp_coop_blocks, nullptr) == 0;
-    if (!launched) {
-      cudaGetLastError();
-      for (int i = 0; i < max_iter; ++i)
-        launch_icp_fused_iteration(L, c->kp, a, c->gn2, c->acc32 + 32, c->ticket, max_iter, p.stopping_threshold,
-                                   p.delta, c->comm_on ? &c->comm : nullptr, c->icp_blocks);
-    }
   }
+  launch_pose_finalize(L, c->gn2, c->pd, 1, c->poses, c->poses_inv, c->map_timestamp);
   return SB_OK;
 }
 
@@ -1007,7 +1071,7 @@ int sb_create(const sb_params* p, int device, sb_ctx** out) {
   {
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-    int maxb = coop ? icp_persistent_max_blocks(c->sm_count) : 0;
+    int maxb = coop ? gn_persistent_max_blocks(c->sm_count) : 0;
     c->icp_coop_blocks = maxb < c->icp_blocks ? maxb : c->icp_blocks;
     if (c->icp_coop_blocks > 0) c->icp_coop_blocks = icp_balanced_blocks(p->data_width * p->data_height, c->icp_coop_blocks);
     c->icp_blocks = icp_balanced_blocks(p->data_width * p->data_height, c->icp_blocks);
@@ -1015,16 +1079,6 @@ int sb_create(const sb_params* p, int device, sb_ctx** out) {
     if (getenv("SUMA_B200_ICP_BLOCKS")) {
       int b = atoi(getenv("SUMA_B200_ICP_BLOCKS"));
       if (b > 0 && b <= maxb && b <= 1024) c->icp_coop_blocks = b;
-    }
-    if (getenv("SUMA_B200_ICP_TRACE")) {
-      if (std::string(getenv("SUMA_B200_ICP_TRACE")) == "host") {  // host-mapped: readable while a kernel hangs
-        cudaHostAlloc(&c->icp_trace_host, 4096 * 8, cudaHostAllocMapped);
-        memset(c->icp_trace_host, 0, 4096 * 8);
-        cudaHostGetDevicePointer((void**)&c->icp_trace, c->icp_trace_host, 0);
-      } else {
-        cudaMalloc(&c->icp_trace, 4096 * 8);
-        cudaMemset(c->icp_trace, 0, 4096 * 8);
-      }
     }
   }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -1141,7 +1195,7 @@ int sb_preprocess(sb_ctx* c, const float* pts4, const float* labels, const float
   const float4* dp; const float* dl; const float* dq;
   int r = upload_scan(c, pts4, labels, probs, n, on_device, &dp, &dl, &dq);
   if (r) return r;
-  launch_preprocess(L_(c), c->kp, dp, dl, dq, n, timestamp, c->prep, out->d, nullptr, nullptr, nullptr);
+  launch_preprocess(L_(c), c->kp, dp, dl, dq, n, timestamp, c->prep, out->d, nullptr, nullptr, nullptr, nullptr);
   SB_CUDA(c, cudaGetLastError());
   return SB_OK;
 }
@@ -1189,8 +1243,8 @@ int sb_map_render_composed(sb_ctx* c, const float pose_old[16], const float pose
   // GL_LEQUAL (SurfelMap.cpp:1126), old then new without clearing (:1146-1152); COLOR2 not attached (Q4)
   launch_render_scatter(L, kp, c->A, c->d_counts, n_grid(c), c->Mtab_old, conf_thr, thr, 1, 0, 1, t);
   launch_render_scatter(L, kp, c->A, c->d_counts, n_grid(c), c->Mtab_new, conf_thr, thr, 0, 1, 1, t);
-  launch_render_resolve(L, kp, c->A, c->Mtab_old, c->Mtab_new, t, null_frame(), null_frame(), c->f_comp->d, null_frame(), 1,
-                        1);
+  launch_render_resolve(L, kp, c->A, c->Mtab_old, c->Mtab_new, t, null_frame(), null_frame(), c->f_comp->d, null_frame(),
+                        null_frame(), 1, 1);
   SB_CUDA(c, cudaGetLastError());
   return SB_OK;
 }
@@ -1378,7 +1432,8 @@ int sb_process_scan(sb_ctx* c, const float* pts4, const float* labels, const flo
   c->cur_has_semantics = labels != nullptr;
   // ---- everything below is enqueued on the stream without a host round trip; ONE synchronisation at the end ----
   // preprocess(), :342-358
-  launch_preprocess(L, c->kp, dp, dl, dq, n, c->timestamp, c->prep, c->cur->d, c->radius_map, c->key_index, c->integrated);
+  launch_preprocess(L, c->kp, dp, dl, dq, n, c->timestamp, c->prep, c->cur->d, c->radius_map, c->key_index, c->integrated,
+                    c->group_counts);
   c->prepped_for_update = true;
   float ct = conf_threshold(c);
   float Pold[16], Pnew[16];
@@ -1386,24 +1441,27 @@ int sb_process_scan(sb_ctx* c, const float* pts4, const float* labels, const flo
   cast_f(c->currentPose_new, Pnew);
   if ((r = render_full(c, Pold, Pnew, ct, c->last_model))) return r;
   const bool had_icp = c->timestamp > 0;
-  if (had_icp && (r = update_pose_enqueue(c))) return r;
-  launch_pose_finalize(L, c->gn2, c->pd, had_icp ? 1 : 0, c->poses, c->poses_inv, c->map_timestamp);
+  bool tables_ready = false;
+  if (had_icp) {
+    if ((r = update_pose_enqueue(c, &tables_ready))) return r;
+  } else {
+    launch_pose_finalize(L, c->gn2, c->pd, 0, c->poses, c->poses_inv, c->map_timestamp);
+  }
   // updateMap(), :797-804
   const uint32_t t_map = c->map_timestamp;
-  if ((r = map_update(c, nullptr, c->cur, &c->pd->P_cur, &c->pd->invP_cur))) return r;
+  if ((r = map_update(c, nullptr, c->cur, &c->pd->P_cur, &c->pd->invP_cur, tables_ready))) return r;
   float ct2 = conf_threshold(c);
   if (p.render_after_update) {
     if ((r = render_full(c, nullptr, nullptr, ct2, c->cur_model, &c->pd->invP_cur, true))) return r;
   }
   // ---- the scan's results: pose block, statistics sums, surfel counts ----
   char* hp = (char*)c->h_pinned;
-  SB_CUDA(c, cudaMemcpyAsync(hp, c->pd, sizeof(PoseDev), cudaMemcpyDeviceToHost, c->stream));
-  SB_CUDA(c, cudaMemcpyAsync(hp + 4096, c->acc32, 32 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-  SB_CUDA(c, cudaMemcpyAsync(hp + 8192, c->d_counts, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  SB_CUDA(c, cudaMemcpyAsync(hp, c->result_block, 8192 + 64, cudaMemcpyDeviceToHost, c->stream));
   SB_CUDA(c, cudaStreamSynchronize(c->stream));
   SB_CUDA(c, cudaGetLastError());
   PoseDev pdh;
   memcpy(&pdh, hp, sizeof(pdh));
+  if (pdh.gn_error) return fail(c, SB_ERR_STATE, "Gauss-Newton kernel timed out waiting for a block or a peer GPU");
   memcpy(c->lastPose, pdh.lastPose, sizeof(c->lastPose));
   memcpy(c->currentPose, pdh.currentPose, sizeof(c->currentPose));
   memcpy(c->currentPose_old, pdh.currentPose, sizeof(c->currentPose));
@@ -1531,23 +1589,6 @@ int sb_get_statistics(sb_ctx* c, double stats[16]) {
   return SB_OK;
 }
 
-int sb_debug_icp_block_states(sb_ctx* c, uint64_t* out1024) {  // debugging aid: per-block progress (host-mapped trace)
-  if (!c || !out1024 || !c->icp_trace_host) return SB_ERR_STATE;
-  memcpy(out1024, c->icp_trace_host + 1024, 2048 * 8);
-  return SB_OK;
-}
-
-// debugging aid: %globaltimer stamps of the last sb_icp_minimize (16 iterations x 16 slots), see sb_icp.cu SB_TR
-int sb_debug_icp_trace(sb_ctx* c, uint64_t* out256) {
-  if (!c || !out256 || !c->icp_trace) return SB_ERR_STATE;
-  if (c->icp_trace_host) {
-    memcpy(out256, c->icp_trace_host, 16 * 16 * 8);
-    return SB_OK;
-  }
-  SB_CUDA(c, cudaStreamSynchronize(c->stream));
-  SB_CUDA(c, cudaMemcpy(out256, c->icp_trace, 16 * 16 * 8, cudaMemcpyDeviceToHost));
-  return SB_OK;
-}
 
 // ---- profiling ------------------------------------------------------------------------------------------------
 int sb_profile_enable(sb_ctx* c, int on) {

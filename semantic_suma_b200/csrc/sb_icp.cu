@@ -295,8 +295,66 @@ void launch_icp_jacobian(const Launch& L, const KParams& kp, const IcpArgs& a, c
   }
 }
 
-// ---- fused Gauss-Newton iteration ----
-__global__ void k_gn_init(GnState* st, Mat4d T0, long long* acc32, unsigned int* ticket, unsigned int* epoch_flag) {
+// ------------------------------------------------------------------------------------------------------------
+// Device-side pose bookkeeping of SurfelMapping::updatePose (SurfelMapping.cpp:389-473): fp64, one thread, the same
+// functions (sbg::*) the host-side API uses, so host and device agree bit for bit. Used by the last block of the
+// persistent kernel (pipeline) and by the one-thread kernels below (first scan, host-callback exchange).
+// ------------------------------------------------------------------------------------------------------------
+__device__ void pose_after_icp_body(const double* gn_pose, int gn_k, PoseDev* pd, const double* T0, uint32_t timestamp,
+                                    int fallback_mode) {
+  double inc[16], inv_last[16], delta[16], Pn[16];
+  for (int i = 0; i < 16; ++i) pd->T0[i] = T0[i];
+  for (int i = 0; i < 16; ++i) inc[i] = gn_pose[i];  // increment = gn_->pose()   :395
+  for (int i = 0; i < 16; ++i) pd->increment[i] = inc[i];
+  pd->icp_iterations = gn_k;
+  sbg::rigid_inverse_d(pd->lastIncrement, inv_last);
+  mat4_mul<double>(inv_last, inc, delta);           // delta = lastIncrement_.inverse() * increment   :397
+  mat4_mul<double>(pd->currentPose, inc, Pn);       // currentPose_new_ * increment   :406
+  for (int i = 0; i < 16; ++i) pd->P_active.m[i] = (float)Pn[i];
+  sbg::rigid_inverse_f(pd->P_active.m, pd->invP_active.m);
+  float t_err = (float)sqrt((delta[12] * delta[12] + delta[13] * delta[13]) + delta[14] * delta[14]);  // :433
+  float angle = (float)(0.5 * (((delta[0] + delta[5]) + delta[10]) - 1.0));
+  float ca = angle < 1.0f ? angle : 1.0f;
+  ca = ca > -1.0f ? ca : -1.0f;
+  float r_err = acosf_(ca);
+  pd->t_err = t_err;
+  pd->r_err = r_err;
+  int fb = (timestamp > 1 && ((double)t_err > 0.4 || (double)r_err > 0.1) && fallback_mode) ? 1 : 0;  // :437
+  pd->fallback = fb;
+  if (fb) pd->trackLoss += 1;
+}
+
+// lastPose_ = currentPose_; currentPose_ = currentPose_ * increment; ... (SurfelMapping.cpp:451-473) and the pose-table
+// entry of this scan (SurfelMap.cpp:494-495)
+__device__ void pose_finalize_body(const double* recovery_pose, PoseDev* pd, int had_icp, float* poses, float* poses_inv,
+                                   uint32_t t) {
+  if (had_icp) {
+    double inc[16], np[16];
+    if (pd->fallback)
+      for (int i = 0; i < 16; ++i) inc[i] = recovery_pose[i];  // increment = gn_->pose() of the recovery run   :446
+    else
+      for (int i = 0; i < 16; ++i) inc[i] = pd->increment[i];
+    for (int i = 0; i < 16; ++i) pd->lastPose[i] = pd->currentPose[i];
+    mat4_mul<double>(pd->currentPose, inc, np);  // :452
+    for (int i = 0; i < 16; ++i) {
+      pd->currentPose[i] = np[i];
+      pd->lastIncrement[i] = inc[i];  // :473
+      pd->increment[i] = inc[i];
+    }
+  }
+  for (int i = 0; i < 16; ++i) pd->P_cur.m[i] = (float)pd->currentPose[i];
+  sbg::rigid_inverse_f(pd->P_cur.m, pd->invP_cur.m);
+  if (t < kMaxPoses) {
+    float inv[16];
+    sbg::rigid_inverse_f(pd->P_cur.m, inv);
+    for (int i = 0; i < 16; ++i) {
+      poses[16 * (size_t)t + i] = pd->P_cur.m[i];
+      poses_inv[16 * (size_t)t + i] = inv[i];
+    }
+  }
+}
+
+__global__ void k_gn_init(GnState* st, Mat4d T0, long long* acc32) {
   int i = threadIdx.x;
   if (i < 16) st->pose[i] = T0.m[i];
   if (i < 32) acc32[i] = 0;
@@ -306,108 +364,65 @@ __global__ void k_gn_init(GnState* st, Mat4d T0, long long* acc32, unsigned int*
     st->k = 0;
     st->done = 0;
     st->history_len = 0;
-    *ticket = 0;
-    *epoch_flag = 0;
+    st->error = 0;
   }
 }
 
-void launch_gn_init(const Launch& L, GnState* st, const Mat4d& T0, long long* acc32, unsigned int* ticket,
-                    unsigned int* epoch_flag) {
+void launch_gn_init(const Launch& L, GnState* st, const Mat4d& T0, long long* acc32) {
   {
     ScopedKernel sk(L, K_GN_INIT);
-    k_gn_init<<<1, 64, 0, L.stream>>>(st, T0, acc32, ticket, epoch_flag);
+    k_gn_init<<<1, 64, 0, L.stream>>>(st, T0, acc32);
   }
 }
 
-// one-shot all-reduce of the 32 sums over the ranks' peer-mapped mailboxes (only thread 0 of the last block runs it):
-// every rank stores its sums + an epoch stamp into slot [epoch&1][rank] of every peer, then waits for the stamps.
-__device__ void comm_allreduce32(const CommDev& cd, long long* raw) {
-  const int epoch = (int)(*cd.epoch) + 1;  // stamps start at 1: a zeroed mailbox never matches
-  *cd.epoch = (unsigned int)epoch;
-  const int slot = epoch & 1;
-  for (int r = 0; r < cd.nranks; ++r) {
-    volatile long long* dst = cd.mailbox[r] + ((size_t)(slot * 8 + cd.rank)) * 40;
-    for (int i = 0; i < 32; ++i) dst[i] = raw[i];
-  }
-  __threadfence_system();
-  for (int r = 0; r < cd.nranks; ++r) {
-    volatile long long* dst = cd.mailbox[r] + ((size_t)(slot * 8 + cd.rank)) * 40;
-    dst[32] = (long long)epoch;
-  }
-  __threadfence_system();
-  volatile long long* mine = cd.mailbox[cd.rank];
-  for (int i = 0; i < 32; ++i) raw[i] = 0;
-  for (int r = 0; r < cd.nranks; ++r) {
-    volatile long long* src = mine + ((size_t)(slot * 8 + r)) * 40;
-    while (src[32] != (long long)epoch) {
-    }
-    __threadfence_system();
-    for (int i = 0; i < 32; ++i) raw[i] += src[i];
+__global__ void k_pose_after_icp(const GnState* __restrict__ gn, PoseDev* __restrict__ pd, Mat4d T0, uint32_t timestamp,
+                                 int fallback_mode) {
+  if (threadIdx.x != 0) return;
+  pose_after_icp_body(gn->pose, gn->k, pd, T0.m, timestamp, fallback_mode);
+}
+void launch_pose_after_icp(const Launch& L, const GnState* gn, PoseDev* pd, const Mat4d& T0, uint32_t timestamp,
+                           int fallback_mode) {
+  {
+    ScopedKernel sk(L, K_GN_INIT);
+    k_pose_after_icp<<<1, 32, 0, L.stream>>>(gn, pd, T0, timestamp, fallback_mode);
   }
 }
 
-__global__ void __launch_bounds__(kIcpThreads, 2) k_icp_fused(KParams kp, IcpArgs a, GnState* __restrict__ st,
-                                                           long long* __restrict__ g_acc, unsigned int* ticket,
-                                                           int max_iter, double eps, double delta, CommDev cd) {
-  // all blocks read the state written by the previous launch
-  if (*(volatile int*)&st->done) return;
-  float M[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) M[i] = (float)st->pose[i];  // pose_.cast<float>(), Frame2Model.cpp:194
-  const int k = st->k;
-  Acc acc;
-  icp_accumulate(kp, a, M, k, acc);
-  block_reduce_to_global<true>(acc, g_acc);
-  __shared__ bool is_last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    unsigned int t = atomicAdd(ticket, 1u);
-    is_last = (t == gridDim.x - 1);
+__global__ void k_pose_finalize(const GnState* __restrict__ gn, PoseDev* __restrict__ pd, int had_icp,
+                                float* __restrict__ poses, float* __restrict__ poses_inv, uint32_t t) {
+  if (threadIdx.x != 0) return;
+  pose_finalize_body(gn->pose, pd, had_icp, poses, poses_inv, t);
+}
+void launch_pose_finalize(const Launch& L, const GnState* gn, PoseDev* pd, int had_icp, float* poses, float* poses_inv,
+                          uint32_t t) {
+  {
+    ScopedKernel sk(L, K_GN_INIT);
+    k_pose_finalize<<<1, 32, 0, L.stream>>>(gn, pd, had_icp, poses, poses_inv, t);
   }
-  __syncthreads();
-  if (!is_last || threadIdx.x != 0) return;
-  __threadfence();
-  long long raw[32];
-  for (int i = 0; i < 32; ++i) {
-    raw[i] = *(volatile long long*)(g_acc + i);
-    g_acc[i] = 0;
-  }
-  *ticket = 0;
-  if (cd.nranks > 1) comm_allreduce32(cd, raw);
-  double out48[48], pose[16], dx[6];
-  sbg::unpack48(raw, out48);
-  for (int i = 0; i < 16; ++i) pose[i] = st->pose[i];
-  int hl = st->history_len;
-  for (int i = 0; i < 16; ++i) st->history[hl * 16 + i] = pose[i];  // history_.push_back(Tk_)
-  ++hl;
-  int result = sbg::gn_step(out48, st->last_error, eps, delta, pose, dx);
-  for (int i = 0; i < 16; ++i) st->pose[i] = pose[i];
-  for (int i = 0; i < 48; ++i) st->out48[i] = out48[i];
-  st->last_error = out48[43];
-  int kk = k;
-  int done = 0;
-  if (result == 0) {
-    done = 1;
-  } else {
-    ++kk;
-    if (kk >= max_iter) {  // the loop pushes the pose once more and leaves (LieGaussNewton.cpp:24-27)
-      for (int i = 0; i < 16; ++i) st->history[hl * 16 + i] = pose[i];
-      ++hl;
-      done = 1;
-    }
-  }
-  st->k = kk;
-  st->history_len = hl;
-  __threadfence();
-  st->done = done;
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Persistent Gauss-Newton kernel: ONE cooperative launch runs every iteration. All blocks are co-resident; after the
-// reduction the last block to arrive performs the GN step (warp-parallel 6x6 LDL^T, SE3 exp, pose update), then
-// releases the other blocks through an epoch flag in HBM. No kernel boundary and no host round trip per iteration
-// (the reference does a 48-float read-back and two glFinish per iteration, Frame2Model.cpp:205-258).
+// Persistent Gauss-Newton kernel: ONE cooperative launch runs every iteration of a minimisation AND the bookkeeping
+// around it. All blocks are co-resident; after the reduction the last block to arrive performs the GN step
+// (warp-parallel 6x6 LDL^T, SE3 exp, pose update) and releases the other blocks through an epoch word in HBM. No kernel
+// boundary and no host round trip per iteration (the reference does a 48-float read-back and two glFinish per
+// iteration, Frame2Model.cpp:205-258).
+//
+// Three jobs (GnJob::mode):
+//  GN_PLAIN  LieGaussNewton::minimize on a pre-initialised state (sb_icp_minimize).
+//  GN_MAIN   updatePose, first half (SurfelMapping.cpp:372-406): T0 from the device-resident pose block, the
+//            frame-to-model minimisation, then -- by the block that did the last step -- the increment, the pose of the
+//            post-ICP rendering and the track-loss test; finally ALL blocks fill the table inv(P_active) * poses[t] that
+//            render_active needs. (Round 1: four launches.)
+//  GN_POST   updatePose, second half (:415-473): pass 0 is the statistics evaluation at identity against the freshly
+//            rendered active model (result_new_); if the track was lost the same loop then runs the frame-to-frame
+//            recovery minimisation; the finishing block chains the poses and writes the pose-table entry; finally all
+//            blocks fill inv(P_cur) * poses[t] for the map update and the model rendering. (Round 1: five launches.)
+//
+// Epoch words never need a reset: launch j waits for base_j + iteration + 1 with base_{j+1} > every value launch j can
+// publish (the host advances the base by max_iter + 8 per launch). The arrival ticket is returned to 0 by each step.
+// Every spin is bounded (%globaltimer): a peer or a block that never shows up ends the launch with GnState::error set
+// instead of hanging the stream.
 // ------------------------------------------------------------------------------------------------------------
 struct GnShared {
   double A[36];
@@ -428,16 +443,16 @@ __device__ __forceinline__ void tri_cr(int k, int& c, int& r) {  // k-th entry o
   r = c + (k - start[c]);
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long kSpinTimeoutNs = 10ull * 1000ull * 1000ull * 1000ull;  // 10 s
+
 // same arithmetic as sbg::ldlt_solve6 / sbg::gn_step, spread over the 32 lanes of one warp (per-element operation
 // order unchanged, so the result is bit-identical to the sequential code)
-__device__ void gn_step_warp(GnShared& sh, long long raw, int lane, double last_error, double eps, double delta_thr,
-                             unsigned long long* tr) {
-#define SB_TG(slot)                                              \
-  if (tr && lane == 0) {                                         \
-    unsigned long long t__;                                      \
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));      \
-    tr[slot] = t__;                                              \
-  }
+__device__ void gn_step_warp(GnShared& sh, long long raw, int lane, double last_error, double eps, double delta_thr) {
   const double s = 1.0 / 1073741824.0;
   // unpack (Frame2Model.cpp:214-227)
   if (lane < 21) {
@@ -510,7 +525,6 @@ __device__ void gn_step_warp(GnShared& sh, long long raw, int lane, double last_
     }
     __syncwarp();
   }
-  SB_TG(12)
   if (lane == 0) {
     double y[6], dx[6];
 #pragma unroll
@@ -541,7 +555,6 @@ __device__ void gn_step_warp(GnShared& sh, long long raw, int lane, double last_
     if (fabs(maxc) < eps) result = 0;
     if (current_error < last_error && fabs(current_error - last_error) < eps) result = 0;
     sh.result = result;
-    SB_TG(13)
     double E[16];
     sbg::se3_exp(dx, E);
 #pragma unroll
@@ -559,13 +572,13 @@ __device__ void gn_step_warp(GnShared& sh, long long raw, int lane, double last_
   __syncwarp();
   if (lane < 16) sh.P[lane] = pn;
   __syncwarp();
-#undef SB_TG
 }
 
-// lane-parallel one-shot all-reduce of the 32 sums over the ranks' peer-mapped mailboxes (warp 0 of the last block)
-__device__ long long comm_allreduce32_warp(const CommDev& cd, long long raw, int lane, volatile unsigned long long* dbg) {
+// lane-parallel one-shot all-reduce of the 32 sums over the ranks' peer-mapped mailboxes (warp 0 of the last block):
+// every rank stores its sums + an epoch stamp into slot [epoch&1][rank] of EVERY rank's mailbox (plain stores over
+// NVLink), then waits for the stamps of all ranks in its own mailbox. Returns false on timeout.
+__device__ bool comm_allreduce32_warp(const CommDev& cd, long long& raw, int lane) {
   int epoch = 0;
-  if (dbg && lane == 0) dbg[240] = 1 + dbg[240];
   if (lane == 0) {
     epoch = (int)(*cd.epoch) + 1;  // stamps start at 1: a zeroed mailbox never matches
     *cd.epoch = (unsigned int)epoch;
@@ -578,269 +591,219 @@ __device__ long long comm_allreduce32_warp(const CommDev& cd, long long raw, int
   }
   __threadfence_system();
   __syncwarp();
+  int ok = 1;
   if (lane == 0) {
-    if (dbg) { dbg[241] = (unsigned long long)epoch; dbg[242] = (unsigned long long)cd.nranks; dbg[243] = (unsigned long long)cd.rank; }
     for (int r = 0; r < cd.nranks; ++r) {
       volatile long long* dst = cd.mailbox[r] + ((size_t)(slot * 8 + cd.rank)) * 40;
       dst[32] = (long long)epoch;
     }
     __threadfence_system();
     volatile long long* mine = cd.mailbox[cd.rank];
-    if (dbg) dbg[244] = 1 + dbg[244];
-    for (int r = 0; r < cd.nranks; ++r) {
+    const unsigned long long t0 = globaltimer_ns();
+    for (int r = 0; r < cd.nranks && ok; ++r) {
       volatile long long* src = mine + ((size_t)(slot * 8 + r)) * 40;
-      if (dbg) { dbg[245] = (unsigned long long)r; dbg[246] = (unsigned long long)src[32]; dbg[248 + r] = (unsigned long long)(size_t)cd.mailbox[r]; }
+      unsigned int spins = 0;
       while (src[32] != (long long)epoch) {
-        if (dbg) dbg[247] = (unsigned long long)src[32];
+        if ((++spins & 1023u) == 0u && globaltimer_ns() - t0 > kSpinTimeoutNs) {
+          ok = 0;
+          break;
+        }
       }
     }
-    if (dbg) dbg[244] = 100 + dbg[244];
     __threadfence_system();
   }
-  __syncwarp();
+  ok = __shfl_sync(0xffffffffu, ok, 0);
   long long tot = 0;
   volatile long long* mine = cd.mailbox[cd.rank];
   for (int r = 0; r < cd.nranks; ++r) tot += mine[((size_t)(slot * 8 + r)) * 40 + lane];
-  return tot;
+  raw = tot;
+  return ok != 0;
 }
 
-__global__ void __launch_bounds__(kIcpThreads, 2) k_icp_persistent(KParams kp, IcpArgs a, GnState* __restrict__ st,
-                                                                long long* __restrict__ slots, unsigned int* ticket,
-                                                                unsigned int* epoch_flag, int max_iter, double eps,
-                                                                double delta, CommDev cd, unsigned long long* trace) {
-#define SB_TR(slot)                                                                     \
-  if (trace && threadIdx.x == 0 && it < 16 && (blockIdx.x == 0 || (slot) >= 8)) {       \
-    unsigned long long t__;                                                             \
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                             \
-    trace[it * 16 + (slot)] = t__;                                                      \
-  }
-#define SB_BS(phase)                                                              \
-  if (trace && threadIdx.x == 0) ((volatile unsigned long long*)trace)[1024 + blockIdx.x] = (unsigned long long)(it * 16u + (phase));
+__device__ __forceinline__ void load_mat_cg(const float* table, int idx, float* M) {  // coherent (L2) read of a pose
+  const float4* t = reinterpret_cast<const float4*>(table + 16 * (size_t)idx);
+  float4 a = __ldcg(t), b = __ldcg(t + 1), c = __ldcg(t + 2), d = __ldcg(t + 3);
+  M[0] = a.x; M[1] = a.y; M[2] = a.z; M[3] = a.w;
+  M[4] = b.x; M[5] = b.y; M[6] = b.z; M[7] = b.w;
+  M[8] = c.x; M[9] = c.y; M[10] = c.z; M[11] = c.w;
+  M[12] = d.x; M[13] = d.y; M[14] = d.z; M[15] = d.w;
+}
+
+__global__ void __launch_bounds__(kIcpThreads, 2) k_gn_persistent(KParams kp, GnJob job, long long* __restrict__ slots,
+                                                               unsigned int* ticket, unsigned int* epoch_flag, CommDev cd) {
   __shared__ GnShared sh;
   __shared__ bool is_last;
   __shared__ double s_pose[16];
-  __shared__ int s_k, s_done;
+  __shared__ int s_done, s_error;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  GnState* st = job.st;
+  PoseDev* pd = job.pd;
+  if (threadIdx.x == 0) s_error = 0;
   for (unsigned int it = 0;; ++it) {
-    // Warp 0 waits for the previous iteration's step (epoch flag), then fetches the state written by that step with
-    // ONE round of coherent loads spread over its lanes and broadcasts it through shared memory (every thread reading
-    // the pose from L2 would hammer a single L2 sector with ~40k requests per iteration).
+    // Warp 0 waits for the previous iteration's step (epoch word), then fetches the state written by that step with ONE
+    // round of coherent loads spread over its lanes and broadcasts it through shared memory (every thread reading the
+    // pose from L2 would hammer a single L2 sector with ~40k requests per iteration).
     if (warp == 0) {
-      if (it > 0) {
-        if (lane == 0) {
-          if (trace) ((volatile unsigned long long*)trace)[2048 + blockIdx.x] = (unsigned long long)(it * 16u + 9u);
-          while (*(volatile unsigned int*)epoch_flag != it) {
+      if (it == 0) {
+        if (job.mode == GN_PLAIN) {  // state prepared by k_gn_init earlier on the stream
+          if (lane < 16) s_pose[lane] = st->pose[lane];
+          if (lane == 17) s_done = st->done;
+        } else {
+          // GN_MAIN: T0 = lastIncrement_ or identity (SurfelMapping.cpp:373-376); GN_POST: the statistics pass runs at
+          // identity (objective_->initialize(Identity), :414)
+          if (lane < 16) {
+            double v = (lane % 5 == 0) ? 1.0 : 0.0;
+            if (job.mode == GN_MAIN && !job.initialize_identity) v = pd->lastIncrement[lane];
+            s_pose[lane] = v;
           }
-          if (trace) ((volatile unsigned long long*)trace)[2048 + blockIdx.x] = (unsigned long long)(it * 16u + 10u);
+          if (lane == 17) s_done = 0;
+        }
+      } else {
+        if (lane == 0) {
+          const unsigned int want = job.epoch_base + it;
+          const unsigned long long t0 = globaltimer_ns();
+          unsigned int spins = 0;
+          while (*(volatile unsigned int*)epoch_flag != want) {
+            if ((++spins & 4095u) == 0u && globaltimer_ns() - t0 > kSpinTimeoutNs) {
+              s_error = 1;
+              break;
+            }
+          }
           __threadfence();
-          if (trace) ((volatile unsigned long long*)trace)[2048 + blockIdx.x] = (unsigned long long)(it * 16u + 11u);
         }
         __syncwarp();
+        if (lane < 16) s_pose[lane] = *(volatile double*)&st->pose[lane];
+        if (lane == 17) s_done = *(volatile int*)&st->done;
       }
-      if (lane < 16) s_pose[lane] = *(volatile double*)&st->pose[lane];
-      if (lane == 16) s_k = *(volatile int*)&st->k;
-      if (lane == 17) s_done = *(volatile int*)&st->done;
-      if (trace && lane == 0) ((volatile unsigned long long*)trace)[2048 + blockIdx.x] = (unsigned long long)(it * 16u + 12u);
     }
     __syncthreads();
-    if (s_done) {
-      SB_BS(15)
-      break;
+    if (s_error) {  // a block (or a peer GPU) never arrived: give up instead of hanging the stream
+      if (threadIdx.x == 0) {
+        *(volatile int*)&st->error = 1;
+        if (pd) *(volatile int*)&pd->gn_error = 1;
+      }
+      return;
     }
-    SB_BS(1)
-    SB_TR(0)
+    if (s_done) break;
+    const bool stats_pass = job.mode == GN_POST && it == 0;
+    const bool recovery = job.mode == GN_POST && it > 0;
+    const int k = job.mode == GN_POST ? (int)it - 1 : (int)it;  // k_ of LieGaussNewton: one increment per completed step
     float M[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) M[i] = (float)s_pose[i];  // pose_.cast<float>(), Frame2Model.cpp:194
-    const int k = s_k;
     Acc acc;
-    icp_accumulate(kp, a, M, k, acc);
+    icp_accumulate(kp, recovery ? job.fb : job.a, M, stats_pass ? 0 : k, acc);
     __syncthreads();
-    SB_BS(2)
-    SB_TR(1)
     block_reduce_to_replica(acc, slots);
     __syncthreads();
-    SB_BS(3)
-    SB_TR(2)
     if (threadIdx.x == 0) {
-      __threadfence();  // cumulative: orders this block's slot stores (observed through the barrier) before the ticket
+      __threadfence();  // cumulative: orders this block's slot adds (observed through the barrier) before the ticket
       unsigned int t = atomicAdd(ticket, 1u);
       is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
-    SB_BS(4)
-    SB_TR(3)
     if (is_last && warp == 0) {
-      SB_TR(8)
       __threadfence();
       long long raw = sum_replicas(slots, lane);
-      SB_TR(9)
-      double last_error = 0.0;
-      if (lane == 16) last_error = *(volatile double*)&st->last_error;
-      last_error = __shfl_sync(0xffffffffu, last_error, 16);
-      SB_BS(5)
-      if (cd.epoch) raw = comm_allreduce32_warp(cd, raw, lane, trace);
-      SB_BS(6)
-      if (lane < 16) sh.P[lane] = s_pose[lane];
-      int hl = (int)it;  // one pose has been pushed per completed iteration
-      if (lane < 16) st->history[hl * 16 + lane] = s_pose[lane];  // history_.push_back(Tk_)
-      ++hl;
-      __syncwarp();
-      gn_step_warp(sh, raw, lane, last_error, eps, delta, (trace && it < 16) ? trace + it * 16 : nullptr);
-      SB_TR(10)
-      if (lane < 16) st->pose[lane] = sh.P[lane];
-      for (int i = lane; i < 48; i += 32) st->out48[i] = sh.O[i];
-      int kk = k, done = 0;
-      if (sh.result == 0) {
-        done = 1;
-      } else {
-        ++kk;
-        if (kk >= max_iter) {  // the loop pushes the pose once more and leaves (LieGaussNewton.cpp:24-27)
-          if (lane < 16) st->history[hl * 16 + lane] = sh.P[lane];
-          ++hl;
+      int done = 0, error = 0;
+      if (stats_pass) {
+        // result_new_ (SurfelMapping.cpp:415-423): the host unpacks these 32 sums after the scan
+        job.stats32[lane] = raw;
+        const int fb = job.fallback_mode ? *(volatile int*)&pd->fallback : 0;
+        if (fb) {  // recovery_->setData(currentFrame_, lastFrame_); gn_->minimize(*recovery_, T0)   :442-444
+          if (lane < 16) st->pose[lane] = pd->T0[lane];
+          if (lane == 0) {
+            st->last_error = (double)3.402823466e+38f;
+            st->k = 0;
+            st->history_len = 0;
+          }
+        } else {
           done = 1;
+        }
+      } else {
+        double last_error = (double)3.402823466e+38f;  // LieGaussNewton.cpp:48
+        if (k > 0 && lane == 16) last_error = *(volatile double*)&st->last_error;
+        last_error = __shfl_sync(0xffffffffu, last_error, 16);
+        if (cd.epoch) error = comm_allreduce32_warp(cd, raw, lane) ? 0 : 1;
+        if (lane < 16) sh.P[lane] = s_pose[lane];
+        int hl = k;  // one pose has been pushed per completed iteration
+        if (lane < 16) st->history[hl * 16 + lane] = s_pose[lane];  // history_.push_back(Tk_)
+        ++hl;
+        __syncwarp();
+        gn_step_warp(sh, raw, lane, last_error, job.eps, job.delta);
+        if (lane < 16) st->pose[lane] = sh.P[lane];
+        for (int i = lane; i < 48; i += 32) st->out48[i] = sh.O[i];
+        int kk = k;
+        if (sh.result == 0) {
+          done = 1;
+        } else {
+          ++kk;
+          if (kk >= job.max_iter) {  // the loop pushes the pose once more and leaves (LieGaussNewton.cpp:24-27)
+            if (lane < 16) st->history[hl * 16 + lane] = sh.P[lane];
+            ++hl;
+            done = 1;
+          }
+        }
+        if (error) done = 1;
+        if (lane == 0) {
+          st->last_error = sh.O[43];
+          st->k = kk;
+          st->history_len = hl;
+        }
+        __syncwarp();
+      }
+      if (done && lane == 0 && !error) {
+        if (job.mode == GN_MAIN) {
+          double T0[16];
+          for (int i = 0; i < 16; ++i) T0[i] = job.initialize_identity ? ((i % 5 == 0) ? 1.0 : 0.0) : pd->lastIncrement[i];
+          pose_after_icp_body(sh.P, st->k, pd, T0, job.timestamp, job.fallback_mode);
+        } else if (job.mode == GN_POST) {
+          pose_finalize_body(st->pose, pd, 1, job.poses, job.poses_inv, job.t_map);
         }
       }
       if (lane == 0) {
-        st->last_error = sh.O[43];
-        st->k = kk;
-        st->history_len = hl;
+        if (error) {
+          st->error = 1;
+          if (pd) pd->gn_error = 1;
+        }
         st->done = done;
         *ticket = 0;
       }
       __threadfence();
       __syncwarp();
-      if (lane == 0) atomicExch(epoch_flag, it + 1u);
-      SB_BS(8)
-      SB_TR(11)
+      if (lane == 0) atomicExch(epoch_flag, job.epoch_base + it + 1u);
     }
-    // The last block's other warps wait for the step HERE, not at the loop-top barrier: with a peer exchange in the step
-    // (tens of microseconds) the version that let them run ahead to the next iteration's barrier deadlocked on a
-    // 2-GPU box; is_last is block-uniform, so this barrier is too.
+    // The last block's other warps wait for the step HERE, not at the loop-top barrier (is_last is block-uniform).
     if (is_last) __syncthreads();
   }
-#undef SB_TR
-#undef SB_BS
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (opt-in: SUMA_B200_ICP_VARIANT=1, single GPU only, not measured yet -- DESIGN.md section 8).
-// Same iteration, no "last block": the ticket is a grid barrier, after which EVERY block's warp 0 sums the replicas and
-// performs the identical 6x6 step redundantly (deterministic code on identical integers => identical poses), so the
-// publish-through-an-epoch-flag hop and the re-load of the pose from L2 disappear from the critical path of each
-// iteration. The replica accumulators are cumulative and double buffered by iteration parity (never cleared inside the
-// kernel): iteration i adds into buffer i&1 and reads it after barrier i; the buffer is next written in iteration i+2,
-// which no block enters before every block has arrived at barrier i+1, i.e. after every block finished reading it.
-// Block 0 alone mirrors the state into GnState for the host and the kernels that follow.
-// ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kIcpThreads, 2) k_icp_persistent_all(KParams kp, IcpArgs a, GnState* __restrict__ st,
-                                                                    long long* __restrict__ cum, unsigned int* ticket,
-                                                                    int max_iter, double eps, double delta) {
-  __shared__ GnShared sh;
-  __shared__ double s_pose[16];
-  __shared__ double s_last_error;
-  __shared__ int s_k, s_done;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int hl = 0;
-  if (warp == 0) {
-    if (lane < 16) s_pose[lane] = st->pose[lane];
-    if (lane == 16) s_k = st->k;
-    if (lane == 17) s_done = st->done;
-    if (lane == 18) s_last_error = st->last_error;
-    hl = st->history_len;
-  }
-  long long prev0 = 0, prev1 = 0;  // lanes of warp 0: the cumulative totals already consumed, per buffer
-  __syncthreads();
-  for (unsigned int it = 0;; ++it) {
-    if (s_done) break;
-    float M[16];
+  // ---- all blocks: the table inv(P) * poses[t] of the rendering / map update that follows (render_surfels.vert:46) ----
+  if (job.Mtab) {
+    if (*(volatile int*)&pd->gn_error) return;
+    const float* A = job.mode == GN_MAIN ? pd->invP_active.m : pd->invP_cur.m;
+    float a[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) M[i] = (float)s_pose[i];  // pose_.cast<float>(), Frame2Model.cpp:194
-    const int k = s_k;
-    Acc acc;
-    icp_accumulate(kp, a, M, k, acc);
-    __syncthreads();
-    long long* buf = cum + (size_t)(it & 1u) * kAccReplicas * 32;
-    block_reduce_to_replica(acc, buf);
-    __syncthreads();
-    if (warp == 0) {
-      if (lane == 0) {
-        __threadfence();  // cumulative: orders this block's REDs (observed through the barrier) before the ticket
-        atomicAdd(ticket, 1u);
-        const unsigned int target = gridDim.x * (it + 1u);
-        while (*(volatile unsigned int*)ticket < target) {
-        }
-        __threadfence();
-      }
-      __syncwarp();
-      long long tot = 0;
-#pragma unroll
-      for (int r = 0; r < kAccReplicas; ++r) tot += *(volatile long long*)(buf + (size_t)r * 32 + lane);
-      long long raw;
-      if (it & 1u) {
-        raw = tot - prev1;
-        prev1 = tot;
-      } else {
-        raw = tot - prev0;
-        prev0 = tot;
-      }
-      const double last_error = s_last_error;
-      const bool writer = blockIdx.x == 0;
-      if (lane < 16) sh.P[lane] = s_pose[lane];
-      if (writer && lane < 16) st->history[hl * 16 + lane] = s_pose[lane];  // history_.push_back(Tk_)
-      ++hl;
-      __syncwarp();
-      gn_step_warp(sh, raw, lane, last_error, eps, delta, nullptr);
-      int kk = k, done = 0;
-      if (sh.result == 0) {
-        done = 1;
-      } else {
-        ++kk;
-        if (kk >= max_iter) {  // the loop pushes the pose once more and leaves (LieGaussNewton.cpp:24-27)
-          if (writer && lane < 16) st->history[hl * 16 + lane] = sh.P[lane];
-          ++hl;
-          done = 1;
-        }
-      }
-      if (lane < 16) s_pose[lane] = sh.P[lane];
-      if (lane == 0) {
-        s_k = kk;
-        s_done = done;
-        s_last_error = sh.O[43];
-      }
-      if (writer) {
-        if (lane < 16) st->pose[lane] = sh.P[lane];
-        for (int i = lane; i < 48; i += 32) st->out48[i] = sh.O[i];
-        if (lane == 0) {
-          st->last_error = sh.O[43];
-          st->k = kk;
-          st->history_len = hl;
-          st->done = done;
-        }
-      }
+    for (int i = 0; i < 16; ++i) a[i] = *(volatile const float*)&A[i];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < job.n_poses; t += gridDim.x * blockDim.x) {
+      float b[16], c[16];
+      load_mat_cg(job.poses, (int)t, b);
+      mat4_mul<float>(a, b, c);
+      float4* o = reinterpret_cast<float4*>(job.Mtab + 16 * (size_t)t);
+      o[0] = make_float4(c[0], c[1], c[2], c[3]);
+      o[1] = make_float4(c[4], c[5], c[6], c[7]);
+      o[2] = make_float4(c[8], c[9], c[10], c[11]);
+      o[3] = make_float4(c[12], c[13], c[14], c[15]);
     }
-    __syncthreads();
   }
 }
 
-static int icp_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SUMA_B200_ICP_VARIANT");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
-
-int icp_persistent_max_blocks(int sm_count) {
+int gn_persistent_max_blocks(int sm_count) {
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_persistent, kIcpThreads, 0) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gn_persistent, kIcpThreads, 0) != cudaSuccess) return 0;
   return per_sm * sm_count;
 }
 
-int launch_icp_persistent(const Launch& L, const KParams& kp, const IcpArgs& a, GnState* st, long long* slots,
-                          unsigned int* ticket, unsigned int* epoch_flag, int max_iter, double eps, double delta,
-                          const CommDev* comm, int blocks, unsigned long long* trace) {
+int launch_gn_persistent(const Launch& L, const KParams& kp, const GnJob& job, long long* slots, unsigned int* ticket,
+                         unsigned int* epoch_flag, const CommDev* comm, int blocks) {
   CommDev cd;
   if (comm) {
     cd = *comm;
@@ -849,148 +812,14 @@ int launch_icp_persistent(const Launch& L, const KParams& kp, const IcpArgs& a, 
     cd.nranks = 1;
   }
   KParams kpv = kp;
-  IcpArgs av = a;
-  if (icp_variant() == 1 && !comm) {  // experimental all-blocks-solve kernel; its accumulators live behind the others
-    long long* cum = slots + (size_t)512 * 32;
-    if (cudaMemsetAsync(cum, 0, sizeof(long long) * 2 * kAccReplicas * 32, L.stream) != cudaSuccess) return -1;
-    void* args2[] = {&kpv, &av, &st, &cum, &ticket, &max_iter, &eps, &delta};
-    cudaError_t e2;
-    {
-      ScopedKernel sk(L, K_ICP_FUSED);
-      e2 = cudaLaunchCooperativeKernel((void*)k_icp_persistent_all, dim3(blocks), dim3(kIcpThreads), args2, 0, L.stream);
-    }
-    return e2 == cudaSuccess ? 0 : -1;
-  }
-  void* args[] = {&kpv, &av, &st, &slots, &ticket, &epoch_flag, &max_iter, &eps, &delta, &cd, &trace};
+  GnJob jv = job;
+  void* args[] = {&kpv, &jv, &slots, &ticket, &epoch_flag, &cd};
   cudaError_t e;
   {
     ScopedKernel sk(L, K_ICP_FUSED);
-    e = cudaLaunchCooperativeKernel((void*)k_icp_persistent, dim3(blocks), dim3(kIcpThreads), args, 0, L.stream);
+    e = cudaLaunchCooperativeKernel((void*)k_gn_persistent, dim3(blocks), dim3(kIcpThreads), args, 0, L.stream);
   }
   return e == cudaSuccess ? 0 : -1;
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// Device-side pose bookkeeping of SurfelMapping::updatePose (SurfelMapping.cpp:389-473). One thread, fp64, the same
-// functions (sbg::*) the host-side API uses, so host and device agree bit for bit.
-// ------------------------------------------------------------------------------------------------------------
-__global__ void k_pose_after_icp(const GnState* __restrict__ gn, PoseDev* __restrict__ pd, Mat4d T0, uint32_t timestamp,
-                                 int fallback_mode) {
-  if (threadIdx.x != 0) return;
-  double inc[16], inv_last[16], delta[16], Pn[16];
-  for (int i = 0; i < 16; ++i) pd->T0[i] = T0.m[i];
-  for (int i = 0; i < 16; ++i) inc[i] = gn->pose[i];  // increment = gn_->pose()   :395
-  for (int i = 0; i < 16; ++i) pd->increment[i] = inc[i];
-  pd->icp_iterations = gn->k;
-  sbg::rigid_inverse_d(pd->lastIncrement, inv_last);
-  mat4_mul<double>(inv_last, inc, delta);           // delta = lastIncrement_.inverse() * increment   :397
-  mat4_mul<double>(pd->currentPose, inc, Pn);       // currentPose_new_ * increment   :406
-  for (int i = 0; i < 16; ++i) pd->P_active.m[i] = (float)Pn[i];
-  sbg::rigid_inverse_f(pd->P_active.m, pd->invP_active.m);
-  float t_err = (float)sqrt((delta[12] * delta[12] + delta[13] * delta[13]) + delta[14] * delta[14]);  // :433
-  float angle = (float)(0.5 * (((delta[0] + delta[5]) + delta[10]) - 1.0));
-  float ca = angle < 1.0f ? angle : 1.0f;
-  ca = ca > -1.0f ? ca : -1.0f;
-  float r_err = acosf_(ca);
-  pd->t_err = t_err;
-  pd->r_err = r_err;
-  int fb = (timestamp > 1 && ((double)t_err > 0.4 || (double)r_err > 0.1) && fallback_mode) ? 1 : 0;  // :437
-  pd->fallback = fb;
-  if (fb) pd->trackLoss += 1;
-}
-
-void launch_pose_after_icp(const Launch& L, const GnState* gn, PoseDev* pd, const Mat4d& T0, uint32_t timestamp,
-                           int fallback_mode) {
-  {
-    ScopedKernel sk(L, K_GN_INIT);
-    k_pose_after_icp<<<1, 32, 0, L.stream>>>(gn, pd, T0, timestamp, fallback_mode);
-  }
-}
-
-// prepares the GN state for the frame-to-frame fallback run; when no track loss was detected the state is marked done
-// and the minimisation kernel that follows returns at once
-__global__ void k_gn_init_fallback(GnState* st, const PoseDev* __restrict__ pd, long long* acc32, unsigned int* ticket,
-                                   unsigned int* epoch_flag) {
-  int i = threadIdx.x;
-  const int fb = pd->fallback;
-  if (fb) {
-    if (i < 16) st->pose[i] = pd->T0[i];
-    if (i < 48) st->out48[i] = 0.0;
-  }
-  if (i < 32) acc32[i] = 0;
-  if (i == 0) {
-    if (fb) {
-      st->last_error = (double)3.402823466e+38f;
-      st->k = 0;
-      st->history_len = 0;
-    }
-    st->done = fb ? 0 : 1;
-    *ticket = 0;
-    *epoch_flag = 0;
-  }
-}
-
-void launch_gn_init_fallback(const Launch& L, GnState* st, const PoseDev* pd, long long* acc32, unsigned int* ticket,
-                             unsigned int* epoch_flag) {
-  {
-    ScopedKernel sk(L, K_GN_INIT);
-    k_gn_init_fallback<<<1, 64, 0, L.stream>>>(st, pd, acc32, ticket, epoch_flag);
-  }
-}
-
-// lastPose_ = currentPose_; currentPose_ = currentPose_ * increment; ... (SurfelMapping.cpp:451-473) and the pose-table
-// entry of this scan (SurfelMap.cpp:494-495)
-__global__ void k_pose_finalize(const GnState* __restrict__ gn, PoseDev* __restrict__ pd, int had_icp,
-                                float* __restrict__ poses, float* __restrict__ poses_inv, uint32_t t) {
-  if (threadIdx.x != 0) return;
-  if (had_icp) {
-    double inc[16], np[16];
-    if (pd->fallback)
-      for (int i = 0; i < 16; ++i) inc[i] = gn->pose[i];  // increment = gn_->pose() of the recovery run   :446
-    else
-      for (int i = 0; i < 16; ++i) inc[i] = pd->increment[i];
-    for (int i = 0; i < 16; ++i) pd->lastPose[i] = pd->currentPose[i];
-    mat4_mul<double>(pd->currentPose, inc, np);  // :452
-    for (int i = 0; i < 16; ++i) {
-      pd->currentPose[i] = np[i];
-      pd->lastIncrement[i] = inc[i];  // :473
-      pd->increment[i] = inc[i];
-    }
-  }
-  for (int i = 0; i < 16; ++i) pd->P_cur.m[i] = (float)pd->currentPose[i];
-  sbg::rigid_inverse_f(pd->P_cur.m, pd->invP_cur.m);
-  if (t < kMaxPoses) {
-    float inv[16];
-    sbg::rigid_inverse_f(pd->P_cur.m, inv);
-    for (int i = 0; i < 16; ++i) {
-      poses[16 * (size_t)t + i] = pd->P_cur.m[i];
-      poses_inv[16 * (size_t)t + i] = inv[i];
-    }
-  }
-}
-
-void launch_pose_finalize(const Launch& L, const GnState* gn, PoseDev* pd, int had_icp, float* poses, float* poses_inv,
-                          uint32_t t) {
-  {
-    ScopedKernel sk(L, K_GN_INIT);
-    k_pose_finalize<<<1, 32, 0, L.stream>>>(gn, pd, had_icp, poses, poses_inv, t);
-  }
-}
-
-void launch_icp_fused_iteration(const Launch& L, const KParams& kp, const IcpArgs& a, GnState* st, long long* acc32,
-                                unsigned int* ticket, int max_iter, double eps, double delta, const CommDev* comm,
-                                int blocks) {
-  CommDev cd;
-  if (comm) {
-    cd = *comm;
-  } else {
-    memset(&cd, 0, sizeof(cd));
-    cd.nranks = 1;
-  }
-  {
-    ScopedKernel sk(L, K_ICP_FUSED);
-    k_icp_fused<<<blocks, kIcpThreads, 0, L.stream>>>(kp, a, st, acc32, ticket, max_iter, eps, delta, cd);
-  }
 }
 
 }  // namespace sb

@@ -20,6 +20,7 @@ constexpr uint32_t kComposeAge = 100u;           // SurfelMap.h:144
 constexpr int kMaxGnIter = 256;
 constexpr uint32_t kTilePoolCap = 16u * 1024u * 1024u;  // surfels held by the HBM tile cache (1 GiB)
 constexpr uint32_t kMaxTileSlots = 16384u;
+constexpr int kGroupCounts = 256;  // group totals of the update pass: kMaxSurfels / 256 threads / 64 blocks per group = 256
 
 // everything the kernels need from sb_params plus the derived constants the reference computes on the host
 struct KParams {
@@ -64,7 +65,7 @@ struct GnState {
   int k;                 // k_
   int done;              // loop left (converged or max iterations)
   int history_len;
-  int pad;
+  int error;             // a bounded spin of the persistent kernel timed out (missing block / peer GPU)
   double history[(kMaxGnIter + 1) * 16];
 };
 
@@ -102,7 +103,7 @@ struct PoseDev {
   int fallback;                // track loss detected: the frame-to-frame minimisation runs
   int trackLoss;               // counter
   int icp_iterations;          // k_ of the frame-to-model minimisation
-  int pad;
+  int gn_error;                // the persistent Gauss-Newton kernel gave up (timeout): the scan's pose is invalid
   float t_err, r_err;
   int pad2[2];
 };
@@ -165,25 +166,35 @@ bool make_key_tensor_map(CUtensorMap* out, const unsigned long long* keys, int W
 // K1-K3 (+ optionally K6b radius map and the re-arming of the index-map keys / integrated flags for the map update)
 void launch_preprocess(const Launch& L, const KParams& kp, const float4* pts, const float* labels, const float* probs,
                        uint32_t n, uint32_t timestamp, PrepKeys& keys, FrameDev out, float4* radius_map,
-                       unsigned long long* index_keys, uint8_t* integrated);
+                       unsigned long long* index_keys, uint8_t* integrated, uint32_t* group_counts);
 
 // sb_icp.cu
 void launch_icp_jacobian(const Launch& L, const KParams& kp, const IcpArgs& a, const Mat4& pose, int iteration,
                          long long* acc32, long long* slots, unsigned int* ticket, int blocks);
-void launch_icp_fused_iteration(const Launch& L, const KParams& kp, const IcpArgs& a, GnState* st, long long* acc32,
-                                unsigned int* ticket, int max_iter, double eps, double delta, const CommDev* comm,
-                                int blocks);
-void launch_gn_init(const Launch& L, GnState* st, const Mat4d& T0, long long* acc32, unsigned int* ticket,
-                    unsigned int* epoch_flag);
-int launch_icp_persistent(const Launch& L, const KParams& kp, const IcpArgs& a, GnState* st, long long* slots,
-                          unsigned int* ticket, unsigned int* epoch_flag, int max_iter, double eps, double delta,
-                          const CommDev* comm, int blocks, unsigned long long* trace);
-int icp_persistent_max_blocks(int sm_count);
-// pose bookkeeping kernels (sb_icp.cu)
+// ---- persistent Gauss-Newton kernel (sb_icp.cu) ----
+enum GnMode { GN_PLAIN = 0, GN_MAIN = 1, GN_POST = 2 };
+struct GnJob {
+  int mode;
+  IcpArgs a;    // GN_PLAIN / GN_MAIN: the objective; GN_POST: the statistics pass at identity (all rows)
+  IcpArgs fb;   // GN_POST: the frame-to-frame recovery objective (row stripe in multi-GPU mode)
+  GnState* st;  // state of the run (GN_PLAIN: prepared by k_gn_init)
+  PoseDev* pd;  // GN_MAIN / GN_POST
+  long long* stats32;                       // GN_POST: raw sums of the statistics pass, read by the host after the scan
+  float* poses; float* poses_inv; uint32_t t_map;  // GN_POST: pose-table entry of this scan
+  float* Mtab; uint32_t n_poses;            // GN_MAIN / GN_POST: table inv(P) * poses[t] filled at the end (or null)
+  int initialize_identity, fallback_mode;
+  uint32_t timestamp;
+  int max_iter;
+  double eps, delta;
+  unsigned int epoch_base;
+};
+void launch_gn_init(const Launch& L, GnState* st, const Mat4d& T0, long long* acc32);
+int launch_gn_persistent(const Launch& L, const KParams& kp, const GnJob& job, long long* slots, unsigned int* ticket,
+                         unsigned int* epoch_flag, const CommDev* comm, int blocks);
+int gn_persistent_max_blocks(int sm_count);
+// one-thread bookkeeping kernels: first scan of a sequence and the host-callback exchange
 void launch_pose_after_icp(const Launch& L, const GnState* gn, PoseDev* pd, const Mat4d& T0, uint32_t timestamp,
                            int fallback_mode);
-void launch_gn_init_fallback(const Launch& L, GnState* st, const PoseDev* pd, long long* acc32, unsigned int* ticket,
-                             unsigned int* epoch_flag);
 void launch_pose_finalize(const Launch& L, const GnState* gn, PoseDev* pd, int had_icp, float* poses, float* poses_inv,
                           uint32_t t);
 int icp_grid_blocks(int sm_count);
@@ -202,20 +213,20 @@ void launch_render_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, c
                            RenderTargets t);
 void launch_render_resolve(const Launch& L, const KParams& kp, SurfelPlanes s, const float* M_old, const float* M_new,
                            RenderTargets t, FrameDev f_old, FrameDev f_new, FrameDev f_comp, FrameDev f_out,
-                           int keep_semantic, int lequal);
+                           FrameDev f_copy, int keep_semantic, int lequal);
 void launch_index_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, const uint32_t* n_dev, uint32_t n_upper,
                           const float* M, unsigned long long* keys);
 void launch_radius(const Launch& L, const KParams& kp, FrameDev frame, float4* radius_map, unsigned long long* index_keys,
-                   uint8_t* integrated);
+                   uint8_t* integrated, uint32_t* group_counts);
+void launch_compact_update(const Launch& L, SurfelPlanes src, const uint8_t* keep, const uint32_t* block_counts,
+                           const uint32_t* group_counts, const uint32_t* n_dev, uint32_t n_upper, SurfelPlanes dst,
+                           uint32_t cap, uint32_t* count_out, uint32_t* kept_out);
 void launch_update_surfels(const Launch& L, const KParams& kp, SurfelPlanes src, SurfelPlanes tmp, const uint32_t* n_dev,
                            uint32_t n_upper, const Mat4& pose, const Mat4& inv_pose, const Mat4* pose_dev,
                            const Mat4* inv_pose_dev, const float* poses,
                            const float* poses_inv, const unsigned long long* index_keys, const float4* radius_map,
                            FrameDev frame, int timestamp, float2 submap_center, float submap_extent,
-                           uint8_t* integrated, uint8_t* keep, uint32_t* block_counts);
-void launch_gen_surfels(const Launch& L, const KParams& kp, FrameDev frame, const float4* radius_map,
-                        const uint8_t* integrated, const float* poses, int timestamp, float2 submap_center,
-                        float submap_extent, SurfelPlanes tmp, uint8_t* keep, uint32_t* block_counts);
+                           uint8_t* integrated, uint8_t* keep, uint32_t* block_counts, uint32_t* group_counts);
 // single-pass update / generate with in-place ordered compaction (decoupled look-back)
 void launch_gen_compact(const Launch& L, const KParams& kp, FrameDev frame, const float4* radius_map,
                         const uint8_t* integrated, const float* poses, int timestamp, float2 submap_center,

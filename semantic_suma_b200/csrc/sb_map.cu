@@ -80,12 +80,6 @@ __device__ __forceinline__ long long edge_fn(const RVert& P, const RVert& Q, lon
   return (Q.X - P.X) * (Y - P.Y) - (Q.Y - P.Y) * (X - P.X);
 }
 
-// what a fragment of one surfel writes to: which key images, with which low key bits
-struct Emit {
-  uint32_t k;
-  uint32_t flags;  // bit0 old-class surfel, bit1 new-class surfel, bit2 GL_LEQUAL composed mode
-};
-
 __device__ __forceinline__ bool edge_tie(const RVert& P, const RVert& Q) {  // rule for pixels exactly on an edge
   long long dx = Q.X - P.X, dy = Q.Y - P.Y;
   return dy > 0 || (dy == 0 && dx > 0);
@@ -141,142 +135,184 @@ __device__ __forceinline__ TriSetup tri_prepare(RVert A, RVert B, RVert C, int W
   return t;
 }
 
-// fragment stage for one covered pixel (render_surfels.frag:19-33 + depth test)
-__device__ __forceinline__ void tri_fragment(const TriSetup& t, const Emit& e, const RenderTargets& rt, int W,
-                                             long long wB, long long wC, int di, int dj) {
+constexpr int kRenderThreads = 256;
+// A quad whose pixel bounding box is at most 12 x 5 is rasterised by its own lane (azimuth pixels are 2.5 x finer than
+// elevation pixels at 64 x 2048, so the typical disc is ~6 x 2.5 pixels) ...
+constexpr int kSmallW = 12, kSmallH = 5;
+constexpr int kSmallSpan = 1 << 14;  // ... if its vertices lie within 64 pixels of the box origin: int32 edge functions are exact
+
+// a surfel that passed every test of the vertex / geometry stage (render_surfels.geom:84-92)
+struct Cand {
+  float px, py, pz, nx, ny, nz, r, cx;
+  uint32_t k, flags;  // flags: bit0 old-class surfel, bit1 new-class surfel, bit2 GL_LEQUAL composed mode
+};
+
+// render_surfels.geom:80-82, 100-118: the four quad corners in window coordinates (1/256 pixel)
+__device__ __forceinline__ void quad_corners(const KParams& kp, const Cand& c, RVert q[4]) {
+  const V3 pp = mk3(c.px, c.py, c.pz), nn = mk3(c.nx, c.ny, c.nz);
+  V3 u = normalize3(mk3(nn.y - nn.z, -nn.x, nn.x));
+  V3 v = normalize3(cross3(nn, u));
+  V3 ru = scale3(c.r, u), rv = scale3(c.r, v);
+  V3 corner[4];
+  corner[0] = sub3(sub3(pp, ru), rv);
+  corner[1] = sub3(add3(pp, ru), rv);
+  corner[2] = add3(sub3(pp, ru), rv);
+  corner[3] = add3(add3(pp, ru), rv);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float x, y, z;
+    project01(corner[i], kp.m_fov_up, kp.m_fov, kp.m_min_depth, kp.m_max_depth, x, y, z);
+    if (c.cx - x > 0.5f) x += 1.0f;  // .geom:68
+    if (x - c.cx > 0.5f) x -= 1.0f;  // .geom:69
+    float xw = (0.5f * (2.0f * x - 1.0f) + 0.5f) * (float)kp.Wm;
+    float yw = (0.5f * (2.0f * y - 1.0f) + 0.5f) * (float)kp.Hm;
+    q[i].z = 0.5f * (2.0f * z - 1.0f) + 0.5f;
+    q[i].X = __float2ll_rn(xw * 256.0f);
+    q[i].Y = __float2ll_rn(yw * 256.0f);
+    q[i].tx = (i & 1) ? 1.0f : -1.0f;
+    q[i].ty = (i & 2) ? 1.0f : -1.0f;
+  }
+}
+
+// fragment stage (render_surfels.frag:19-33) + depth test + key update, shared by both rasterisers
+__device__ __forceinline__ void emit_fragment(float tx, float ty, float z, size_t pix, uint32_t k, uint32_t flags,
+                                              const RenderTargets& rt) {
+  if (tx * tx + ty * ty > 1.0f) return;   // outside the disc
+  if (!(z >= 0.0f && z <= 1.0f)) return;  // near / far clip
+  unsigned long long d = (unsigned long long)depth24(z);
+  const bool lequal = (flags & 4u) != 0;
+  if (!lequal && d >= kDepthClear) return;  // GL_LESS against the cleared depth
+  unsigned long long hi = d << 40;
+  // keys only ever decrease: a (possibly stale) read that is already smaller proves the atomic cannot win, so most hidden
+  // fragments never reach the L2 atomic unit
+  if (flags & 1u) {  // old-class surfel
+    if (rt.key_old) {
+      unsigned long long key = hi | k;
+      if (key < rt.key_old[pix]) atomicMin(rt.key_old + pix, key);
+    }
+    if (rt.key_comp) {  // old pass is drawn first: it wins depth ties under GL_LESS, loses them under GL_LEQUAL
+      unsigned long long key = lequal ? (hi | (1ull << 32) | (unsigned long long)(0xffffffffu - k)) : (hi | k);
+      if (key < rt.key_comp[pix]) atomicMin(rt.key_comp + pix, key);
+    }
+  }
+  if (flags & 2u) {  // new-class surfel
+    if (rt.key_new) {
+      unsigned long long key = hi | k;
+      if (key < rt.key_new[pix]) atomicMin(rt.key_new + pix, key);
+    }
+    if (rt.key_comp) {
+      unsigned long long key = lequal ? (hi | (unsigned long long)(0xffffffffu - k)) : (hi | (1ull << 32) | k);
+      if (key < rt.key_comp[pix]) atomicMin(rt.key_comp + pix, key);
+    }
+  }
+}
+
+// One triangle of a small quad, everything relative to the quad's first pixel centre (X0, Y0): all magnitudes stay below
+// 2^14 + 2^10, so the int32 edge functions, their steps and the area equal the int64 ones of tri_prepare() bit for bit.
+struct TriSmall {
+  int eA, eB, eC, sxA, sxB, sxC, syA, syB, syC;
+  float farea, zA, zB, zC, txA, txB, txC, tyA, tyB, tyC;
+  uint32_t ties, valid;
+};
+__device__ __forceinline__ int edge32(int Px, int Py, int Qx, int Qy) {  // edge_fn(P, Q, X0, Y0), P and Q relative to (X0, Y0)
+  return (Qx - Px) * (0 - Py) - (Qy - Py) * (0 - Px);
+}
+__device__ __forceinline__ bool tie32(int Px, int Py, int Qx, int Qy) {
+  int dx = Qx - Px, dy = Qy - Py;
+  return dy > 0 || (dy == 0 && dx > 0);
+}
+__device__ __forceinline__ TriSmall tri_small(const RVert& a, const RVert& b0, const RVert& c0, long long X0, long long Y0) {
+  TriSmall t;
+  t.valid = 0;
+  int Ax = (int)(a.X - X0), Ay = (int)(a.Y - Y0);
+  int Bx = (int)(b0.X - X0), By = (int)(b0.Y - Y0);
+  int Cx = (int)(c0.X - X0), Cy = (int)(c0.Y - Y0);
+  float zB = b0.z, zC = c0.z, txB = b0.tx, txC = c0.tx, tyB = b0.ty, tyC = c0.ty;
+  int area = (Bx - Ax) * (Cy - Ay) - (By - Ay) * (Cx - Ax);
+  if (area == 0) return t;
+  if (area < 0) {  // same orientation fix as tri_prepare(): swap B and C
+    int ti = Bx; Bx = Cx; Cx = ti;
+    ti = By; By = Cy; Cy = ti;
+    float tf = zB; zB = zC; zC = tf;
+    tf = txB; txB = txC; txC = tf;
+    tf = tyB; tyB = tyC; tyC = tf;
+    area = -area;
+  }
+  t.farea = (float)area;
+  t.eA = edge32(Bx, By, Cx, Cy);
+  t.eB = edge32(Cx, Cy, Ax, Ay);
+  t.eC = edge32(Ax, Ay, Bx, By);
+  t.sxA = -256 * (Cy - By); t.sxB = -256 * (Ay - Cy); t.sxC = -256 * (By - Ay);
+  t.syA = 256 * (Cx - Bx); t.syB = 256 * (Ax - Cx); t.syC = 256 * (Bx - Ax);
+  t.ties = (tie32(Bx, By, Cx, Cy) ? 1u : 0u) | (tie32(Cx, Cy, Ax, Ay) ? 2u : 0u) | (tie32(Ax, Ay, Bx, By) ? 4u : 0u);
+  t.zA = a.z; t.zB = zB; t.zC = zC;
+  t.txA = a.tx; t.txB = txB; t.txC = txC;
+  t.tyA = a.ty; t.tyB = tyB; t.tyC = tyC;
+  t.valid = 1;
+  return t;
+}
+__device__ __forceinline__ void tri_small_pixel(const TriSmall& t, int di, int dj, size_t pix, uint32_t k, uint32_t flags,
+                                                const RenderTargets& rt) {
+  const int wA = t.eA + di * t.sxA + dj * t.syA, wB = t.eB + di * t.sxB + dj * t.syB, wC = t.eC + di * t.sxC + dj * t.syC;
+  const bool in = (wA > 0 || (wA == 0 && (t.ties & 1u))) && (wB > 0 || (wB == 0 && (t.ties & 2u))) &&
+                  (wC > 0 || (wC == 0 && (t.ties & 4u)));
+  if (!in) return;
   float fB = (float)wB / t.farea, fC = (float)wC / t.farea;
   float fA = (1.0f - fB) - fC;
   float tx = (fA * t.txA + fB * t.txB) + fC * t.txC;
   float ty = (fA * t.tyA + fB * t.tyB) + fC * t.tyC;
-  if (tx * tx + ty * ty > 1.0f) return;  // outside the disc
   float z = (fA * t.zA + fB * t.zB) + fC * t.zC;
-  if (!(z >= 0.0f && z <= 1.0f)) return;  // near / far clip
-  unsigned long long d = (unsigned long long)depth24(z);
-  const bool lequal = (e.flags & 4u) != 0;
-  if (!lequal && d >= kDepthClear) return;  // GL_LESS against the cleared depth
-  size_t pix = (size_t)(t.j0 + dj) * W + (size_t)(t.i0 + di);
-  unsigned long long hi = d << 40;
-  // keys only ever decrease: a (possibly stale, L1-cached) read that is already smaller proves the atomic cannot
-  // win, so most hidden fragments never reach the L2 atomic unit
-  if (e.flags & 1u) {  // old-class surfel
-    if (rt.key_old) {
-      unsigned long long key = hi | e.k;
-      if (key < rt.key_old[pix]) atomicMin(rt.key_old + pix, key);
-    }
-    if (rt.key_comp) {  // old pass is drawn first: it wins depth ties under GL_LESS, loses them under GL_LEQUAL
-      unsigned long long key = lequal ? (hi | (1ull << 32) | (unsigned long long)(0xffffffffu - e.k)) : (hi | e.k);
-      if (key < rt.key_comp[pix]) atomicMin(rt.key_comp + pix, key);
-    }
-  }
-  if (e.flags & 2u) {  // new-class surfel
-    if (rt.key_new) {
-      unsigned long long key = hi | e.k;
-      if (key < rt.key_new[pix]) atomicMin(rt.key_new + pix, key);
-    }
-    if (rt.key_comp) {
-      unsigned long long key = lequal ? (hi | (unsigned long long)(0xffffffffu - e.k)) : (hi | (1ull << 32) | e.k);
-      if (key < rt.key_comp[pix]) atomicMin(rt.key_comp + pix, key);
-    }
-  }
+  emit_fragment(tx, ty, z, pix, k, flags, rt);
 }
 
-constexpr int kRenderThreads = 128;
-constexpr int kTrisPerWarp = 64;  // two triangles per surfel, 32 surfels per warp pass
-
-// the triangles of one warp pass, structure-of-arrays in shared memory (lanes read different triangles: an array per
-// field keeps those reads spread over the banks)
-struct WarpTris {
-  long long e[3][kTrisPerWarp], sx[3][kTrisPerWarp], sy[3][kTrisPerWarp];
-  float farea[kTrisPerWarp], z[3][kTrisPerWarp], tx[3][kTrisPerWarp], ty[3][kTrisPerWarp];
-  int i0[kTrisPerWarp], j0[kTrisPerWarp], ni[kTrisPerWarp], nj[kTrisPerWarp];
-  uint32_t ties[kTrisPerWarp], k[kTrisPerWarp], flags[kTrisPerWarp];
-  int prefix[kTrisPerWarp + 1];  // exclusive prefix sums of the bounding-box pixel counts
-};
-
-__device__ __forceinline__ void tris_store(WarpTris& w, int slot, const TriSetup& t, const Emit& e) {
-  w.e[0][slot] = t.eA; w.e[1][slot] = t.eB; w.e[2][slot] = t.eC;
-  w.sx[0][slot] = t.sxA; w.sx[1][slot] = t.sxB; w.sx[2][slot] = t.sxC;
-  w.sy[0][slot] = t.syA; w.sy[1][slot] = t.syB; w.sy[2][slot] = t.syC;
-  w.farea[slot] = t.farea;
-  w.z[0][slot] = t.zA; w.z[1][slot] = t.zB; w.z[2][slot] = t.zC;
-  w.tx[0][slot] = t.txA; w.tx[1][slot] = t.txB; w.tx[2][slot] = t.txC;
-  w.ty[0][slot] = t.tyA; w.ty[1][slot] = t.tyB; w.ty[2][slot] = t.tyC;
-  w.i0[slot] = t.i0; w.j0[slot] = t.j0; w.ni[slot] = t.ni; w.nj[slot] = t.nj;
-  w.ties[slot] = t.ties; w.k[slot] = e.k; w.flags[slot] = e.flags;
-  w.prefix[slot + 1] = (t.ni + 1) * (t.nj + 1);
-}
-__device__ __forceinline__ void tris_load(const WarpTris& w, int slot, TriSetup& t, Emit& e) {
-  t.eA = w.e[0][slot]; t.eB = w.e[1][slot]; t.eC = w.e[2][slot];
-  t.sxA = w.sx[0][slot]; t.sxB = w.sx[1][slot]; t.sxC = w.sx[2][slot];
-  t.syA = w.sy[0][slot]; t.syB = w.sy[1][slot]; t.syC = w.sy[2][slot];
-  t.farea = w.farea[slot];
-  t.zA = w.z[0][slot]; t.zB = w.z[1][slot]; t.zC = w.z[2][slot];
-  t.txA = w.tx[0][slot]; t.txB = w.tx[1][slot]; t.txC = w.tx[2][slot];
-  t.tyA = w.ty[0][slot]; t.tyB = w.ty[1][slot]; t.tyC = w.ty[2][slot];
-  t.i0 = w.i0[slot]; t.j0 = w.j0[slot]; t.ni = w.ni[slot]; t.nj = w.nj[slot];
-  t.ties = w.ties[slot]; t.valid = 1;
-  e.k = w.k[slot]; e.flags = w.flags[slot];
-}
-
-// Balanced rasterisation of all triangles of the warp pass: the bounding-box pixels of all triangles form one
-// flattened list of T items, lane l walks items [l*ch, (l+1)*ch). Quads differ by two orders of magnitude in size
-// (a surfel created far away and seen from close by covers hundreds of pixels); with one lane per quad the warp runs
-// as long as its largest quad while most lanes idle. Edge functions stay exact: incremental int64 adds inside a row,
-// re-based at every row / triangle change.
-__device__ __forceinline__ void raster_balanced(const WarpTris& w, int ntris, int total, const RenderTargets& rt, int W,
-                                                int lane) {
-  const int ch = (total + 31) >> 5;
-  int item = lane * ch;
-  const int end = min(item + ch, total);
-  if (item >= end) return;
-  int lo = 0, hi = ntris;  // largest j with prefix[j] <= item
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (w.prefix[mid] <= item) lo = mid; else hi = mid;
-  }
-  int j = lo;
-  while (item < end) {
-    TriSetup t;
-    Emit e;
-    tris_load(w, j, t, e);
-    const int first = w.prefix[j], cnt = w.prefix[j + 1] - first;
-    const int local = item - first;
-    const int wd = t.ni + 1;
-    int dj = local / wd, di = local - dj * wd;
-    int n_here = min(end - item, cnt - local);
+// a large quad, rasterised by a whole warp: the lanes stride over the bounding-box pixels of each triangle (int64 edges)
+__device__ __forceinline__ void raster_big(const KParams& kp, const Cand& c, const RenderTargets& rt, int lane) {
+  RVert q[4];
+  quad_corners(kp, c, q);
+#pragma unroll 1
+  for (int tri = 0; tri < 2; ++tri) {
+    TriSetup t = tri == 0 ? tri_prepare(q[0], q[1], q[2], kp.Wm, kp.Hm) : tri_prepare(q[1], q[2], q[3], kp.Wm, kp.Hm);
+    if (!t.valid) continue;
+    const int wd = t.ni + 1, total = wd * (t.nj + 1);
     const bool tieA = t.ties & 1u, tieB = t.ties & 2u, tieC = t.ties & 4u;
-    long long rowA = t.eA + (long long)dj * t.syA, rowB = t.eB + (long long)dj * t.syB, rowC = t.eC + (long long)dj * t.syC;
-    long long wA = rowA + (long long)di * t.sxA, wB = rowB + (long long)di * t.sxB, wC = rowC + (long long)di * t.sxC;
-    for (int q = 0; q < n_here; ++q) {
-      bool in = (wA > 0 || (wA == 0 && tieA)) && (wB > 0 || (wB == 0 && tieB)) && (wC > 0 || (wC == 0 && tieC));
-      if (in) tri_fragment(t, e, rt, W, wB, wC, di, dj);
-      if (++di > t.ni) {
-        di = 0;
-        ++dj;
-        rowA += t.syA; rowB += t.syB; rowC += t.syC;
-        wA = rowA; wB = rowB; wC = rowC;
-      } else {
-        wA += t.sxA; wB += t.sxB; wC += t.sxC;
-      }
+    for (int item = lane; item < total; item += 32) {
+      const int dj = item / wd, di = item - dj * wd;
+      const long long wA = t.eA + (long long)di * t.sxA + (long long)dj * t.syA;
+      const long long wB = t.eB + (long long)di * t.sxB + (long long)dj * t.syB;
+      const long long wC = t.eC + (long long)di * t.sxC + (long long)dj * t.syC;
+      const bool in = (wA > 0 || (wA == 0 && tieA)) && (wB > 0 || (wB == 0 && tieB)) && (wC > 0 || (wC == 0 && tieC));
+      if (!in) continue;
+      float fB = (float)wB / t.farea, fC = (float)wC / t.farea;
+      float fA = (1.0f - fB) - fC;
+      float tx = (fA * t.txA + fB * t.txB) + fC * t.txC;
+      float ty = (fA * t.tyA + fB * t.tyB) + fC * t.tyC;
+      float z = (fA * t.zA + fB * t.zB) + fC * t.zC;
+      emit_fragment(tx, ty, z, (size_t)(t.j0 + dj) * kp.Wm + (size_t)(t.i0 + di), c.k, c.flags, rt);
     }
-    item += n_here;
-    ++j;
   }
 }
 
-// render_surfels.vert:42-54 + .geom:76-122 for every surfel of the map. One lane per surfel for the transform, the
-// visibility tests, the corner projection and the triangle setup; the rasterisation of the warp's triangles is then
-// shared evenly by its 32 lanes (raster_balanced).
-__global__ void __launch_bounds__(kRenderThreads) k_render_scatter(KParams kp, SurfelPlanes s, const uint32_t* __restrict__ n_dev,
-                                                                   const float* __restrict__ Mtab, float conf_thr, int t_thr,
-                                                                   int emit_old, int emit_new, int lequal, RenderTargets rt) {
-  __shared__ WarpTris s_tris[kRenderThreads / 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  WarpTris& wt = s_tris[warp];
-  wt.prefix[2 * lane + 1] = 0;
-  wt.prefix[2 * lane + 2] = 0;
-  if (lane == 0) wt.prefix[0] = 0;
-  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+// render_surfels.vert:42-54 + .geom:76-122 + rasterisation + depth test for every surfel of the map.
+//  stage A/B (one thread per surfel): confidence / age-class tests on two lanes, then transform, visibility and the
+//    projection of the centre -- about half of the map drops out here;
+//  compaction: the survivors are packed densely through shared memory, so that
+//  stage C (corner projections + triangle set-up, the expensive part) and the rasterisation run on full warps.
+//  A surfel covers about the pixel it was created from, so almost every quad is small: those are rasterised by their own
+//  lane with int32 edge functions held in registers; the rare large ones are queued and rasterised by whole warps.
+//  (Round 1 kept every triangle in shared memory and balanced single pixels over the warp: 15 of 32 lanes active, 51 %
+//  issue utilisation at 25 % occupancy -- profiles/r01_ncu_full_summary.csv.)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kRenderThreads, kMinBlocks) k_render_scatter(KParams kp, SurfelPlanes s, const uint32_t* __restrict__ n_dev,
+                                                                      const float* __restrict__ Mtab, float conf_thr, int t_thr,
+                                                                      int emit_old, int emit_new, int lequal, RenderTargets rt) {
+  __shared__ float c_f[8][kRenderThreads];
+  __shared__ uint32_t c_k[kRenderThreads], c_flags[kRenderThreads];
+  __shared__ int s_warp_cnt[kRenderThreads / 32];
+  __shared__ int s_nbig;
+  __shared__ uint16_t s_big[kRenderThreads];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_nbig = 0;
+  const uint32_t k = blockIdx.x * blockDim.x + tid;
   bool alive = k < *n_dev;
   float4 p0, p1, p2;
   bool is_old = false, is_new = false;
@@ -291,276 +327,88 @@ __global__ void __launch_bounds__(kRenderThreads) k_render_scatter(KParams kp, S
     is_new = emit_new && (creation >= t_thr || ts >= t_thr);  // .geom:91
     alive = is_old || is_new;
   }
-  TriSetup t0, t1;
-  t0.valid = t1.valid = 0;
+  Cand c;
   if (alive) {
     p0 = __ldg(s.p0 + k);
     float M[16];
     load_mat(Mtab, pose_index(p2.w), M);
     V3 pp = xform_point(M, mk3(p0.x, p0.y, p0.z));
     V3 nn = xform_dir(M, mk3(p1.x, p1.y, p1.z));
-    float r = p0.w;
     bool visible = dot3(nn, divs3(neg3(pp), len3(pp))) > 0.01f;  // .geom:84
     float cx, cy, cz;
     project01(pp, kp.m_fov_up, kp.m_fov, kp.m_min_depth, kp.m_max_depth, cx, cy, cz);
-    if (visible && cx >= 0.0f && cy >= 0.0f && cz >= 0.0f && cx < 1.0f && cy < 1.0f && cz < 1.0f) {
-      V3 u = normalize3(mk3(nn.y - nn.z, -nn.x, nn.x));
-      V3 v = normalize3(cross3(nn, u));
-      V3 ru = scale3(r, u), rv = scale3(r, v);
-      V3 corner[4];
-      corner[0] = sub3(sub3(pp, ru), rv);
-      corner[1] = sub3(add3(pp, ru), rv);
-      corner[2] = add3(sub3(pp, ru), rv);
-      corner[3] = add3(add3(pp, ru), rv);
-      RVert q[4];
+    alive = visible && cx >= 0.0f && cy >= 0.0f && cz >= 0.0f && cx < 1.0f && cy < 1.0f && cz < 1.0f;
+    c.px = pp.x; c.py = pp.y; c.pz = pp.z; c.nx = nn.x; c.ny = nn.y; c.nz = nn.z; c.r = p0.w; c.cx = cx;
+  }
+  // ---- dense packing of the survivors (their order inside the block is irrelevant: visibility is decided by the keys) ----
+  const unsigned ballot = __ballot_sync(0xffffffffu, alive);
+  if (lane == 0) s_warp_cnt[warp] = __popc(ballot);
+  __syncthreads();
+  int base = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kRenderThreads / 32; ++w) {
+    const int cnt = s_warp_cnt[w];
+    if (w < warp) base += cnt;
+    total += cnt;
+  }
+  if (total == 0) return;
+  if (alive) {
+    const int slot = base + __popc(ballot & ((1u << lane) - 1u));
+    c_f[0][slot] = c.px; c_f[1][slot] = c.py; c_f[2][slot] = c.pz; c_f[3][slot] = c.nx;
+    c_f[4][slot] = c.ny; c_f[5][slot] = c.nz; c_f[6][slot] = c.r; c_f[7][slot] = c.cx;
+    c_k[slot] = k;
+    c_flags[slot] = (is_old ? 1u : 0u) | (is_new ? 2u : 0u) | (lequal ? 4u : 0u);
+  }
+  __syncthreads();
+  // ---- stage C + small-quad rasterisation on dense lanes ----
+  if (tid < total) {
+    c.px = c_f[0][tid]; c.py = c_f[1][tid]; c.pz = c_f[2][tid]; c.nx = c_f[3][tid];
+    c.ny = c_f[4][tid]; c.nz = c_f[5][tid]; c.r = c_f[6][tid]; c.cx = c_f[7][tid];
+    c.k = c_k[tid]; c.flags = c_flags[tid];
+    RVert q[4];
+    quad_corners(kp, c, q);
+    // pixel bounding box of the quad (union of the boxes of its two triangles), clamped to the image
+    long long minX = min(min(q[0].X, q[1].X), min(q[2].X, q[3].X)), maxX = max(max(q[0].X, q[1].X), max(q[2].X, q[3].X));
+    long long minY = min(min(q[0].Y, q[1].Y), min(q[2].Y, q[3].Y)), maxY = max(max(q[0].Y, q[1].Y), max(q[2].Y, q[3].Y));
+    long long i0 = ceil_div256(minX - 128), i1 = floor_div256(maxX - 128);
+    long long j0 = ceil_div256(minY - 128), j1 = floor_div256(maxY - 128);
+    if (i0 < 0) i0 = 0;
+    if (j0 < 0) j0 = 0;
+    if (i1 > kp.Wm - 1) i1 = kp.Wm - 1;
+    if (j1 > kp.Hm - 1) j1 = kp.Hm - 1;
+    if (i0 <= i1 && j0 <= j1) {  // otherwise the quad covers no pixel centre
+      const long long X0 = i0 * 256 + 128, Y0 = j0 * 256 + 128;
+      const int ni = (int)(i1 - i0), nj = (int)(j1 - j0);
+      bool small = ni < kSmallW && nj < kSmallH;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float x, y, z;
-        project01(corner[i], kp.m_fov_up, kp.m_fov, kp.m_min_depth, kp.m_max_depth, x, y, z);
-        if (cx - x > 0.5f) x += 1.0f;  // .geom:68
-        if (x - cx > 0.5f) x -= 1.0f;  // .geom:69
-        float xw = (0.5f * (2.0f * x - 1.0f) + 0.5f) * (float)kp.Wm;
-        float yw = (0.5f * (2.0f * y - 1.0f) + 0.5f) * (float)kp.Hm;
-        q[i].z = 0.5f * (2.0f * z - 1.0f) + 0.5f;
-        q[i].X = __float2ll_rn(xw * 256.0f);
-        q[i].Y = __float2ll_rn(yw * 256.0f);
-        q[i].tx = (i & 1) ? 1.0f : -1.0f;
-        q[i].ty = (i & 2) ? 1.0f : -1.0f;
+        long long dx = q[i].X - X0, dy = q[i].Y - Y0;
+        small = small && dx > -kSmallSpan && dx < kSmallSpan && dy > -kSmallSpan && dy < kSmallSpan;
       }
-      t0 = tri_prepare(q[0], q[1], q[2], kp.Wm, kp.Hm);
-      t1 = tri_prepare(q[1], q[2], q[3], kp.Wm, kp.Hm);
-    }
-  }
-  // slots of this lane's triangles: exclusive prefix of the per-lane triangle counts
-  const int cnt = (int)t0.valid + (int)t1.valid;
-  int incl = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  const int ntris = __shfl_sync(0xffffffffu, incl, 31);
-  if (ntris == 0) return;
-  __syncwarp();
-  if (cnt) {
-    Emit e;
-    e.k = k;
-    e.flags = (is_old ? 1u : 0u) | (is_new ? 2u : 0u) | (lequal ? 4u : 0u);
-    int slot = incl - cnt;
-    if (t0.valid) tris_store(wt, slot++, t0, e);
-    if (t1.valid) tris_store(wt, slot, t1, e);
-  }
-  __syncwarp();
-  // prefix sums of the pixel counts (pairs of adjacent slots per lane)
-  int a = wt.prefix[2 * lane + 1], b = wt.prefix[2 * lane + 2];
-  int sum = a + b, isum = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, isum, o);
-    if (lane >= o) isum += v;
-  }
-  const int total = __shfl_sync(0xffffffffu, isum, 31);
-  __syncwarp();
-  wt.prefix[2 * lane + 1] = isum - sum + a;
-  wt.prefix[2 * lane + 2] = isum;
-  __syncwarp();
-  raster_balanced(wt, ntris, total, rt, kp.Wm, lane);
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (opt-in: SUMA_B200_RENDER_VARIANT=1|2, not measured yet -- DESIGN.md section 8): the same kernel with a
-// leaner per-warp triangle store, so that more blocks fit on an SM. ncu on the default kernel shows 51 % issue-slot use
-// at 25 % occupancy (86 registers, 36.9 KB shared memory per block). Here the x/y edge steps are kept as int32 (they
-// are 256 * a vertex-coordinate difference of one quad, |.| <= 2^28), the texture coordinates as six sign bits (they
-// are +-1), the bounding box in two packed words: 21.5 KB per block. Arithmetic and results are identical.
-// ------------------------------------------------------------------------------------------------------------
-struct WarpTrisLite {
-  long long e[3][kTrisPerWarp];
-  int sx[3][kTrisPerWarp], sy[3][kTrisPerWarp];
-  float farea[kTrisPerWarp], z[3][kTrisPerWarp];
-  uint32_t boxx[kTrisPerWarp], boxy[kTrisPerWarp];  // i0 | ni << 16, j0 | nj << 16
-  uint32_t k[kTrisPerWarp];
-  uint32_t meta[kTrisPerWarp];  // bits 0-2 ties, 3-5 flags, 6-8 tx sign of A,B,C (set = +1), 9-11 ty sign of A,B,C
-  int prefix[kTrisPerWarp + 1];
-};
-
-__device__ __forceinline__ void tris_store_lite(WarpTrisLite& w, int slot, const TriSetup& t, const Emit& e) {
-  w.e[0][slot] = t.eA; w.e[1][slot] = t.eB; w.e[2][slot] = t.eC;
-  w.sx[0][slot] = (int)t.sxA; w.sx[1][slot] = (int)t.sxB; w.sx[2][slot] = (int)t.sxC;
-  w.sy[0][slot] = (int)t.syA; w.sy[1][slot] = (int)t.syB; w.sy[2][slot] = (int)t.syC;
-  w.farea[slot] = t.farea;
-  w.z[0][slot] = t.zA; w.z[1][slot] = t.zB; w.z[2][slot] = t.zC;
-  w.boxx[slot] = (uint32_t)t.i0 | ((uint32_t)t.ni << 16);
-  w.boxy[slot] = (uint32_t)t.j0 | ((uint32_t)t.nj << 16);
-  w.k[slot] = e.k;
-  w.meta[slot] = (t.ties & 7u) | ((e.flags & 7u) << 3) | ((t.txA > 0.0f ? 1u : 0u) << 6) | ((t.txB > 0.0f ? 1u : 0u) << 7) |
-                 ((t.txC > 0.0f ? 1u : 0u) << 8) | ((t.tyA > 0.0f ? 1u : 0u) << 9) | ((t.tyB > 0.0f ? 1u : 0u) << 10) |
-                 ((t.tyC > 0.0f ? 1u : 0u) << 11);
-  w.prefix[slot + 1] = (t.ni + 1) * (t.nj + 1);
-}
-__device__ __forceinline__ void tris_load_lite(const WarpTrisLite& w, int slot, TriSetup& t, Emit& e) {
-  t.eA = w.e[0][slot]; t.eB = w.e[1][slot]; t.eC = w.e[2][slot];
-  t.sxA = (long long)w.sx[0][slot]; t.sxB = (long long)w.sx[1][slot]; t.sxC = (long long)w.sx[2][slot];
-  t.syA = (long long)w.sy[0][slot]; t.syB = (long long)w.sy[1][slot]; t.syC = (long long)w.sy[2][slot];
-  t.farea = w.farea[slot];
-  t.zA = w.z[0][slot]; t.zB = w.z[1][slot]; t.zC = w.z[2][slot];
-  const uint32_t m = w.meta[slot], bx = w.boxx[slot], by = w.boxy[slot];
-  t.txA = (m & (1u << 6)) ? 1.0f : -1.0f; t.txB = (m & (1u << 7)) ? 1.0f : -1.0f; t.txC = (m & (1u << 8)) ? 1.0f : -1.0f;
-  t.tyA = (m & (1u << 9)) ? 1.0f : -1.0f; t.tyB = (m & (1u << 10)) ? 1.0f : -1.0f; t.tyC = (m & (1u << 11)) ? 1.0f : -1.0f;
-  t.i0 = (int)(bx & 0xffffu); t.ni = (int)(bx >> 16);
-  t.j0 = (int)(by & 0xffffu); t.nj = (int)(by >> 16);
-  t.ties = m & 7u; t.valid = 1;
-  e.k = w.k[slot]; e.flags = (m >> 3) & 7u;
-}
-
-// raster_balanced over the lean store (same walk, same arithmetic)
-__device__ __forceinline__ void raster_balanced_lite(const WarpTrisLite& w, int ntris, int total, const RenderTargets& rt,
-                                                     int W, int lane) {
-  const int ch = (total + 31) >> 5;
-  int item = lane * ch;
-  const int end = min(item + ch, total);
-  if (item >= end) return;
-  int lo = 0, hi = ntris;  // largest j with prefix[j] <= item
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (w.prefix[mid] <= item) lo = mid; else hi = mid;
-  }
-  int j = lo;
-  while (item < end) {
-    TriSetup t;
-    Emit e;
-    tris_load_lite(w, j, t, e);
-    const int first = w.prefix[j], cnt = w.prefix[j + 1] - first;
-    const int local = item - first;
-    const int wd = t.ni + 1;
-    int dj = local / wd, di = local - dj * wd;
-    int n_here = min(end - item, cnt - local);
-    const bool tieA = t.ties & 1u, tieB = t.ties & 2u, tieC = t.ties & 4u;
-    long long rowA = t.eA + (long long)dj * t.syA, rowB = t.eB + (long long)dj * t.syB, rowC = t.eC + (long long)dj * t.syC;
-    long long wA = rowA + (long long)di * t.sxA, wB = rowB + (long long)di * t.sxB, wC = rowC + (long long)di * t.sxC;
-    for (int q = 0; q < n_here; ++q) {
-      bool in = (wA > 0 || (wA == 0 && tieA)) && (wB > 0 || (wB == 0 && tieB)) && (wC > 0 || (wC == 0 && tieC));
-      if (in) tri_fragment(t, e, rt, W, wB, wC, di, dj);
-      if (++di > t.ni) {
-        di = 0;
-        ++dj;
-        rowA += t.syA; rowB += t.syB; rowC += t.syC;
-        wA = rowA; wB = rowB; wC = rowC;
+      if (small) {
+        const TriSmall t0 = tri_small(q[0], q[1], q[2], X0, Y0), t1 = tri_small(q[1], q[2], q[3], X0, Y0);
+        for (int dj = 0; dj <= nj; ++dj)
+          for (int di = 0; di <= ni; ++di) {
+            const size_t pix = (size_t)((int)j0 + dj) * kp.Wm + (size_t)((int)i0 + di);
+            if (t0.valid) tri_small_pixel(t0, di, dj, pix, c.k, c.flags, rt);
+            if (t1.valid) tri_small_pixel(t1, di, dj, pix, c.k, c.flags, rt);
+          }
       } else {
-        wA += t.sxA; wB += t.sxB; wC += t.sxC;
+        s_big[atomicAdd(&s_nbig, 1)] = (uint16_t)tid;
       }
     }
-    item += n_here;
-    ++j;
   }
-}
-
-template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(kRenderThreads, MIN_BLOCKS)
-    k_render_scatter_lite(KParams kp, SurfelPlanes s, const uint32_t* __restrict__ n_dev, const float* __restrict__ Mtab,
-                          float conf_thr, int t_thr, int emit_old, int emit_new, int lequal, RenderTargets rt) {
-  __shared__ WarpTrisLite s_tris[kRenderThreads / 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  WarpTrisLite& wt = s_tris[warp];
-  wt.prefix[2 * lane + 1] = 0;
-  wt.prefix[2 * lane + 2] = 0;
-  if (lane == 0) wt.prefix[0] = 0;
-  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  bool alive = k < *n_dev;
-  float4 p0, p1, p2;
-  bool is_old = false, is_new = false;
-  if (alive) {
-    p2 = __ldg(s.p2 + k);
-    p1 = __ldg(s.p1 + k);
-    alive = !kp.use_stability || p1.w > conf_thr;  // .geom:87 (cheap test first)
+  __syncthreads();
+  // ---- large quads: one warp each ----
+  const int nbig = s_nbig;
+  for (int b = warp; b < nbig; b += kRenderThreads / 32) {
+    const int slot = s_big[b];
+    Cand cb;
+    cb.px = c_f[0][slot]; cb.py = c_f[1][slot]; cb.pz = c_f[2][slot]; cb.nx = c_f[3][slot];
+    cb.ny = c_f[4][slot]; cb.nz = c_f[5][slot]; cb.r = c_f[6][slot]; cb.cx = c_f[7][slot];
+    cb.k = c_k[slot]; cb.flags = c_flags[slot];
+    raster_big(kp, cb, rt, lane);
   }
-  if (alive) {
-    int creation = (int)p2.w, ts = (int)__float_as_uint(p2.x);
-    is_old = emit_old && (creation < t_thr);                  // .geom:90
-    is_new = emit_new && (creation >= t_thr || ts >= t_thr);  // .geom:91
-    alive = is_old || is_new;
-  }
-  TriSetup t0, t1;
-  t0.valid = t1.valid = 0;
-  if (alive) {
-    p0 = __ldg(s.p0 + k);
-    float M[16];
-    load_mat(Mtab, pose_index(p2.w), M);
-    V3 pp = xform_point(M, mk3(p0.x, p0.y, p0.z));
-    V3 nn = xform_dir(M, mk3(p1.x, p1.y, p1.z));
-    float r = p0.w;
-    bool visible = dot3(nn, divs3(neg3(pp), len3(pp))) > 0.01f;  // .geom:84
-    float cx, cy, cz;
-    project01(pp, kp.m_fov_up, kp.m_fov, kp.m_min_depth, kp.m_max_depth, cx, cy, cz);
-    if (visible && cx >= 0.0f && cy >= 0.0f && cz >= 0.0f && cx < 1.0f && cy < 1.0f && cz < 1.0f) {
-      V3 u = normalize3(mk3(nn.y - nn.z, -nn.x, nn.x));
-      V3 v = normalize3(cross3(nn, u));
-      V3 ru = scale3(r, u), rv = scale3(r, v);
-      V3 corner[4];
-      corner[0] = sub3(sub3(pp, ru), rv);
-      corner[1] = sub3(add3(pp, ru), rv);
-      corner[2] = add3(sub3(pp, ru), rv);
-      corner[3] = add3(add3(pp, ru), rv);
-      RVert q[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float x, y, z;
-        project01(corner[i], kp.m_fov_up, kp.m_fov, kp.m_min_depth, kp.m_max_depth, x, y, z);
-        if (cx - x > 0.5f) x += 1.0f;  // .geom:68
-        if (x - cx > 0.5f) x -= 1.0f;  // .geom:69
-        float xw = (0.5f * (2.0f * x - 1.0f) + 0.5f) * (float)kp.Wm;
-        float yw = (0.5f * (2.0f * y - 1.0f) + 0.5f) * (float)kp.Hm;
-        q[i].z = 0.5f * (2.0f * z - 1.0f) + 0.5f;
-        q[i].X = __float2ll_rn(xw * 256.0f);
-        q[i].Y = __float2ll_rn(yw * 256.0f);
-        q[i].tx = (i & 1) ? 1.0f : -1.0f;
-        q[i].ty = (i & 2) ? 1.0f : -1.0f;
-      }
-      t0 = tri_prepare(q[0], q[1], q[2], kp.Wm, kp.Hm);
-      t1 = tri_prepare(q[1], q[2], q[3], kp.Wm, kp.Hm);
-    }
-  }
-  const int cnt = (int)t0.valid + (int)t1.valid;
-  int incl = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  const int ntris = __shfl_sync(0xffffffffu, incl, 31);
-  if (ntris == 0) return;
-  __syncwarp();
-  if (cnt) {
-    Emit e;
-    e.k = k;
-    e.flags = (is_old ? 1u : 0u) | (is_new ? 2u : 0u) | (lequal ? 4u : 0u);
-    int slot = incl - cnt;
-    if (t0.valid) tris_store_lite(wt, slot++, t0, e);
-    if (t1.valid) tris_store_lite(wt, slot, t1, e);
-  }
-  __syncwarp();
-  int a = wt.prefix[2 * lane + 1], b = wt.prefix[2 * lane + 2];
-  int sum = a + b, isum = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, isum, o);
-    if (lane >= o) isum += v;
-  }
-  const int total = __shfl_sync(0xffffffffu, isum, 31);
-  __syncwarp();
-  wt.prefix[2 * lane + 1] = isum - sum + a;
-  wt.prefix[2 * lane + 2] = isum;
-  __syncwarp();
-  raster_balanced_lite(wt, ntris, total, rt, kp.Wm, lane);
-}
-
-static int render_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SUMA_B200_RENDER_VARIANT");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
 }
 
 void launch_render_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, const uint32_t* n_dev, uint32_t n_upper,
@@ -570,17 +418,19 @@ void launch_render_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, c
   {
     ScopedKernel sk(L, K_RENDER_SCATTER);
     const unsigned grid = (n_upper + kRenderThreads - 1) / kRenderThreads;
-    const int variant = render_variant();
-    if (variant == 1) {  // lean triangle store, up to 6 blocks per SM without spills
-      k_render_scatter_lite<6><<<grid, kRenderThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr, emit_old,
-                                                                      emit_new, lequal, t);
-    } else if (variant == 2) {  // lean triangle store, 8 blocks per SM (64 registers, a few spills)
-      k_render_scatter_lite<8><<<grid, kRenderThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr, emit_old,
-                                                                      emit_new, lequal, t);
-    } else {
-      k_render_scatter<<<grid, kRenderThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr, emit_old, emit_new,
-                                                              lequal, t);
+    // resident blocks per SM the register allocation aims at (2: 110 registers, 3: 80, 4: 64 with a few spills);
+    // TEMPORARY measurement switch, the winner becomes the only instantiation
+    static int occ = -1;
+    if (occ < 0) {
+      const char* e = getenv("SUMA_B200_RENDER_OCC");
+      occ = e ? atoi(e) : 3;
     }
+    if (occ == 2)
+      k_render_scatter<2><<<grid, kRenderThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr, emit_old, emit_new, lequal, t);
+    else if (occ == 4)
+      k_render_scatter<4><<<grid, kRenderThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr, emit_old, emit_new, lequal, t);
+    else
+      k_render_scatter<3><<<grid, kRenderThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr, emit_old, emit_new, lequal, t);
   }
 }
 
@@ -616,7 +466,7 @@ __device__ __forceinline__ Px resolve_px(const SurfelPlanes& s, unsigned long lo
 __global__ void __launch_bounds__(kThreads) k_render_resolve(KParams kp, SurfelPlanes s, const float* __restrict__ M_old,
                                                             const float* __restrict__ M_new, RenderTargets t,
                                                             FrameDev f_old, FrameDev f_new, FrameDev f_comp,
-                                                            FrameDev f_out, int keep_semantic, int lequal) {
+                                                            FrameDev f_out, FrameDev f_copy, int keep_semantic, int lequal) {
   int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= kp.Wm * kp.Hm) return;
   // every key image that is read here is cleared again ("consume and clear"): no separate fill before the next view
@@ -637,6 +487,11 @@ __global__ void __launch_bounds__(kThreads) k_render_resolve(KParams kp, SurfelP
     f_new.vertex[pix] = pn.v;
     f_new.normal[pix] = pn.n;
     if (!keep_semantic) f_new.semantic[pix] = pn.s;
+    if (f_copy.vertex) {  // lastModelFrame_->copy(*map_->newMapFrame()), SurfelMapping.cpp:407, fused into this pass
+      f_copy.vertex[pix] = pn.v;
+      f_copy.normal[pix] = pn.n;
+      f_copy.semantic[pix] = keep_semantic ? f_new.semantic[pix] : pn.s;
+    }
   }
   if (f_comp.vertex && !t.key_comp && t.key_old && t.key_new) {
     // GL_LESS, old pass drawn before the new pass on an uncleared buffer (SurfelMap.cpp:893-906): the winner of the
@@ -672,12 +527,12 @@ __global__ void __launch_bounds__(kThreads) k_render_resolve(KParams kp, SurfelP
 
 void launch_render_resolve(const Launch& L, const KParams& kp, SurfelPlanes s, const float* M_old, const float* M_new,
                            RenderTargets t, FrameDev f_old, FrameDev f_new, FrameDev f_comp, FrameDev f_out,
-                           int keep_semantic, int lequal) {
+                           FrameDev f_copy, int keep_semantic, int lequal) {
   int P = kp.Wm * kp.Hm;
   {
     ScopedKernel sk(L, K_RENDER_RESOLVE);
     k_render_resolve<<<(P + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, s, M_old, M_new, t, f_old, f_new,
-                                                                            f_comp, f_out, keep_semantic, lequal);
+                                                                            f_comp, f_out, f_copy, keep_semantic, lequal);
   }
 }
 
@@ -722,11 +577,12 @@ void launch_index_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, co
 // stand-alone map update; in the per-scan pipeline the tiled preprocessing pass has already done all three)
 __global__ void __launch_bounds__(kThreads) k_radius(KParams kp, FrameDev f, float4* __restrict__ radius_map,
                                                     unsigned long long* __restrict__ index_keys,
-                                                    uint8_t* __restrict__ integrated) {
+                                                    uint8_t* __restrict__ integrated, uint32_t* __restrict__ group_counts) {
   int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= kp.W * kp.H) return;
   index_keys[pix] = ~0ull;
   integrated[pix] = 0;
+  if (pix < kGroupCounts) group_counts[pix] = 0;
   float4 V = __ldg(f.vertex + pix), N = __ldg(f.normal + pix);
   float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
   V3 v = mk3(V.x, V.y, V.z), n = mk3(N.x, N.y, N.z);
@@ -745,11 +601,12 @@ __global__ void __launch_bounds__(kThreads) k_radius(KParams kp, FrameDev f, flo
 }
 
 void launch_radius(const Launch& L, const KParams& kp, FrameDev frame, float4* radius_map, unsigned long long* index_keys,
-                   uint8_t* integrated) {
+                   uint8_t* integrated, uint32_t* group_counts) {
   int P = kp.W * kp.H;
   {
     ScopedKernel sk(L, K_RADIUS);
-    k_radius<<<(P + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, frame, radius_map, index_keys, integrated);
+    k_radius<<<(P + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, frame, radius_map, index_keys, integrated,
+                                                                       group_counts);
   }
 }
 
@@ -885,7 +742,8 @@ __global__ void __launch_bounds__(kThreads) k_update_surfels(KParams kp, SurfelP
                                                             const uint32_t* __restrict__ n_dev, UpdateArgs ua,
                                                             FrameDev f, uint8_t* __restrict__ integrated,
                                                             uint8_t* __restrict__ keep,
-                                                            uint32_t* __restrict__ block_counts) {
+                                                            uint32_t* __restrict__ block_counts,
+                                                            uint32_t* __restrict__ group_counts) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   bool kept = false;
   if (k < *n_dev) {
@@ -1018,46 +876,12 @@ __global__ void __launch_bounds__(kThreads) k_update_surfels(KParams kp, SurfelP
     keep[k] = kept ? 1 : 0;
   }
   int cnt = __syncthreads_count(kept ? 1 : 0);
-  if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)cnt;
-}
-
-// K6d: gen_surfels.vert:38-52 + .geom:109-145; thread t <-> pixel (x = t / H, y = t % H): x-major order
-// (SurfelMap.cpp:88-92), fused with the K6e predicate
-__global__ void __launch_bounds__(kThreads) k_gen_surfels(KParams kp, FrameDev f, const float4* __restrict__ radius_map,
-                                                         const uint8_t* __restrict__ integrated,
-                                                         const float* __restrict__ poses, int timestamp,
-                                                         float2 center, float extent, SurfelPlanes tmp,
-                                                         uint8_t* __restrict__ keep,
-                                                         uint32_t* __restrict__ block_counts) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  bool kept = false;
-  if (t < kp.W * kp.H) {
-    int x = t / kp.H, y = t - x * kp.H;
-    size_t pix = (size_t)y * kp.W + x;
-    float4 V = __ldg(f.vertex + pix), N = __ldg(f.normal + pix), R = __ldg(radius_map + pix);
-    bool invalid = (V.w < 1.0f) || (N.w < 1.0f);
-    invalid = invalid || (R.w < 0.5f);
-    bool integ = integrated[pix] != 0;
-    V3 v = mk3(V.x, V.y, V.z), n = mk3(N.x, N.y, N.z);
-    V3 view_dir = divs3(neg3(v), len3(v));
-    bool valid = !invalid && !integ && (dot3(n, view_dir) > 0.01f);
-    if (valid) {
-      V3 ng = normalize3(n);
-      float4 S = __ldg(f.semantic + pix);
-      float conf = is_movable(S.x * 255.0f) ? kp.log_prior - 0.5f : kp.log_prior;
-      float4 o0 = make_float4(v.x, v.y, v.z, R.x);
-      float4 o1 = make_float4(ng.x, ng.y, ng.z, conf);
-      float4 o2 = make_float4(__uint_as_float((uint32_t)timestamp), pack_rgb(0.0f, 0.0f, 1.0f), 1.0f, (float)timestamp);
-      kept = submap_keep(poses, o0, o2, center, extent);
-      tmp.p0[t] = o0;
-      tmp.p1[t] = o1;
-      tmp.p2[t] = o2;
-      tmp.p3[t] = S;
-    }
-    keep[t] = kept ? 1 : 0;
+  if (threadIdx.x == 0) {
+    block_counts[blockIdx.x] = (uint32_t)cnt;
+    // two-level counts: the ordered compaction that follows finds a block's output offset from <= 64 group totals + <= 63
+    // block counts -- no scan pass (group totals are cleared by the per-pixel prologue of the map update)
+    if (cnt) atomicAdd(group_counts + (blockIdx.x >> 6), (uint32_t)cnt);
   }
-  int cnt = __syncthreads_count(kept ? 1 : 0);
-  if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)cnt;
 }
 
 // K6d + K6e in ONE pass: new surfels are appended in x-major pixel order behind the updated ones
@@ -1210,6 +1034,68 @@ __global__ void __launch_bounds__(kThreads) k_compact_scatter(SurfelPlanes src, 
   dst.p3[d] = src.p3[k];
 }
 
+// Ordered compaction of the update pass without a scan kernel: block b's offset = sum of the group totals before its
+// group (<= 64 for 4M surfels) + the counts of the earlier blocks of its own group (<= 63), summed by one warp.
+// The last block also publishes the totals (S' = base of the new surfels, kept count).
+__global__ void __launch_bounds__(kThreads) k_compact_update(SurfelPlanes src, const uint8_t* __restrict__ keep,
+                                                            const uint32_t* __restrict__ block_counts,
+                                                            const uint32_t* __restrict__ group_counts,
+                                                            const uint32_t* __restrict__ n_dev, SurfelPlanes dst, uint32_t cap,
+                                                            uint32_t* __restrict__ count_out,
+                                                            uint32_t* __restrict__ kept_out) {
+  __shared__ uint32_t warp_cnt[kThreads / 32];
+  __shared__ uint32_t s_offset;
+  const uint32_t n = *n_dev;
+  const uint32_t nblocks = (n + kThreads - 1) / kThreads;
+  if (blockIdx.x >= nblocks) {
+    if (nblocks == 0 && blockIdx.x == 0 && threadIdx.x == 0) {  // empty map
+      *count_out = 0;
+      if (kept_out) *kept_out = 0;
+    }
+    return;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool kept = (k < n) && keep[k];
+  const unsigned m = __ballot_sync(0xffffffffu, kept);
+  if (lane == 0) warp_cnt[warp] = __popc(m);
+  if (warp == 0) {
+    const uint32_t g = blockIdx.x >> 6, first = g << 6;
+    uint32_t v = 0;
+    for (uint32_t i = lane; i < g; i += 32) v += group_counts[i];
+    for (uint32_t b = first + lane; b < blockIdx.x; b += 32) v += block_counts[b];
+    v = __reduce_add_sync(0xffffffffu, v);
+    if (lane == 0) s_offset = v;
+  }
+  __syncthreads();
+  uint32_t before = 0;
+  for (int w = 0; w < warp; ++w) before += warp_cnt[w];
+  if (blockIdx.x == nblocks - 1 && threadIdx.x == 0) {
+    const uint32_t total = s_offset + block_counts[blockIdx.x];
+    *count_out = total < cap ? total : cap;
+    if (kept_out) *kept_out = total;
+  }
+  if (!kept) return;
+  const uint32_t d = s_offset + before + __popc(m & ((1u << lane) - 1u));
+  if (d >= cap) return;  // transform feedback drops what does not fit
+  dst.p0[d] = src.p0[k];
+  dst.p1[d] = src.p1[k];
+  dst.p2[d] = src.p2[k];
+  dst.p3[d] = src.p3[k];
+}
+
+void launch_compact_update(const Launch& L, SurfelPlanes src, const uint8_t* keep, const uint32_t* block_counts,
+                           const uint32_t* group_counts, const uint32_t* n_dev, uint32_t n_upper, SurfelPlanes dst,
+                           uint32_t cap, uint32_t* count_out, uint32_t* kept_out) {
+  uint32_t blocks = (n_upper + kThreads - 1) / kThreads;
+  if (blocks == 0) blocks = 1;
+  {
+    ScopedKernel sk(L, K_COMPACT_SCATTER);
+    k_compact_update<<<blocks, kThreads, 0, L.stream>>>(src, keep, block_counts, group_counts, n_dev, dst, cap, count_out,
+                                                       kept_out);
+  }
+}
+
 void launch_compact(const Launch& L, SurfelPlanes src, const uint8_t* keep, const uint32_t* block_counts,
                     uint32_t* block_offsets, const uint32_t* n_dev, uint32_t n_upper, SurfelPlanes dst,
                     const uint32_t* base_dev, uint32_t cap, uint32_t* count_out, uint32_t* kept_out) {
@@ -1263,26 +1149,15 @@ void launch_update_surfels(const Launch& L, const KParams& kp, SurfelPlanes src,
                            const Mat4* inv_pose_dev, const float* poses,
                            const float* poses_inv, const unsigned long long* index_keys, const float4* radius_map,
                            FrameDev frame, int timestamp, float2 submap_center, float submap_extent,
-                           uint8_t* integrated, uint8_t* keep, uint32_t* block_counts) {
+                           uint8_t* integrated, uint8_t* keep, uint32_t* block_counts, uint32_t* group_counts) {
   if (n_upper == 0) return;
   UpdateArgs ua{pose, inv_pose, pose_dev, inv_pose_dev, poses, poses_inv, index_keys, radius_map, timestamp,
                 submap_center, submap_extent};
   {
     ScopedKernel sk(L, K_UPDATE_SURFELS);
     k_update_surfels<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, src, tmp, n_dev, ua, frame,
-                                                                                  integrated, keep, block_counts);
-  }
-}
-
-void launch_gen_surfels(const Launch& L, const KParams& kp, FrameDev frame, const float4* radius_map,
-                        const uint8_t* integrated, const float* poses, int timestamp, float2 submap_center,
-                        float submap_extent, SurfelPlanes tmp, uint8_t* keep, uint32_t* block_counts) {
-  int P = kp.W * kp.H;
-  {
-    ScopedKernel sk(L, K_GEN_SURFELS);
-    k_gen_surfels<<<(P + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(kp, frame, radius_map, integrated, poses,
-                                                                         timestamp, submap_center, submap_extent, tmp,
-                                                                         keep, block_counts);
+                                                                                  integrated, keep, block_counts,
+                                                                                  group_counts);
   }
 }
 

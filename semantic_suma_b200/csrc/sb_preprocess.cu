@@ -91,6 +91,7 @@ struct PrepIO {
   float4* radius_map;               // optional: init_radiusConf output of this frame (pipeline mode)
   unsigned long long* index_keys;   // optional: index-map key image to re-arm (pipeline mode)
   uint8_t* integrated;              // optional: "measurement integrated" flags to clear (pipeline mode)
+  uint32_t* group_counts;           // optional: group totals of the update pass to clear (pipeline mode)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(kPrepThreads) k_preprocess_tile(KParams kp, Pr
     }
     if (io.index_keys) io.index_keys[pix] = ~0ull;
     if (io.integrated) io.integrated[pix] = 0;
+    if (io.group_counts && pix < (size_t)kGroupCounts) io.group_counts[pix] = 0;
     // re-arm the other key image (own pixel and its mirror copies in the pads)
     unsigned long long* row = io.keys_next + (size_t)gy * Wp;
     row[gx + kPrepHalo] = ~0ull;
@@ -289,7 +291,7 @@ size_t preprocess_key_elems(int W, int H) { return (size_t)(W + 2 * kPrepHalo) *
 
 void launch_preprocess(const Launch& L, const KParams& kp, const float4* pts, const float* labels, const float* probs,
                        uint32_t n, uint32_t timestamp, PrepKeys& keys, FrameDev out, float4* radius_map,
-                       unsigned long long* index_keys, uint8_t* integrated) {
+                       unsigned long long* index_keys, uint8_t* integrated, uint32_t* group_counts) {
   unsigned long long* cur = keys.img[keys.cur];
   unsigned long long* nxt = keys.img[keys.cur ^ 1];
   if (n > 0) {
@@ -299,7 +301,7 @@ void launch_preprocess(const Launch& L, const KParams& kp, const float4* pts, co
     }
   }
   PrepIO io{pts, labels, probs, n, timestamp < 10 ? 1 : 0, cur, nxt, out.vertex, out.normal, out.semantic, radius_map,
-            index_keys, integrated};
+            index_keys, integrated, group_counts};
   dim3 grid((kp.W + kPrepTX - 1) / kPrepTX, (kp.H + kPrepTY - 1) / kPrepTY);
   {
     ScopedKernel sk(L, K_PREPROCESS_TILE);
