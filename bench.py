@@ -8,8 +8,10 @@ HDL-64E-shaped scans: 64 x 2048 range images, exactly 10 Gauss-Newton iterations
 One step = one scan through the whole path (K1-K3 preprocessing, model rendering, 10 x (K5 + GN step), post-ICP
 rendering + statistics pass, K6 map update, model re-render). `value` is measured with the scans already resident in
 HBM; `e2e` goes through the C ABI with pinned HOST buffers (H2D of the scan and D2H of the pose / sums inside the
-timed region). N > 1 runs one independent sequence per GPU (weak scaling, no data-path collective).
-Prints ONE JSON line on rank 0.
+timed region). Every pass first pre-rolls the map with --preroll scans (steady-state map size) and the
+--warmup scans, untimed. N > 1 runs one independent sequence per GPU (weak scaling, no data-path collective) and adds a
+`striped` record: BASELINE.json configs[3] (128x4096, 15 iterations, row-striped K5 with the in-kernel peer-memory
+all-reduce) on the same GPUs, against the same sequence without striping. Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -125,7 +127,6 @@ def algorithmic_bytes(kernel, P, S, N, semantic):
     """compulsory HBM bytes of one launch (DESIGN.md 'Kernels and their rooflines')"""
     t = {
         "fill_u64": 8 * P, "project_scatter": 16 * N, "preprocess_tile": 8 * P + 16 * N + (48 + 16) * P,
-        "normals_erode": 32 * P + 32 * P, "floodfill": 32 * P + 16 * P,
         "icp_fused": (96 if semantic else 64) * P, "icp_jacobian": (96 if semantic else 64) * P,
         "render_scatter": 48 * S, "render_resolve": 3 * 8 * P + 4 * 48 * P,
         "index_scatter": 48 * S, "radius": 48 * P, "update_surfels": 129 * S, "gen_surfels": 84 * P,
@@ -134,17 +135,38 @@ def algorithmic_bytes(kernel, P, S, N, semantic):
     return float(t.get(kernel, 0))
 
 
+def pin_to_gpu_numa_node(local_rank):
+    """run this rank on the CPUs next to its GPU (nvidia-smi topo 'CPU Affinity'): launches and pinned copies of GPUs
+    4-7 otherwise cross the socket interconnect. Returns the cpu list used (or None)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].isdigit() else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d-%d (%d cpus)" % (min(cpus), max(cpus), len(cpus))
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def run_native(args, w, rank, world, local_rank):
     import torch
     from semantic_suma_b200 import api
 
-    n_frames = args.warmup + args.steps
-    dbg = bool(os.environ.get("SUMA_B200_WATCHDOG"))
-    if dbg:
-        print("[r%d] generating %d scans" % (rank, n_frames), file=sys.stderr, flush=True)
-    scans = generate_scans(w, n_frames, seed=1337 + (0 if args.striped else 1000 * rank))
-    if dbg:
-        print("[r%d] scans ready" % rank, file=sys.stderr, flush=True)
+    pre = args.preroll + args.warmup            # scans processed before the timed region of every pass
+    n_frames = pre + args.steps
+    scans = generate_scans(w, n_frames, seed=1337 + 1000 * rank)
+    striped_scans = None
+    if world > 1 and not args.no_striped:  # generated now: the worker pool forks, which must happen before CUDA is up
+        striped_scans = generate_scans(WORKLOADS["ouster128_4096_geometric"], STRIPED_PRE + STRIPED_STEPS, seed=4242)
+    numa = pin_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -153,9 +175,6 @@ def run_native(args, w, rank, world, local_rank):
     pp = api.default_params(**param_kwargs(w))
     slam = api.SurfelMapping(pp, device=local_rank)
     ctx = slam.ctx
-    if dist is not None and args.striped:
-        from semantic_suma_b200 import stripes
-        stripes.setup_comm(ctx, dist, fused=(args.comm == "fused"))
     stream = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     sem = w["semantic"]
@@ -164,7 +183,7 @@ def run_native(args, w, rank, world, local_rank):
             torch.from_numpy(q).cuda() if sem else None) for p, l, q in scans]
     pin = [(torch.from_numpy(p).pin_memory(), torch.from_numpy(l).pin_memory() if sem else None,
             torch.from_numpy(q).pin_memory() if sem else None) for p, l, q in scans]
-    h2d = sum(int(p.numel() * 4 + (l.numel() * 4 + q.numel() * 4 if sem else 0)) for p, l, q in pin[args.warmup:])
+    h2d = sum(int(p.numel() * 4 + (l.numel() * 4 + q.numel() * 4 if sem else 0)) for p, l, q in pin[pre:])
     torch.cuda.synchronize()
 
     def barrier():
@@ -173,13 +192,20 @@ def run_native(args, w, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def feed(bufs, f, on_device):
+        p, l, q = bufs[f]
+        slam.process_scan_raw(p.data_ptr(), l.data_ptr() if sem else 0, q.data_ptr() if sem else 0, p.shape[0], on_device)
+
+    def preroll(bufs, on_device):
+        """map pre-rolled to the steady state of SURVEY.md 8d (independent of --steps / --warmup) + the warm-up scans"""
+        slam.reset()
+        for f in range(pre):
+            feed(bufs, f, on_device)
+        ctx.synchronize()
+
     def one_pass(bufs, on_device, sampler=None):
         prefetch = args.prefetch and not on_device
-        slam.reset()
-        for f in range(args.warmup):
-            p, l, q = bufs[f]
-            slam.process_scan_raw(p.data_ptr(), l.data_ptr() if sem else 0, q.data_ptr() if sem else 0, p.shape[0],
-                                  on_device)
+        preroll(bufs, on_device)
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         launches0 = ctx.launch_count()
         barrier()
@@ -187,15 +213,13 @@ def run_native(args, w, rank, world, local_rank):
             sampler.start()
         t_wall = time.time()
         for i in range(args.steps):
-            p, l, q = bufs[args.warmup + i]
             with torch.cuda.stream(stream):
                 flush.zero_()  # L2 flush between timed steps (not timed)
             ev[i][0].record(stream)
-            if prefetch and i + 1 < args.steps:  # experimental: stage the next scan while this one is processed
-                pn, ln, qn = bufs[args.warmup + i + 1]
+            if prefetch and i + 1 < args.steps:  # stage the next scan on the copy stream while this one is processed
+                pn, ln, qn = bufs[pre + i + 1]
                 slam.prefetch_scan_raw(pn.data_ptr(), ln.data_ptr() if sem else 0, qn.data_ptr() if sem else 0, pn.shape[0])
-            slam.process_scan_raw(p.data_ptr(), l.data_ptr() if sem else 0, q.data_ptr() if sem else 0, p.shape[0],
-                                  on_device)
+            feed(bufs, pre + i, on_device)
             if not on_device:
                 slam.getCurrentPose()  # the step's result, read on the host
             ev[i][1].record(stream)
@@ -204,47 +228,52 @@ def run_native(args, w, rank, world, local_rank):
         if sampler:
             sampler.stop_flag = True
         ms = [a.elapsed_time(b) for a, b in ev]
-        total_ms = float(sum(ms))
+        total_ms = worst_ms = float(sum(ms))
         if dist is not None:
             t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
-        return total_ms, ctx.launch_count() - launches0, t_wall, ms
+            worst_ms = float(t.item())
+        return worst_ms, ctx.launch_count() - launches0, t_wall, ms
 
-    if dbg:
-        print("[r%d] buffers ready, starting passes" % rank, file=sys.stderr, flush=True)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # every GPU busy for >= 0.6 s right before the first timed pass: clocks of GPUs that idled are up, the caches of the
+    # host launch path are warm (SCALE_r01: the first pass caught a transient on the slowest rank)
+    t0 = time.time()
+    while True:
+        preroll(dev, True)
+        if time.time() - t0 > 0.6:
+            break
+    sampler = ClockSampler(local_rank)
     ms_dev, launches, wall_dev, per_step = one_pass(dev, True, sampler)
-    if dbg:
-        print("[r%d] device-resident pass done" % rank, file=sys.stderr, flush=True)
-    ms_e2e, _, wall_e2e, _ = one_pass(pin, False)
+    ms_e2e, _, wall_e2e, per_step_e2e = one_pass(pin, False)
     surfels = slam.getMap().size()
     gt = np.linalg.inv(synth.trajectory(1)[0]) @ synth.trajectory(n_frames)[-1]
     drift = float(np.linalg.norm(slam.getCurrentPose()[:3, 3] - gt[:3, 3]))
+    mine = {"rank": rank, "step_ms_min_med_max": [round(min(per_step), 4), round(statistics.median(per_step), 4),
+                                                  round(max(per_step), 4)],
+            "e2e_step_ms_med": round(statistics.median(per_step_e2e), 4), "clocks": sampler.summary(), "numa_cpus": numa}
+    per_rank = [mine]
+    if dist is not None:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
 
     # per-kernel device time with CUDA events on the launching stream, over the same timed frames
     roofline = None
     kernel_table = {}
-    if (rank == 0 or args.striped) and not args.no_profile:  # striped: every rank must walk the same scans
-        slam.reset()
-        for f in range(args.warmup):
-            p, l, q = dev[f]
-            slam.process_scan_raw(p.data_ptr(), l.data_ptr() if sem else 0, q.data_ptr() if sem else 0, p.shape[0], True)
-        ctx.synchronize()
+    if rank == 0 and not args.no_profile:
+        preroll(dev, True)
         ctx.profile(True)
         s_sum = 0
         for i in range(args.steps):
-            p, l, q = dev[args.warmup + i]
             with torch.cuda.stream(stream):
                 flush.zero_()
             s_sum += slam.getMap().size()
-            slam.process_scan_raw(p.data_ptr(), l.data_ptr() if sem else 0, q.data_ptr() if sem else 0, p.shape[0], True)
+            feed(dev, pre + i, True)
         prof = ctx.profile_collect()
         ctx.profile(False)
         tot = sum(v[0] for v in prof.values())
         P = w["width"] * w["height"]
         S_avg = s_sum / max(1, args.steps)
-        N_avg = float(np.mean([p.shape[0] for p, _, _ in scans[args.warmup:]]))
+        N_avg = float(np.mean([p.shape[0] for p, _, _ in scans[pre:]]))
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -272,71 +301,140 @@ def run_native(args, w, rank, world, local_rank):
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                     "avg_launch_us": round(us, 2), "surfels_avg": int(S_avg),
                     "step_share": kernel_table[top]["share"]}
+    slam.ctx.close()
+    del dev, pin
+    torch.cuda.empty_cache()
+
+    striped = None
+    if dist is not None and not args.no_striped:
+        striped = striped_record(striped_scans, rank, world, local_rank, dist)
 
     out = None
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_baseline(w, scans, budget_s=args.cpu_budget)
-        seqs = 1 if args.striped else world
-        value = seqs * args.steps / (ms_dev * 1e-3)
-        e2e_value = seqs * args.steps / (ms_e2e * 1e-3)
+        value = world * args.steps / (ms_dev * 1e-3)
+        e2e_value = world * args.steps / (ms_e2e * 1e-3)
         out = {
             "metric": "scans_per_sec", "value": round(value, 2), "unit": "scans/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_dev / args.steps, 4),
-            "higher_is_better": True, "scaling": "strong" if args.striped else "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "range_image": "%dx%d" % (w["height"], w["width"]),
-                       "icp_iterations": w["iters"], "semantic": sem, "sequences": 1 if args.striped else world,
-                       "parallelism": ("k5-row-stripes-x%d (%s)" % (world, "peer-memory all-reduce in-kernel" if args.comm == "fused"
-                                                                   else "torch.distributed all-reduce per iteration")) if args.striped
-                       else "one sequence per GPU",
-                       "surfels_end": int(surfels), "pose_drift_m": round(drift, 4),
+                       "icp_iterations": w["iters"], "semantic": sem, "sequences": world,
+                       "parallelism": "one sequence per GPU, no data-path collective",
+                       "map_preroll_scans": args.preroll, "surfels_end": int(surfels), "pose_drift_m": round(drift, 4),
                        "l2": "flushed between timed steps (256 MiB memset, untimed)",
-                       "step_ms_min_med_max": [round(min(per_step), 4), round(statistics.median(per_step), 4),
-                                               round(max(per_step), 4)],
+                       "gpu_preroll": ">= 0.6 s of scans on every rank before the timed pass",
+                       "per_rank": per_rank,
                        "timing": "CUDA events on the library's stream around every step, summed; max over ranks",
                        "reference_defaults": "config/default.xml except image size, max iterations, eps=delta=0"},
             "e2e": {"value": round(e2e_value, 2), "unit": "scans/s", "ms_per_step": round(ms_e2e / args.steps, 4),
-                    "h2d_bytes_per_step": int(h2d / args.steps) + 128, "d2h_bytes_per_step": 536 + 256 + 16,
+                    "h2d_bytes_per_step": int(h2d / args.steps) + 128, "d2h_bytes_per_step": 8192 + 64,
                     "wall_s": round(wall_e2e, 3), "input_prefetch": bool(args.prefetch)},
             "gpu_launches": int(launches),
-            "clocks": sampler.summary() if sampler else None,
+            "clocks": per_rank[0]["clocks"],
             "roofline": roofline, "kernels": kernel_table, "cpu_baseline": cpu,
         }
-    slam.ctx.close()
+        if striped is not None:
+            out["striped"] = striped
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return out
 
 
-def pick_oracle_threads(w, scans):
-    """The oracle scales with cores only up to a point (per-thread raster targets are merged per pixel, the host may be
-    a container with fewer usable cores than it reports): try a few thread counts on the first scans, keep the best."""
-    from oracle import oracle as O
-    ncpu = os.cpu_count() or 1
-    cands = sorted({c for c in (min(ncpu, 64), 32, 16, 8, 4) if c <= max(ncpu, 1)}, reverse=True)
-    po = O.default_params(**param_kwargs(w))
-    best, best_t, tried = cands[-1], float("inf"), {}
-    for c in cands:
-        O.set_threads(c)
-        sl = O.Slam(po)
-        for a in scans[:2]:
-            sl.process_scan(*a)
-        t0 = time.time()
-        for a in scans[2:6]:
-            sl.process_scan(*a)
-        dt = time.time() - t0
-        tried[c] = round(dt, 3)
-        if dt < best_t:
-            best, best_t = c, dt
-    return O.set_threads(best), tried
+STRIPED_PRE, STRIPED_STEPS = 10, 10
+
+
+def striped_record(scans, rank, world, local_rank, dist):
+    """BASELINE.json configs[3] on the same N GPUs: 128x4096 Ouster-style scans, 15 Gauss-Newton iterations, ONE sequence,
+    the K5 reduction striped over image rows, the 32 sums exchanged inside the persistent kernel over peer memory
+    (NVLink); the map is replicated. Measured against the same sequence run by every rank on its own (all rows, no
+    exchange); poses must be bit-identical across ranks and between both runs."""
+    import torch
+    from semantic_suma_b200 import api, stripes
+    w = WORKLOADS["ouster128_4096_geometric"]
+    pre, steps = STRIPED_PRE, STRIPED_STEPS
+    pp = api.default_params(**param_kwargs(w))
+    dev = [torch.from_numpy(p).cuda() for p, _, _ in scans]
+    torch.cuda.synchronize()
+    res = {}
+    poses = {}
+    for mode in ("solo", "striped"):
+        slam = api.SurfelMapping(pp, device=local_rank)
+        ctx = slam.ctx
+        rows = (0, w["height"])
+        if mode == "striped":
+            rows = stripes.setup_comm(ctx, dist, fused=True)
+        stream = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)
+        for f in range(pre):
+            slam.process_scan_raw(dev[f].data_ptr(), 0, 0, dev[f].shape[0], True)
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ctx.profile(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            slam.process_scan_raw(dev[pre + i].data_ptr(), 0, 0, dev[pre + i].shape[0], True)
+        e1.record(stream)
+        ctx.synchronize()
+        prof = ctx.profile_collect()
+        ctx.profile(False)
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gn_ms, gn_n = prof.get("icp_fused", (0.0, 1))
+        # the long launch is the 15-iteration minimisation; the short one the statistics pass
+        res[mode] = {"ms_per_scan": round(float(t.item()) / steps, 4), "rows": list(rows),
+                     "gn_launch_us_avg": round(1e3 * gn_ms / max(gn_n, 1), 2), "gn_launches_per_scan": round(gn_n / steps, 2)}
+        poses[mode] = slam.getCurrentPose().tobytes()
+        slam.ctx.close()
+    allp = [None] * world
+    dist.all_gather_object(allp, (poses["solo"], poses["striped"]))
+    identical = all(a == allp[0][0] and b == allp[0][0] for a, b in allp)
+    it = w["iters"]
+    # per scan: one GN_MAIN launch (15 iterations) + one GN_POST launch (1 statistics pass): 16 passes
+    d_us = (res["striped"]["gn_launch_us_avg"] - res["solo"]["gn_launch_us_avg"]) * 2.0 / (it + 1)
+    return {"workload": "ouster128_4096_geometric", "icp_iterations": it, "n_gpus": world, "scans": steps,
+            "exchange": "32 int64 sums per iteration, stored into every rank's mailbox and summed in-kernel (peer memory)",
+            "solo": res["solo"], "striped": res["striped"],
+            "speedup_vs_solo": round(res["solo"]["ms_per_scan"] / res["striped"]["ms_per_scan"], 4),
+            "gn_pass_us_delta_striped_minus_solo": round(d_us, 3),
+            "poses_bit_identical_across_ranks_and_modes": bool(identical)}
+
+
+def physical_cores_per_socket():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("cpu cores"):
+                return int(line.split(":")[1])
+    except Exception:  # noqa: BLE001
+        pass
+    return os.cpu_count() or 1
+
+
+def oracle_threads():
+    """a FIXED rule, so that the CPU arm does not swing between boxes: the physical cores of one socket, at most 64 (the
+    oracle's cap) and at most what this process may use"""
+    return max(1, min(physical_cores_per_socket(), 64, len(os.sched_getaffinity(0))))
 
 
 def cpu_baseline(w, scans, budget_s=15.0, max_frames=None):
-    """the CPU restatement of the reference (oracle/, OpenMP over all host cores) on a bounded sample of the same scans"""
+    """the CPU restatement of the reference (oracle/) on a bounded sample of the same scans: OpenMP on the physical cores
+    of one socket, plus the single-thread figure BASELINE.json's north_star names"""
     from oracle import oracle as O
-    threads, tried = pick_oracle_threads(w, scans)
     po = O.default_params(**param_kwargs(w))
+    O.set_threads(1)
+    sl = O.Slam(po)
+    t0 = time.time()
+    n1 = 0
+    for p, l, q in scans[:4]:
+        sl.process_scan(p, l, q)
+        n1 += 1
+        if time.time() - t0 > 0.35 * budget_s:
+            break
+    single = n1 / (time.time() - t0)
+    threads = O.set_threads(oracle_threads())
     sl = O.Slam(po)
     t0 = time.time()
     n = 0
@@ -347,28 +445,29 @@ def cpu_baseline(w, scans, budget_s=15.0, max_frames=None):
             break
     dt = time.time() - t0
     return {"value": round(n / dt, 3), "unit": "scans/s", "cores": threads, "kind": "port",
-            "sample": "first %d scans of the same synthetic sequence (map grows from empty), oracle/ C port, "
-                      "%d OpenMP threads (fastest of %s on scans 3-6)" % (n, threads, sorted(tried)),
-            "seconds": round(dt, 2), "host_cpus": os.cpu_count(), "thread_calibration_s": tried}
+            "sample": "first %d scans of the same synthetic sequence (map grows from empty), oracle/ C port, %d OpenMP "
+                      "threads = physical cores of one socket" % (n, threads),
+            "single_thread": {"value": round(single, 3), "unit": "scans/s", "cores": 1, "sample": "first %d scans" % n1},
+            "seconds": round(dt, 2), "host_cpus": os.cpu_count()}
 
 
 def run_reference(args, w, rank, world):
     """--impl reference: the reference has no CPU (or buildable GL) path in this environment; the arm times the
-    oracle's restatement of it on all host cores (C + OpenMP, thread-count independent results) on the same workload."""
+    oracle's restatement of it (C + OpenMP, thread-count independent results) on the same workload, same pre-rolled map."""
     if rank != 0:
         return None
-    n_frames = args.warmup + args.steps
-    scans = generate_scans(w, n_frames, seed=1337)
+    pre = args.preroll + args.warmup
+    scans = generate_scans(w, pre + args.steps, seed=1337)
     from oracle import oracle as O
-    threads, tried = pick_oracle_threads(w, scans)
+    threads = O.set_threads(oracle_threads())
     po = O.default_params(**param_kwargs(w))
     sl = O.Slam(po)
-    for f in range(args.warmup):
+    for f in range(pre):
         sl.process_scan(*scans[f])
     t0 = time.time()
     done = 0
     for i in range(args.steps):
-        sl.process_scan(*scans[args.warmup + i])
+        sl.process_scan(*scans[pre + i])
         done += 1
         if time.time() - t0 > args.ref_budget:
             break
@@ -379,12 +478,13 @@ def run_reference(args, w, rank, world):
         "steps": done, "warmup": args.warmup, "ms_per_step": round(1e3 * dt / done, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "range_image": "%dx%d" % (w["height"], w["width"]),
-                   "icp_iterations": w["iters"], "semantic": w["semantic"],
+                   "icp_iterations": w["iters"], "semantic": w["semantic"], "map_preroll_scans": args.preroll,
                    "note": "reference OpenGL path not runnable here (no GL/EGL, glow/gtsam/rangenet_lib absent); "
-                           "this is the CPU restatement in oracle/ (kind=port)"},
+                           "this is the CPU restatement in oracle/ (kind=port), pinned bit for bit to the reference's "
+                           "shader text (oracle/_ref)"},
         "cpu_baseline": {"value": round(v, 3), "unit": "scans/s", "cores": threads, "kind": "port",
-                         "sample": "%d scans after %d warm-up scans, %d OpenMP threads (fastest of %s)"
-                                   % (done, args.warmup, threads, sorted(tried)), "thread_calibration_s": tried,
+                         "sample": "%d scans after %d pre-roll + %d warm-up scans, %d OpenMP threads (physical cores of "
+                                   "one socket)" % (done, args.preroll, args.warmup, threads),
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": round(v, 3), "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -402,14 +502,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="hdl64_2048_geometric", choices=sorted(WORKLOADS))
-    ap.add_argument("--comm", choices=["fused", "callback"], default="fused",
-                    help="--striped exchange: in-kernel over peer memory (default) or the torch.distributed baseline")
-    ap.add_argument("--striped", action="store_true",
-                    help="N > 1: all ranks process the SAME sequence, the K5 reduction is striped over image rows and "
-                         "all-reduced inside the kernel over peer memory (BASELINE.json configs[3]); strong scaling")
-    ap.add_argument("--prefetch", action="store_true",
-                    help="experimental (not the default, not measured yet): in the e2e pass stage scan i+1 on a copy "
-                         "stream while scan i is processed (sb_prefetch_scan); every copy is still inside the timed region")
+    ap.add_argument("--preroll", type=int, default=60,
+                    help="scans processed (untimed) before the warm-up scans of every pass, in both arms: the map reaches the "
+                         "steady-state size of SURVEY.md 8d (~1e6 surfels) independent of --steps / --warmup")
+    ap.add_argument("--no-striped", action="store_true",
+                    help="N > 1: skip the extra `striped` record (128x4096, 15 iterations, row-striped K5 with the in-kernel "
+                         "peer-memory all-reduce, BASELINE.json configs[3])")
+    ap.add_argument("--no-prefetch", dest="prefetch", action="store_false",
+                    help="e2e pass: do not stage scan i+1 on the copy stream while scan i is processed (sb_prefetch_scan); "
+                         "with or without it every copy is inside the timed region")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)

@@ -26,7 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--surfels", type=int, default=1000000)
     ap.add_argument("--reps", type=int, default=20)
-    ap.add_argument("--max-scans", type=int, default=140)
+    ap.add_argument("--max-scans", type=int, default=110)
     args = ap.parse_args()
     import bench
     from semantic_suma_b200 import api

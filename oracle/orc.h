@@ -4,9 +4,17 @@
  * every function cites the file:line it follows, relative to /root/reference/src). It exists to CHECK the CUDA
  * path; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
  *
- * PARITY STATUS: "parity unpinned" -- the reference ships no tests, golden vectors or fixtures for this path
- *  and cannot be built here (OpenGL + un-vendored glow/gtsam/rangenet_lib). The oracle is
- * pinned by construction (line-by-line restatement) and by analytic known-answer tests (tests/test_oracle_*.py).
+ * PARITY STATUS: pinned to the reference's own shader text. The reference ships no tests, golden vectors or fixtures
+ * for this path and its build (OpenGL + un-vendored glow/gtsam/rangenet_lib + Qt) cannot run here,
+ * but its GLSL sources compile: oracle/ref_harness rewrites them mechanically to C++ where they lie under
+ * /root/reference and drives them with a minimal software GL (oracle/_ref, git-ignored). With GLSL built-ins following
+ * the rules of orc_math.h (a legal GL: the specification leaves their precision open) every image, sum, surfel record and
+ * the surfel order of this oracle equal the transpiled shaders' BIT FOR BIT (tests/test_ref_shaders.py, including
+ * adversarial random inputs); with fp64/libm built-ins (an independent GL) they agree to the tolerances stated there.
+ * Round 2 found and fixed one deviation that way (update_surfels.geom:35: the integrated flag of a surfel that is removed
+ * in the same pass). Not covered by shader text and therefore still "by construction": the fixed-function GL rules
+ * (rasterisation, depth test, blending order -- listed in DESIGN.md section 2), Eigen's LDLT / SE3 (orc_core.c) and the
+ * host-side orchestration of SurfelMapping.cpp (orc_slam.c).
  *
  * Conventions: images are [H][W][4] float32, row 0 = lowest beam; 4x4 matrices are column-major (Eigen/GL).
  */

@@ -212,7 +212,7 @@ __device__ __forceinline__ void emit_fragment(float tx, float ty, float z, size_
 struct TriSmall {
   int eA, eB, eC, sxA, sxB, sxC, syA, syB, syC;
   float farea, zA, zB, zC, txA, txB, txC, tyA, tyB, tyC;
-  uint32_t ties, valid;
+  uint32_t ties, valid, swapped;
 };
 __device__ __forceinline__ int edge32(int Px, int Py, int Qx, int Qy) {  // edge_fn(P, Q, X0, Y0), P and Q relative to (X0, Y0)
   return (Qx - Px) * (0 - Py) - (Qy - Py) * (0 - Px);
@@ -224,6 +224,7 @@ __device__ __forceinline__ bool tie32(int Px, int Py, int Qx, int Qy) {
 __device__ __forceinline__ TriSmall tri_small(const RVert& a, const RVert& b0, const RVert& c0, long long X0, long long Y0) {
   TriSmall t;
   t.valid = 0;
+  t.swapped = 0;
   int Ax = (int)(a.X - X0), Ay = (int)(a.Y - Y0);
   int Bx = (int)(b0.X - X0), By = (int)(b0.Y - Y0);
   int Cx = (int)(c0.X - X0), Cy = (int)(c0.Y - Y0);
@@ -237,6 +238,7 @@ __device__ __forceinline__ TriSmall tri_small(const RVert& a, const RVert& b0, c
     tf = txB; txB = txC; txC = tf;
     tf = tyB; tyB = tyC; tyC = tf;
     area = -area;
+    t.swapped = 1;
   }
   t.farea = (float)area;
   t.eA = edge32(Bx, By, Cx, Cy);
@@ -292,21 +294,71 @@ __device__ __forceinline__ void raster_big(const KParams& kp, const Cand& c, con
   }
 }
 
+// ---- the quad records of a block, structure-of-arrays in shared memory (lanes read different quads) ----
+struct QuadStore {
+  int e[2][3][kRenderThreads];   // per triangle: edge functions at the first pixel centre of the quad's box
+  int sx[2][3][kRenderThreads];  // per-pixel steps in x
+  int sy[2][3][kRenderThreads];  // per-pixel steps in y
+  float farea[2][kRenderThreads];
+  float z[4][kRenderThreads];    // window depth of the four corners
+  uint32_t box[kRenderThreads];   // i0 | j0 << 16
+  uint32_t meta[kRenderThreads];  // ni | nj << 8 | per triangle (ties 3 bits, swapped 1 bit, valid 1 bit) << 16 / << 21 | flags << 26
+  uint32_t k[kRenderThreads];
+  int prefix[kRenderThreads + 1];  // exclusive prefix of the box pixel counts (0 for large / empty quads)
+};
+
+__device__ __forceinline__ void quad_store_tri(QuadStore& Q, int slot, int tri, const TriSmall& t) {
+  Q.e[tri][0][slot] = t.eA; Q.e[tri][1][slot] = t.eB; Q.e[tri][2][slot] = t.eC;
+  Q.sx[tri][0][slot] = t.sxA; Q.sx[tri][1][slot] = t.sxB; Q.sx[tri][2][slot] = t.sxC;
+  Q.sy[tri][0][slot] = t.syA; Q.sy[tri][1][slot] = t.syB; Q.sy[tri][2][slot] = t.syC;
+  Q.farea[tri][slot] = t.farea;
+}
+
+// one box pixel of one small quad, both triangles (a folded quad may cover a pixel twice: GL draws both fragments)
+__device__ __forceinline__ void quad_pixel(const QuadStore& Q, int slot, uint32_t meta, int di, int dj, size_t pix, uint32_t k,
+                                           uint32_t flags, const RenderTargets& rt) {
+#pragma unroll
+  for (int tri = 0; tri < 2; ++tri) {
+    const uint32_t m = (meta >> (16 + 5 * tri)) & 31u;  // ties (3) | swapped (1) | valid (1)
+    if (!(m & 16u)) continue;
+    const int wA = Q.e[tri][0][slot] + di * Q.sx[tri][0][slot] + dj * Q.sy[tri][0][slot];
+    const int wB = Q.e[tri][1][slot] + di * Q.sx[tri][1][slot] + dj * Q.sy[tri][1][slot];
+    const int wC = Q.e[tri][2][slot] + di * Q.sx[tri][2][slot] + dj * Q.sy[tri][2][slot];
+    const bool in = (wA > 0 || (wA == 0 && (m & 1u))) && (wB > 0 || (wB == 0 && (m & 2u))) && (wC > 0 || (wC == 0 && (m & 4u)));
+    if (!in) continue;
+    // corners of this triangle: (tri, tri+1, tri+2), B and C exchanged if the orientation fix swapped them
+    const int cA = tri, cB = (m & 8u) ? tri + 2 : tri + 1, cC = (m & 8u) ? tri + 1 : tri + 2;
+    const float farea = Q.farea[tri][slot];
+    const float fB = (float)wB / farea, fC = (float)wC / farea;
+    const float fA = (1.0f - fB) - fC;
+    const float txA = (cA & 1) ? 1.0f : -1.0f, txB = (cB & 1) ? 1.0f : -1.0f, txC = (cC & 1) ? 1.0f : -1.0f;
+    const float tyA = (cA & 2) ? 1.0f : -1.0f, tyB = (cB & 2) ? 1.0f : -1.0f, tyC = (cC & 2) ? 1.0f : -1.0f;
+    const float tx = (fA * txA + fB * txB) + fC * txC;
+    const float ty = (fA * tyA + fB * tyB) + fC * tyC;
+    const float z = (fA * Q.z[cA][slot] + fB * Q.z[cB][slot]) + fC * Q.z[cC][slot];
+    emit_fragment(tx, ty, z, pix, k, flags, rt);
+  }
+}
+
 // render_surfels.vert:42-54 + .geom:76-122 + rasterisation + depth test for every surfel of the map.
 //  stage A/B (one thread per surfel): confidence / age-class tests on two lanes, then transform, visibility and the
 //    projection of the centre -- about half of the map drops out here;
 //  compaction: the survivors are packed densely through shared memory, so that
-//  stage C (corner projections + triangle set-up, the expensive part) and the rasterisation run on full warps.
-//  A surfel covers about the pixel it was created from, so almost every quad is small: those are rasterised by their own
-//  lane with int32 edge functions held in registers; the rare large ones are queued and rasterised by whole warps.
-//  (Round 1 kept every triangle in shared memory and balanced single pixels over the warp: 15 of 32 lanes active, 51 %
-//  issue utilisation at 25 % occupancy -- profiles/r01_ncu_full_summary.csv.)
+//  stage C (corner projections + triangle set-up) runs on full warps and leaves one lean record per quad in shared memory;
+//  rasterisation: the box pixels of ALL quads of the block form one flattened list that the 256 threads share evenly
+//    (contiguous chunks: one binary search per thread, then a walk) -- quads differ by an order of magnitude in size
+//    (a disc is ~6 x 2.5 pixels at 64 x 2048 but dozens of pixels wide from close by), and per-fragment work is a chain
+//    of dependent L2 round trips, so every lane of every warp has to stay busy. Edge functions are int32, exact because a
+//    "small" quad (box <= 12 x 5 pixels, vertices within 64 pixels) keeps every product below 2^31; the rare larger
+//    quads are rasterised by whole warps with int64 edge functions.
+//  (Round 1 stored int64 set-ups of every triangle per warp and ran stage C on half-empty warps: 15 of 32 lanes active.)
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kRenderThreads, kMinBlocks) k_render_scatter(KParams kp, SurfelPlanes s, const uint32_t* __restrict__ n_dev,
-                                                                      const float* __restrict__ Mtab, float conf_thr, int t_thr,
-                                                                      int emit_old, int emit_new, int lequal, RenderTargets rt) {
+                                                                               const float* __restrict__ Mtab, float conf_thr, int t_thr,
+                                                                               int emit_old, int emit_new, int lequal, RenderTargets rt) {
+  __shared__ QuadStore Q;
   __shared__ float c_f[8][kRenderThreads];
-  __shared__ uint32_t c_k[kRenderThreads], c_flags[kRenderThreads];
+  __shared__ uint32_t c_flags[kRenderThreads];
   __shared__ int s_warp_cnt[kRenderThreads / 32];
   __shared__ int s_nbig;
   __shared__ uint16_t s_big[kRenderThreads];
@@ -356,15 +408,15 @@ __global__ void __launch_bounds__(kRenderThreads, kMinBlocks) k_render_scatter(K
     const int slot = base + __popc(ballot & ((1u << lane) - 1u));
     c_f[0][slot] = c.px; c_f[1][slot] = c.py; c_f[2][slot] = c.pz; c_f[3][slot] = c.nx;
     c_f[4][slot] = c.ny; c_f[5][slot] = c.nz; c_f[6][slot] = c.r; c_f[7][slot] = c.cx;
-    c_k[slot] = k;
+    Q.k[slot] = k;
     c_flags[slot] = (is_old ? 1u : 0u) | (is_new ? 2u : 0u) | (lequal ? 4u : 0u);
   }
   __syncthreads();
-  // ---- stage C + small-quad rasterisation on dense lanes ----
+  // ---- stage C on dense lanes: one quad record per survivor ----
+  int npix = 0;
   if (tid < total) {
     c.px = c_f[0][tid]; c.py = c_f[1][tid]; c.pz = c_f[2][tid]; c.nx = c_f[3][tid];
     c.ny = c_f[4][tid]; c.nz = c_f[5][tid]; c.r = c_f[6][tid]; c.cx = c_f[7][tid];
-    c.k = c_k[tid]; c.flags = c_flags[tid];
     RVert q[4];
     quad_corners(kp, c, q);
     // pixel bounding box of the quad (union of the boxes of its two triangles), clamped to the image
@@ -387,18 +439,78 @@ __global__ void __launch_bounds__(kRenderThreads, kMinBlocks) k_render_scatter(K
       }
       if (small) {
         const TriSmall t0 = tri_small(q[0], q[1], q[2], X0, Y0), t1 = tri_small(q[1], q[2], q[3], X0, Y0);
-        for (int dj = 0; dj <= nj; ++dj)
-          for (int di = 0; di <= ni; ++di) {
-            const size_t pix = (size_t)((int)j0 + dj) * kp.Wm + (size_t)((int)i0 + di);
-            if (t0.valid) tri_small_pixel(t0, di, dj, pix, c.k, c.flags, rt);
-            if (t1.valid) tri_small_pixel(t1, di, dj, pix, c.k, c.flags, rt);
-          }
+        const uint32_t m0 = t0.valid ? (t0.ties | (t0.swapped ? 8u : 0u) | 16u) : 0u;
+        const uint32_t m1 = t1.valid ? (t1.ties | (t1.swapped ? 8u : 0u) | 16u) : 0u;
+        if (m0 | m1) {
+          if (t0.valid) quad_store_tri(Q, tid, 0, t0);
+          if (t1.valid) quad_store_tri(Q, tid, 1, t1);
+          Q.z[0][tid] = q[0].z; Q.z[1][tid] = q[1].z; Q.z[2][tid] = q[2].z; Q.z[3][tid] = q[3].z;
+          Q.box[tid] = (uint32_t)i0 | ((uint32_t)j0 << 16);
+          Q.meta[tid] = (uint32_t)ni | ((uint32_t)nj << 8) | (m0 << 16) | (m1 << 21) | (c_flags[tid] << 26);
+          npix = (ni + 1) * (nj + 1);
+        }
       } else {
         s_big[atomicAdd(&s_nbig, 1)] = (uint16_t)tid;
       }
     }
   }
+  // ---- exclusive prefix of the pixel counts over the 256 slots ----
+  int incl = npix;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  __syncthreads();  // everybody is done with s_warp_cnt (read above) before it is reused
+  if (lane == 31) s_warp_cnt[warp] = incl;
   __syncthreads();
+  int wbase = 0, T = 0;
+#pragma unroll
+  for (int w = 0; w < kRenderThreads / 32; ++w) {
+    const int cnt = s_warp_cnt[w];
+    if (w < warp) wbase += cnt;
+    T += cnt;
+  }
+  Q.prefix[tid + 1] = wbase + incl;
+  if (tid == 0) Q.prefix[0] = 0;
+  __syncthreads();
+  // ---- balanced rasterisation: thread t owns the flattened box pixels [t*ch, (t+1)*ch) ----
+  if (T > 0) {
+    const int ch = (T + kRenderThreads - 1) / kRenderThreads;
+    int item = tid * ch;
+    const int end = min(item + ch, T);
+    if (item < end) {
+      int lo = 0, hi = kRenderThreads;  // largest slot with prefix[slot] <= item
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (Q.prefix[mid] <= item) lo = mid; else hi = mid;
+      }
+      int slot = lo;
+      while (item < end) {
+        const int first = Q.prefix[slot], cnt = Q.prefix[slot + 1] - first;
+        if (cnt == 0) {
+          ++slot;
+          continue;
+        }
+        const uint32_t meta = Q.meta[slot], box = Q.box[slot], kk = Q.k[slot];
+        const int wd = (int)(meta & 255u) + 1;
+        const int i0 = (int)(box & 0xffffu), j0 = (int)(box >> 16);
+        const uint32_t flags = meta >> 26;
+        int local = item - first;
+        const int n_here = min(end - item, cnt - local);
+        int dj = local / wd, di = local - dj * wd;
+        for (int qn = 0; qn < n_here; ++qn) {
+          quad_pixel(Q, slot, meta, di, dj, (size_t)(j0 + dj) * kp.Wm + (size_t)(i0 + di), kk, flags, rt);
+          if (++di == wd) {
+            di = 0;
+            ++dj;
+          }
+        }
+        item += n_here;
+        ++slot;
+      }
+    }
+  }
   // ---- large quads: one warp each ----
   const int nbig = s_nbig;
   for (int b = warp; b < nbig; b += kRenderThreads / 32) {
@@ -406,7 +518,7 @@ __global__ void __launch_bounds__(kRenderThreads, kMinBlocks) k_render_scatter(K
     Cand cb;
     cb.px = c_f[0][slot]; cb.py = c_f[1][slot]; cb.pz = c_f[2][slot]; cb.nx = c_f[3][slot];
     cb.ny = c_f[4][slot]; cb.nz = c_f[5][slot]; cb.r = c_f[6][slot]; cb.cx = c_f[7][slot];
-    cb.k = c_k[slot]; cb.flags = c_flags[slot];
+    cb.k = Q.k[slot]; cb.flags = c_flags[slot];
     raster_big(kp, cb, rt, lane);
   }
 }
@@ -423,10 +535,10 @@ void launch_render_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, c
     static int occ = -1;
     if (occ < 0) {
       const char* e = getenv("SUMA_B200_RENDER_OCC");
-      occ = e ? atoi(e) : 3;
+      occ = e ? atoi(e) : 4;
     }
-    if (occ == 2)
-      k_render_scatter<2><<<grid, kRenderThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr, emit_old, emit_new, lequal, t);
+    if (occ == 5)
+      k_render_scatter<5><<<grid, kRenderThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr, emit_old, emit_new, lequal, t);
     else if (occ == 4)
       k_render_scatter<4><<<grid, kRenderThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr, emit_old, emit_new, lequal, t);
     else
@@ -652,48 +764,36 @@ __device__ __forceinline__ uint32_t block_rank(bool kept, uint32_t& block_count)
   return before + __popc(m & ((1u << lane) - 1u));
 }
 
-// exclusive prefix of `count` over the blocks with a smaller virtual index (warp 0 walks back 32 descriptors at a time)
+// Exclusive prefix of `count` over the blocks with a smaller virtual index. Every block publishes its own count FIRST and
+// then sums the published counts of ALL its predecessors -- 256 descriptors per round with 8 loads in flight per lane.
+// (Round 1 walked back 32 descriptors at a time and stopped at the first inclusive prefix: with all ~500 blocks of the
+// generation pass resident and publishing at about the same moment that is a chain of ~16 dependent L2 round trips for
+// the last blocks: 16 us for a pass that touches 11 MB.) No circular wait: a predecessor holds a smaller ticket, so it is
+// running or finished, and it publishes before it waits for anything.
 __device__ __forceinline__ uint32_t lookback_exclusive(const Lookback& lb, uint32_t vb, uint32_t count) {
   __shared__ uint32_t s_excl;
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
-    if (vb == 0) {
-      if (lane == 0) {
-        s_excl = 0;
-        atomicExch(lb.desc + 0, lb_pack(lb.gen, 2u, count));
-      }
-    } else {
-      if (lane == 0) atomicExch(lb.desc + vb, lb_pack(lb.gen, 1u, count));
-      uint32_t sum = 0;
-      long long base = (long long)vb - 1;
-      for (;;) {
-        long long idx = base - lane;
-        uint32_t status = 2u, value = 0;  // virtual entries before block 0: prefix 0
-        if (idx >= 0) {
-          unsigned long long d;
-          for (;;) {
-            d = *(volatile unsigned long long*)(lb.desc + idx);
-            if ((uint32_t)(d >> 34) == lb.gen && ((d >> 32) & 3ull) != 0ull) break;
-            __nanosleep(200);  // polling from ~1000 resident blocks would otherwise eat a large share of L2 bandwidth
-          }
-          status = (uint32_t)((d >> 32) & 3ull);
-          value = (uint32_t)d;
-        }
-        unsigned pm = __ballot_sync(0xffffffffu, status == 2u);
-        int first = pm ? (__ffs(pm) - 1) : 32;  // closest inclusive prefix in this window
-        uint32_t contrib = (lane <= first) ? value : 0u;
+    if (lane == 0) atomicExch(lb.desc + vb, lb_pack(lb.gen, 1u, count));
+    uint32_t sum = 0;
+    for (uint32_t i0 = 0; i0 < vb; i0 += 256) {
+      unsigned long long d[8];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-        sum += contrib;
-        if (pm) break;
-        base -= 32;
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t idx = i0 + 32 * j + lane;
+        d[j] = idx < vb ? *(volatile unsigned long long*)(lb.desc + idx) : lb_pack(lb.gen, 1u, 0u);
       }
-      if (lane == 0) {
-        s_excl = sum;
-        __threadfence();
-        atomicExch(lb.desc + vb, lb_pack(lb.gen, 2u, sum + count));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t idx = i0 + 32 * j + lane;
+        while (!((uint32_t)(d[j] >> 34) == lb.gen && ((d[j] >> 32) & 3ull) != 0ull))
+          d[j] = *(volatile unsigned long long*)(lb.desc + idx);
+        sum += (uint32_t)d[j];
       }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_excl = sum;
   }
   __syncthreads();
   return s_excl;
