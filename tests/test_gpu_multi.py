@@ -23,7 +23,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q, two_gpus, fused, size, n_scans, iters):
+def _worker(rank, world, port, q, two_gpus, fused, size, n_scans, iters, jump=False):
     try:
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -41,11 +41,18 @@ def _worker(rank, world, port, q, two_gpus, fused, size, n_scans, iters):
             dist.init_process_group("gloo", rank=rank, world_size=world)
         pp = api.default_params(**sized(size), max_iterations=iters, stopping_threshold=0.0, delta=0.0)
         sc, _ = scans(size, n=n_scans)
+        if jump:  # a pose jump after scan 3: the frame-to-frame recovery minimisation runs striped as well
+            from semantic_suma_b200 import synth
+            scene = synth.Scene(width=size, height=64)
+            tr = synth.trajectory(n_scans + 1)
+            J = synth.translate(0.8, 0.3, 0) @ synth.rot_z(np.deg2rad(8.0))
+            sc = [scene.scan(f, tr[f] if f < 4 else tr[f] @ J) for f in range(n_scans)]
         solo = api.SurfelMapping(pp, device=dev)
         for s in sc:
             solo.processScan(*s)
         ref_pose = solo.getCurrentPose().copy()
         ref_n = solo.getMap().size()
+        assert not jump or solo.getStatistics()["track_loss"] >= 1
         solo.ctx.close()
         sl = api.SurfelMapping(pp, device=dev)
         r0, r1 = stripes.setup_comm(sl.ctx, dist, fused=fused)
@@ -62,12 +69,12 @@ def _worker(rank, world, port, q, two_gpus, fused, size, n_scans, iters):
         raise
 
 
-def _run_two_ranks(fused, two_gpus, size=900, n_scans=4, iters=8):
+def _run_two_ranks(fused, two_gpus, size=900, n_scans=4, iters=8, jump=False):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, two_gpus, fused, size, n_scans, iters)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, two_gpus, fused, size, n_scans, iters, jump)) for r in range(2)]
     for p in procs:
         p.start()
     try:
@@ -93,9 +100,9 @@ def test_two_rank_striped_icp_is_bit_identical():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("size,n_scans,iters", [(900, 4, 8), (2048, 6, 10)])
-def test_two_gpu_fused_peer_allreduce_is_bit_identical(size, n_scans, iters):
+@pytest.mark.parametrize("size,n_scans,iters,jump", [(900, 4, 8, False), (2048, 6, 10, False), (900, 7, 33, True)])
+def test_two_gpu_fused_peer_allreduce_is_bit_identical(size, n_scans, iters, jump):
     from semantic_suma_b200 import api
     if api.lib().sb_device_count() < 2:
         pytest.skip("the in-kernel peer exchange needs two GPUs")
-    _run_two_ranks(fused=True, two_gpus=True, size=size, n_scans=n_scans, iters=iters)
+    _run_two_ranks(fused=True, two_gpus=True, size=size, n_scans=n_scans, iters=iters, jump=jump)
