@@ -166,6 +166,41 @@ int sb_process_scan(sb_ctx* ctx, const float* pts4, const float* labels, const f
  * SurfelMapping.cpp:325-331): start the host-to-device copy of the NEXT scan on a separate copy stream; a following
  * sb_process_scan with the same host pointers / count (on_device = 0) uses the staged copy. At most two scans staged. */
 int sb_prefetch_scan(sb_ctx* ctx, const float* pts4, const float* labels, const float* probs, uint32_t n);
+/* ---- loop closure: SurfelMapping::checkLoopClosure, core/SurfelMapping.cpp:478-795 ("close-loops", default.xml:70-76) ----
+ * When enabled, sb_process_scan runs the reference's detection / verification between updatePose() and updateMap()
+ * (:196-200): render_inactive at a candidate pose, three Gauss-Newton runs against the old map frame, render_composed,
+ * residual comparison, verification over consecutive scans, and the chained "old" pose (currentPose_old_) that the next
+ * scan's composed rendering uses. The pose-graph OPTIMISATION (gtsam, core/Posegraph.cpp) stays with the host application:
+ * the library records what the reference feeds into gtsam (sb_get_loop_edges: odometry + loop edges; initial poses =
+ * the odometry chain) and raises optimisation_requested; optimised poses come back through sb_map_update_poses /
+ * sb_set_current_pose (integrateLoopClosures, :212-258). */
+typedef struct sb_loop_params {
+  float search_distance;         /* loop-search-distance (default.xml: 50) */
+  float min_trajectory_distance; /* loop-min-trajectory-distance (SurfelMapping.h:224: 200) */
+  int32_t min_verifications;     /* loop-min-verifications (5) */
+  float residual_threshold;      /* loop-residual-threshold (1.15) */
+  float outlier_threshold;       /* loop-outlier-threshold (1.1) */
+  float valid_threshold;         /* loop-valid-threshold (0.95) */
+} sb_loop_params;
+typedef struct sb_loop_info {
+  uint32_t enabled, loop_count, time_without_loop_closure, candidates_tested, loop_edges_added, unverified;
+  uint32_t already_verified, found_candidate, use_candidate, optimisation_requested;
+  int32_t last_added_candidate;
+  uint32_t n_edges, n_poses;
+  float valid_ratio, outlier_ratio, rel_error; /* statistics_["loop_valid_ratio" / "loop_outlier_ratio" / "loop_relative_error_all"] */
+  double residual_old, residual_new;
+  double current_pose_old[16];                 /* currentPose_old_ after the check */
+} sb_loop_info;
+typedef struct sb_loop_edge {
+  int32_t from, to;
+  double rel_pose[16];
+} sb_loop_edge;
+void sb_default_loop_params(sb_loop_params* p);
+int sb_set_loop_closure(sb_ctx* ctx, int enabled, const sb_loop_params* p /* NULL = defaults */);
+int sb_get_loop_info(sb_ctx* ctx, sb_loop_info* out);
+int sb_get_loop_edges(sb_ctx* ctx, sb_loop_edge* dst, uint32_t cap, uint32_t* n_total);
+int sb_set_current_pose(sb_ctx* ctx, const double pose[16]); /* SurfelMapping::setCurrentPose, core/SurfelMapping.h:66 */
+
 int sb_get_pose(sb_ctx* ctx, double pose[16]);     /* getCurrentPose */
 int sb_get_last_pose(sb_ctx* ctx, double pose[16]); /* getLastPose, core/SurfelMapping.h:63 (pose before the last processScan) */
 int sb_timestamp(sb_ctx* ctx, uint32_t* t);        /* timestamp() */

@@ -470,10 +470,34 @@ class SurfelMapping {
   }
   Frame::Ptr getOldSurfelMap() { return map_->oldMapFrame(); }  // SurfelMapping.h:73
   Frame::Ptr getNewSurfelMap() { return map_->newMapFrame(); }  // SurfelMapping.h:74
-  /** loop closure and the pose graph stay with the caller: this object never finds or uses a
-   * candidate, and the "optimized" poses are the odometry poses */
-  bool foundLoopClosureCandidate() const { return false; }
-  bool useLoopClosureCandidate() const { return false; }
+  /** "close-loops" (config/default.xml:71): loop-closure detection and verification, SurfelMapping::checkLoopClosure
+   * (SurfelMapping.cpp:527-795), run by the library between updatePose() and updateMap(). The pose-graph optimisation
+   * (gtsam, core/Posegraph.cpp) stays with the caller: getLoopEdges() returns the odometry and
+   * loop edges the reference feeds into gtsam, optimisationRequested() mirrors the reference's trigger (:658-663); feed
+   * the optimised poses back with SurfelMap::updatePoses() + setCurrentPose() (integrateLoopClosures, :212-258). */
+  void enableLoopClosure(bool on, const sb_loop_params* lp = nullptr) {
+    check(sb_set_loop_closure(ctx_->get(), on ? 1 : 0, lp), ctx_->get(), "SurfelMapping::enableLoopClosure");
+  }
+  sb_loop_info getLoopInfo() const {
+    sb_loop_info li;
+    sb_get_loop_info(ctx_->get(), &li);
+    return li;
+  }
+  std::vector<sb_loop_edge> getLoopEdges() const {
+    uint32_t n = 0;
+    sb_get_loop_edges(ctx_->get(), nullptr, 0, &n);
+    std::vector<sb_loop_edge> e(n);
+    if (n) sb_get_loop_edges(ctx_->get(), e.data(), n, &n);
+    return e;
+  }
+  bool foundLoopClosureCandidate() const { return getLoopInfo().found_candidate != 0; }  // SurfelMapping.h:88
+  bool useLoopClosureCandidate() const { return getLoopInfo().use_candidate != 0; }      // SurfelMapping.h:89
+  bool optimisationRequested() const { return getLoopInfo().optimisation_requested != 0; }
+  /** SurfelMapping::setCurrentPose, SurfelMapping.h:66 */
+  void setCurrentPose(const Matrix4d& pose) {
+    check(sb_set_current_pose(ctx_->get(), pose.m), ctx_->get(), "SurfelMapping::setCurrentPose");
+  }
+  /** without a pose-graph optimiser attached the "optimized" poses are the odometry poses */
   std::vector<Matrix4d> getOptimizedPoses() const { return trajectory_; }
   uint32_t timestamp() const {
     uint32_t t = 0;

@@ -14,7 +14,8 @@ _LIB = os.path.join(_HERE, "build", "liborc.so")
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h")) or f == "Makefile"]
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h", ".cpp")) or f == "Makefile"]
+    srcs.append(os.path.join(_HERE, "..", "include", "suma_b200_loop.hpp"))
     stale = force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs)
     if stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
@@ -82,6 +83,8 @@ def lib():
         L.orc_icp_minimize.restype = C.c_int
         L.orc_gn_step.restype = C.c_int
         L.orc_set_threads.restype = C.c_int; L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_loop_attach.restype = C.c_void_p
+        L.orc_loop_edges.restype = C.c_uint32
     return _lib
 
 
@@ -284,9 +287,36 @@ class Slam:
         self.p = p
         self.h = C.c_void_p(lib().orc_slam_create(C.byref(p)))
         self.map = Map(p, handle=lib().orc_slam_map(self.h))
+        self.loop = None
+
+    def enable_loop_closure(self, search_distance=50.0, min_trajectory_distance=200.0, min_verifications=5,
+                            residual_threshold=1.15, outlier_threshold=1.1, valid_threshold=0.95):
+        """SurfelMapping::checkLoopClosure between updatePose() and updateMap() (oracle/orc_loop.cpp)"""
+        self.loop = C.c_void_p(lib().orc_loop_attach(self.h, C.c_float(search_distance), C.c_float(min_trajectory_distance),
+                                                     C.c_int32(min_verifications), C.c_float(residual_threshold),
+                                                     C.c_float(outlier_threshold), C.c_float(valid_threshold)))
+
+    def loop_info(self):
+        info = np.zeros(12, np.int64); ratios = np.zeros(5, np.float64); pose = np.zeros(16, np.float64)
+        lib().orc_loop_info(self.loop, _p(info, C.c_int64), _p(ratios, C.c_double), _p(pose, C.c_double))
+        keys = ("loop_count", "time_without_loop_closure", "candidates_tested", "loop_edges_added", "unverified",
+                "already_verified", "found_candidate", "use_candidate", "optimisation_requested", "last_added_candidate",
+                "n_edges", "n_poses")
+        d = dict(zip(keys, (int(x) for x in info)))
+        d.update(valid_ratio=np.float32(ratios[0]), outlier_ratio=np.float32(ratios[1]), rel_error=np.float32(ratios[2]),
+                 residual_old=ratios[3], residual_new=ratios[4], current_pose_old=from_colmajor(pose))
+        return d
+
+    def loop_edges(self):
+        n = int(self.loop_info()["n_edges"])
+        ft = np.zeros((max(n, 1), 2), np.int32); rel = np.zeros((max(n, 1), 16), np.float64)
+        lib().orc_loop_edges(self.loop, _p(ft, C.c_int32), _p(rel, C.c_double), C.c_uint32(n))
+        return [(int(ft[i, 0]), int(ft[i, 1]), from_colmajor(rel[i])) for i in range(n)]
 
     def __del__(self):
         if self.h:
+            if getattr(self, "loop", None):
+                lib().orc_loop_detach(self.loop); self.loop = None
             lib().orc_slam_destroy(self.h); self.h = None
 
     def process_scan(self, pts, labels=None, probs=None):

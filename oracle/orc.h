@@ -160,6 +160,13 @@ orc_map* orc_slam_map(orc_slam* s);
 void orc_slam_get_stats(const orc_slam* s, double stats[16]);
 void orc_slam_get_frame(const orc_slam* s, int which /*0 current data, 1 last model frame*/, float* v, float* n,
                         float* sem);
+/* hooks for the loop-closure twin (orc_loop.cpp): a callback between updatePose() and updateMap() and the members it uses */
+typedef void (*orc_slam_hook)(orc_slam* s, void* user);
+void orc_slam_set_hook(orc_slam* s, orc_slam_hook hook, void* user);
+double* orc_slam_pose_member(orc_slam* s, int which /*0 current 1 current_old 2 current_new 3 last_old 5 increment 6 lastIncrement*/);
+void orc_slam_current_frame(orc_slam* s, float** v, float** n, float** sem);
+float orc_slam_conf_threshold(const orc_slam* s);
+const orc_params* orc_slam_params(const orc_slam* s);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,9 @@ struct orc_slam {
   float *tmp_v, *tmp_n, *tmp_s; /* newMapFrame download */
   uint32_t timestamp;
   double currentPose[16], lastPose[16], currentPose_old[16], currentPose_new[16], lastIncrement[16];
+  double lastPose_old[16], increment[16], prevIncrement[16]; /* lastPose_old_ (:454), this scan's increment, lastIncrement_ before it */
+  orc_slam_hook hook;        /* called between updatePose() and updateMap(): where checkLoopClosure() runs (:196-200) */
+  void* hook_user;
   float confidence_threshold, log_unstable;
   double stats[16];
   uint32_t trackLoss;
@@ -39,7 +42,7 @@ orc_slam* orc_slam_create(const orc_params* p) {
   sframe_alloc(&s->cur_model, Pm); sframe_alloc(&s->last_model, Pm);
   s->tmp_v = (float*)calloc(Pm * 4, 4); s->tmp_n = (float*)calloc(Pm * 4, 4); s->tmp_s = (float*)calloc(Pm * 4, 4);
   ident_d(s->currentPose); ident_d(s->lastPose); ident_d(s->currentPose_old); ident_d(s->currentPose_new);
-  ident_d(s->lastIncrement);
+  ident_d(s->lastIncrement); ident_d(s->lastPose_old); ident_d(s->increment); ident_d(s->prevIncrement);
   s->confidence_threshold = p->confidence_threshold;        /* SurfelMapping.cpp:111-113 */
   { float pu = 0.1f; s->log_unstable = logf(pu / (1.0f - pu)); } /* :108-109 */
   return s;
@@ -111,6 +114,9 @@ static void update_pose(orc_slam* s) {
   double np[16];
   orc_mat4_mul_d(s->currentPose, increment, np); /* :452 */
   memcpy(s->currentPose, np, sizeof(np));
+  memcpy(s->lastPose_old, s->currentPose_old, sizeof(np)); /* :454 */
+  memcpy(s->prevIncrement, s->lastIncrement, sizeof(np));
+  memcpy(s->increment, increment, sizeof(np));
   memcpy(s->currentPose_old, np, sizeof(np));
   memcpy(s->currentPose_new, np, sizeof(np));
   memcpy(s->lastIncrement, increment, sizeof(increment)); /* :473 */
@@ -132,7 +138,10 @@ void orc_slam_process_scan(orc_slam* s, const float* pts4, const float* labels, 
   orc_map_render(s->map, Pold, Pnew, ct, s->last_model.v, s->last_model.n, s->last_model.s);
   s->stats[8] = now_s() - t0;
   t0 = now_s();
-  if (s->timestamp > 0) update_pose(s);
+  if (s->timestamp > 0) {
+    update_pose(s);
+    if (s->hook) s->hook(s, s->hook_user); /* checkLoopClosure(), :198 */
+  }
   s->stats[9] = now_s() - t0;
   /* updateMap(), :797-804 */
   t0 = now_s();
@@ -160,3 +169,21 @@ void orc_slam_get_frame(const orc_slam* s, int which, float* v, float* n, float*
   if (n) memcpy(n, f->n, P * 16);
   if (sem) memcpy(sem, f->s, P * 16);
 }
+
+/* ---- hooks for the loop-closure twin (oracle/orc_loop.cpp) ---- */
+void orc_slam_set_hook(orc_slam* s, orc_slam_hook hook, void* user) { s->hook = hook; s->hook_user = user; }
+double* orc_slam_pose_member(orc_slam* s, int which) {
+  switch (which) {
+    case 0: return s->currentPose;
+    case 1: return s->currentPose_old;
+    case 2: return s->currentPose_new;
+    case 3: return s->lastPose_old;
+    case 4: return s->prevIncrement;  /* lastIncrement_ as checkLoopClosure reads it?  NO: see orc_loop.cpp -- it reads the NEW lastIncrement_ */
+    case 5: return s->increment;
+    case 6: return s->lastIncrement;
+    default: return NULL;
+  }
+}
+void orc_slam_current_frame(orc_slam* s, float** v, float** n, float** sem) { *v = s->cur.v; *n = s->cur.n; *sem = s->cur.s; }
+float orc_slam_conf_threshold(const orc_slam* s) { return conf_threshold(s); }
+const orc_params* orc_slam_params(const orc_slam* s) { return &s->p; }

@@ -21,6 +21,24 @@ class SumaError(RuntimeError):
     pass
 
 
+class LoopParams(C.Structure):  # sb_loop_params
+    _fields_ = [("search_distance", C.c_float), ("min_trajectory_distance", C.c_float), ("min_verifications", C.c_int32),
+                ("residual_threshold", C.c_float), ("outlier_threshold", C.c_float), ("valid_threshold", C.c_float)]
+
+
+class LoopInfo(C.Structure):  # sb_loop_info
+    _fields_ = [(n, C.c_uint32) for n in ("enabled", "loop_count", "time_without_loop_closure", "candidates_tested",
+                                          "loop_edges_added", "unverified", "already_verified", "found_candidate",
+                                          "use_candidate", "optimisation_requested")] + \
+               [("last_added_candidate", C.c_int32), ("n_edges", C.c_uint32), ("n_poses", C.c_uint32),
+                ("valid_ratio", C.c_float), ("outlier_ratio", C.c_float), ("rel_error", C.c_float),
+                ("residual_old", C.c_double), ("residual_new", C.c_double), ("current_pose_old", C.c_double * 16)]
+
+
+class LoopEdge(C.Structure):  # sb_loop_edge
+    _fields_ = [("from_", C.c_int32), ("to", C.c_int32), ("rel_pose", C.c_double * 16)]
+
+
 class Params(C.Structure):
     _fields_ = [
         ("data_width", C.c_int32), ("data_height", C.c_int32),
@@ -116,6 +134,8 @@ def lib(build_if_missing=True):
         "sb_map_update_debug": [vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32)],
         "sb_map_submap_origin": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(u32)],
         "sb_process_scan": [vp, vp, vp, vp, u32, C.c_int], "sb_prefetch_scan": [vp, vp, vp, vp, u32],
+        "sb_set_loop_closure": [vp, C.c_int, vp], "sb_get_loop_info": [vp, vp], "sb_get_loop_edges": [vp, vp, u32, C.POINTER(u32)],
+        "sb_set_current_pose": [vp, pd], "sb_default_loop_params": [vp],
         "sb_get_pose": [vp, pd], "sb_get_last_pose": [vp, pd], "sb_timestamp": [vp, C.POINTER(u32)], "sb_slam_frame": [vp, C.c_int, pv],
         "sb_get_statistics": [vp, pd],
         "sb_comm_export": [vp, vp], "sb_comm_init": [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int],
@@ -149,7 +169,8 @@ EXPORTED_SYMBOLS = [
     "sb_map_update_poses", "sb_map_size", "sb_map_timestamp", "sb_map_download", "sb_map_upload", "sb_map_set_pose",
     "sb_map_update_debug", "sb_map_submap_origin", "sb_process_scan", "sb_prefetch_scan", "sb_get_pose", "sb_get_last_pose", "sb_timestamp", "sb_slam_frame",
     "sb_get_statistics", "sb_comm_export", "sb_comm_init", "sb_comm_shutdown", "sb_comm_set_callback",
-    "sb_profile_enable",
+    "sb_profile_enable", "sb_default_loop_params", "sb_set_loop_closure", "sb_get_loop_info", "sb_get_loop_edges",
+    "sb_set_current_pose",
     "sb_profile_kernels", "sb_profile_name", "sb_profile_collect",
 ]
 
@@ -508,11 +529,44 @@ class SurfelMap:
 
 
 class SurfelMapping:
-    """core/SurfelMapping.h:33-109 (loop closure off)."""
+    """core/SurfelMapping.h:33-109. Loop-closure detection / verification (checkLoopClosure) is off unless
+    enableLoopClosure() is called ("close-loops" in the reference's parameters); the pose-graph optimisation stays with
+    the host application (gtsam is out of scope): see getLoopInfo() / getLoopEdges() / setCurrentPose()."""
 
     def __init__(self, params, device=0):
         self.ctx = Context(params, device)
         self.map_ = SurfelMap(self.ctx)
+
+    def enableLoopClosure(self, enabled=True, **kw):
+        """kw: search_distance, min_trajectory_distance, min_verifications, residual_threshold, outlier_threshold,
+        valid_threshold (defaults: config/default.xml:70-76)"""
+        lp = LoopParams()
+        lib().sb_default_loop_params(C.byref(lp))
+        for k, v in kw.items():
+            if not hasattr(lp, k):
+                raise KeyError(k)
+            setattr(lp, k, v)
+        self.ctx.check(lib().sb_set_loop_closure(self.ctx.h, 1 if enabled else 0, C.byref(lp)), "set_loop_closure")
+
+    def getLoopInfo(self):
+        li = LoopInfo()
+        self.ctx.check(lib().sb_get_loop_info(self.ctx.h, C.byref(li)), "get_loop_info")
+        d = {n: getattr(li, n) for n, _ in LoopInfo._fields_ if n != "current_pose_old"}
+        d["valid_ratio"] = np.float32(d["valid_ratio"]); d["outlier_ratio"] = np.float32(d["outlier_ratio"])
+        d["rel_error"] = np.float32(d["rel_error"])
+        d["current_pose_old"] = from_colmajor(np.array(li.current_pose_old))
+        return d
+
+    def getLoopEdges(self):
+        n = C.c_uint32(0)
+        self.ctx.check(lib().sb_get_loop_edges(self.ctx.h, None, 0, C.byref(n)), "get_loop_edges")
+        arr = (LoopEdge * max(n.value, 1))()
+        self.ctx.check(lib().sb_get_loop_edges(self.ctx.h, arr, n.value, C.byref(n)), "get_loop_edges")
+        return [(arr[i].from_, arr[i].to, from_colmajor(np.array(arr[i].rel_pose))) for i in range(n.value)]
+
+    def setCurrentPose(self, pose):
+        """SurfelMapping::setCurrentPose (core/SurfelMapping.h:66)"""
+        self.ctx.check(lib().sb_set_current_pose(self.ctx.h, _dp(colmajor(pose, np.float64))), "set_current_pose")
 
     def processScan(self, points, labels=None, probs=None, on_device=False):
         if on_device:  # raw device pointers (int) + count: (ptr_pts, ptr_labels, ptr_probs, n)

@@ -14,6 +14,7 @@
 
 #include "sb_gn.cuh"
 #include "sb_internal.cuh"
+#include "../../include/suma_b200_loop.hpp"
 
 using namespace sb;
 
@@ -72,6 +73,10 @@ struct sb_ctx {
   int icp_blocks = 296;
   int icp_coop_blocks = 0;  // > 0: the persistent cooperative Gauss-Newton kernel is available
   unsigned int epoch_base = 0;  // epoch words of the persistent GN kernel: each launch owns a fresh range of values
+  // loop closure (SurfelMapping::checkLoopClosure; include/suma_b200_loop.hpp): off unless sb_set_loop_closure enables it
+  bool close_loops = false;
+  suma_b200::loop::State loop;
+  double lastPose_old[16];
 
   // ---- map
   SurfelPlanes A{}, T{}, G{}, X{};  // current surfels, updated (same index), generated (per pixel), extraction buffer
@@ -903,6 +908,29 @@ int upload_scan(sb_ctx* c, const float* pts4, const float* labels, const float* 
   return SB_OK;
 }
 
+// SurfelMap::render_composed, SurfelMap.cpp:1116-1165
+int render_composed_internal(sb_ctx* c, const float* pose_old, const float* pose_new, float conf_thr) {
+  c->rkey_valid = false;
+  const KParams& kp = c->kp;
+  Launch L = L_(c);
+  size_t Pm = (size_t)kp.Wm * kp.Hm;
+  float inv_old[16], inv_new[16];
+  sbg::rigid_inverse_f(pose_old, inv_old);
+  sbg::rigid_inverse_f(pose_new, inv_new);
+  uint32_t np = pose_table_count(c);
+  launch_pose_products(L, mat4_from(inv_old), nullptr, c->poses, c->Mtab_old, np);
+  launch_pose_products(L, mat4_from(inv_new), nullptr, c->poses, c->Mtab_new, np);
+  RenderTargets t{nullptr, nullptr, c->key_comp};
+  int thr = t_threshold(c);
+  // GL_LEQUAL (SurfelMap.cpp:1126), old then new without clearing (:1146-1152); COLOR2 not attached (Q4)
+  launch_render_scatter(L, kp, c->A, c->d_counts, n_grid(c), c->Mtab_old, conf_thr, thr, 1, 0, 1, t);
+  launch_render_scatter(L, kp, c->A, c->d_counts, n_grid(c), c->Mtab_new, conf_thr, thr, 0, 1, 1, t);
+  launch_render_resolve(L, kp, c->A, c->Mtab_old, c->Mtab_new, t, null_frame(), null_frame(), c->f_comp->d, null_frame(),
+                        null_frame(), 1, 1);
+  SB_CUDA(c, cudaGetLastError());
+  return SB_OK;
+}
+
 // SurfelMapping::updatePose, SurfelMapping.cpp:372-476 -- enqueue only. The increment, the track-loss decision, the
 // recovery minimisation and the pose chaining stay on the device: two cooperative launches (GN_MAIN, GN_POST) around the
 // rendering of the active map at the new pose. Returns with *tables_ready = true when GN_POST has also written the pose
@@ -1003,6 +1031,98 @@ int update_pose_enqueue(sb_ctx* c, bool* tables_ready) {
     }
   }
   launch_pose_finalize(L, c->gn2, c->pd, 1, c->poses, c->poses_inv, c->map_timestamp);
+  return SB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// loop closure: SurfelMapping::checkLoopClosure (SurfelMapping.cpp:527-795) over the CUDA operators; the control flow is
+// include/suma_b200_loop.hpp (shared with the oracle twin)
+// ---------------------------------------------------------------------------------------------------------
+struct CudaLoopBackend {
+  sb_ctx* c;
+  int err = 0;
+  float confidence_threshold() { return conf_threshold(c); }
+  void render_inactive(const float* pose, float ct) {
+    if (!err) err = render_single(c, pose, ct, 0);
+  }
+  void render_composed(const float* pose_old, const float* pose_new, float ct) {
+    if (!err) err = render_composed_internal(c, pose_old, pose_new, ct);
+  }
+  int minimize_old(const double* T0, double* pose_out, double* out48) {  // objective_->setData(currentFrame_, oldMapFrame())
+    int iters = 0;
+    if (!err)
+      err = icp_minimize_enqueue(c, c->cur, c->f_old, T0, c->p.max_iterations, c->p.stopping_threshold, c->p.delta,
+                                 c->p.icp_max_distance, c->p.icp_max_angle, c->cur_has_semantics);
+    if (!err) err = icp_minimize_fetch(c, pose_out, out48, &iters, nullptr, nullptr);
+    return iters;
+  }
+  void evaluate(int model, const double* pose, int iteration, double* out48) {
+    long long raw[32];
+    memset(raw, 0, sizeof(raw));
+    if (!err)
+      err = icp_jacobian_raw(c, c->cur, model == 0 ? c->f_old : c->f_comp, pose, iteration, c->p.icp_max_distance,
+                             c->p.icp_max_angle, 0, c->kp.H, c->cur_has_semantics, raw);
+    sbg::unpack48(raw, out48);
+  }
+};
+
+// host copy of the device-resident pose block after updatePose (shared by the end of every scan and the loop-closure step)
+void absorb_pose_block(sb_ctx* c, const PoseDev& pdh, const char* hp, bool had_icp) {
+  memcpy(c->lastPose, pdh.lastPose, sizeof(c->lastPose));
+  memcpy(c->currentPose, pdh.currentPose, sizeof(c->currentPose));
+  memcpy(c->lastPose_old, c->currentPose_old, sizeof(c->lastPose_old));  // lastPose_old_ = currentPose_old_   :454
+  memcpy(c->currentPose_old, pdh.currentPose, sizeof(c->currentPose));
+  memcpy(c->currentPose_new, pdh.currentPose, sizeof(c->currentPose));
+  memcpy(c->lastIncrement, pdh.lastIncrement, sizeof(c->lastIncrement));
+  c->trackLoss = (uint32_t)pdh.trackLoss;
+  if (had_icp) {
+    long long raw[32];
+    double r48[48];
+    memcpy(raw, hp + 4096, sizeof(raw));
+    sbg::unpack48(raw, r48);
+    c->stats[0] = pdh.icp_iterations;
+    c->stats[1] = r48[43];
+    c->stats[3] = r48[44];
+    c->stats[2] = (double)((uint32_t)r48[42] - (uint32_t)r48[44]);  // Frame2Model.cpp:222-226
+    c->stats[4] = r48[46];
+    c->stats[5] = (float)r48[45];
+    // result_new_, SurfelMapping.cpp:417-423
+    suma_b200::loop::OptResult& rn = c->loop.result_new;
+    rn.error = r48[43];
+    rn.outlier = (uint32_t)(float)r48[44];
+    rn.valid = (uint32_t)r48[42];
+    rn.inlier = rn.valid - rn.outlier;
+    rn.invalid = (uint32_t)(float)r48[46];
+    rn.residual = rn.error / (rn.inlier + rn.outlier);
+    rn.inlier_residual = (float)r48[45] / rn.inlier;
+  }
+  c->stats[6] = c->trackLoss;
+}
+
+// between updatePose() and updateMap() (SurfelMapping.cpp:196-200): needs the scan's poses on the host
+int loop_closure_step(sb_ctx* c) {
+  namespace lp = suma_b200::loop;
+  if (c->comm_on || c->comm_cb) return fail(c, SB_ERR_STATE, "loop closure is not available in row-striped multi-GPU mode");
+  char* hp = (char*)c->h_pinned;
+  SB_CUDA(c, cudaMemcpyAsync(hp, c->result_block, 8192 + 64, cudaMemcpyDeviceToHost, c->stream));
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  PoseDev pdh;
+  memcpy(&pdh, hp, sizeof(pdh));
+  if (pdh.gn_error) return fail(c, SB_ERR_STATE, "Gauss-Newton kernel timed out waiting for a block or a peer GPU");
+  absorb_pose_block(c, pdh, hp, true);
+  lp::Poses P;
+  memcpy(P.current.m, c->currentPose, 128);
+  memcpy(P.current_old.m, c->currentPose_old, 128);
+  memcpy(P.current_new.m, c->currentPose_new, 128);
+  memcpy(P.last_old.m, c->lastPose_old, 128);
+  memcpy(P.last_increment.m, c->lastIncrement, 128);
+  lp::M4 inc;
+  memcpy(inc.m, pdh.increment, 128);
+  c->loop.after_update_pose(c->timestamp, inc, P.current);
+  CudaLoopBackend be{c};
+  lp::check_loop_closure(c->loop, be, c->timestamp, P);
+  if (be.err) return be.err;
+  memcpy(c->currentPose_old, P.current_old.m, 128);
   return SB_OK;
 }
 
@@ -1228,25 +1348,7 @@ int sb_map_render_inactive(sb_ctx* c, const float pose[16], float conf_thr) {
 int sb_map_render_composed(sb_ctx* c, const float pose_old[16], const float pose_new[16], float conf_thr) {
   if (!c || !pose_old || !pose_new) return fail(c, SB_ERR_INVALID, "map_render_composed: null argument");
   cudaSetDevice(c->device);
-  c->rkey_valid = false;
-  const KParams& kp = c->kp;
-  Launch L = L_(c);
-  size_t Pm = (size_t)kp.Wm * kp.Hm;
-  float inv_old[16], inv_new[16];
-  sbg::rigid_inverse_f(pose_old, inv_old);
-  sbg::rigid_inverse_f(pose_new, inv_new);
-  uint32_t np = pose_table_count(c);
-  launch_pose_products(L, mat4_from(inv_old), nullptr, c->poses, c->Mtab_old, np);
-  launch_pose_products(L, mat4_from(inv_new), nullptr, c->poses, c->Mtab_new, np);
-  RenderTargets t{nullptr, nullptr, c->key_comp};
-  int thr = t_threshold(c);
-  // GL_LEQUAL (SurfelMap.cpp:1126), old then new without clearing (:1146-1152); COLOR2 not attached (Q4)
-  launch_render_scatter(L, kp, c->A, c->d_counts, n_grid(c), c->Mtab_old, conf_thr, thr, 1, 0, 1, t);
-  launch_render_scatter(L, kp, c->A, c->d_counts, n_grid(c), c->Mtab_new, conf_thr, thr, 0, 1, 1, t);
-  launch_render_resolve(L, kp, c->A, c->Mtab_old, c->Mtab_new, t, null_frame(), null_frame(), c->f_comp->d, null_frame(),
-                        null_frame(), 1, 1);
-  SB_CUDA(c, cudaGetLastError());
-  return SB_OK;
+  return render_composed_internal(c, pose_old, pose_new, conf_thr);
 }
 int sb_map_frame(sb_ctx* c, int which, sb_frame** out) {
   if (!c || !out || which < 0 || which > 2) return SB_ERR_INVALID;
@@ -1442,8 +1544,14 @@ int sb_process_scan(sb_ctx* c, const float* pts4, const float* labels, const flo
   if ((r = render_full(c, Pold, Pnew, ct, c->last_model))) return r;
   const bool had_icp = c->timestamp > 0;
   bool tables_ready = false;
+  bool loop_ran = false;
   if (had_icp) {
     if ((r = update_pose_enqueue(c, &tables_ready))) return r;
+    if (c->close_loops) {  // checkLoopClosure(), :196-200; its renders overwrite the product table of the map update
+      if ((r = loop_closure_step(c))) return r;
+      tables_ready = false;
+      loop_ran = true;
+    }
   } else {
     launch_pose_finalize(L, c->gn2, c->pd, 0, c->poses, c->poses_inv, c->map_timestamp);
   }
@@ -1462,25 +1570,7 @@ int sb_process_scan(sb_ctx* c, const float* pts4, const float* labels, const flo
   PoseDev pdh;
   memcpy(&pdh, hp, sizeof(pdh));
   if (pdh.gn_error) return fail(c, SB_ERR_STATE, "Gauss-Newton kernel timed out waiting for a block or a peer GPU");
-  memcpy(c->lastPose, pdh.lastPose, sizeof(c->lastPose));
-  memcpy(c->currentPose, pdh.currentPose, sizeof(c->currentPose));
-  memcpy(c->currentPose_old, pdh.currentPose, sizeof(c->currentPose));
-  memcpy(c->currentPose_new, pdh.currentPose, sizeof(c->currentPose));
-  memcpy(c->lastIncrement, pdh.lastIncrement, sizeof(c->lastIncrement));
-  c->trackLoss = (uint32_t)pdh.trackLoss;
-  if (had_icp) {
-    long long raw[32];
-    double r48[48];
-    memcpy(raw, hp + 4096, sizeof(raw));
-    sbg::unpack48(raw, r48);
-    c->stats[0] = pdh.icp_iterations;
-    c->stats[1] = r48[43];
-    c->stats[3] = r48[44];
-    c->stats[2] = (double)((uint32_t)r48[42] - (uint32_t)r48[44]);  // Frame2Model.cpp:222-226
-    c->stats[4] = r48[46];
-    c->stats[5] = (float)r48[45];
-  }
-  c->stats[6] = c->trackLoss;
+  if (!loop_ran) absorb_pose_block(c, pdh, hp, had_icp);  // (the loop-closure step has already done it, and chose currentPose_old_)
   uint32_t cnt[4];
   memcpy(cnt, hp + 8192, sizeof(cnt));
   c->n_host = cnt[0];
@@ -1559,6 +1649,83 @@ int sb_prefetch_scan(sb_ctx* c, const float* pts4, const float* labels, const fl
   slot->has_labels = labels != nullptr;
   slot->has_probs = probs != nullptr;
   slot->valid = true;
+  return SB_OK;
+}
+
+void sb_default_loop_params(sb_loop_params* p) {  // SurfelMapping.h:223-235 overridden by config/default.xml:70-76
+  if (!p) return;
+  p->search_distance = 50.0f;
+  p->min_trajectory_distance = 200.0f;
+  p->min_verifications = 5;
+  p->residual_threshold = 1.15f;
+  p->outlier_threshold = 1.1f;
+  p->valid_threshold = 0.95f;
+}
+
+int sb_set_loop_closure(sb_ctx* c, int enabled, const sb_loop_params* p) {
+  if (!c) return SB_ERR_INVALID;
+  sb_loop_params d;
+  sb_default_loop_params(&d);
+  if (p) d = *p;
+  c->loop.p.search_distance = d.search_distance;
+  c->loop.p.min_trajectory_distance = d.min_trajectory_distance;
+  c->loop.p.min_verifications = d.min_verifications;
+  c->loop.p.residual_threshold = d.residual_threshold;
+  c->loop.p.outlier_threshold = d.outlier_threshold;
+  c->loop.p.valid_threshold = d.valid_threshold;
+  if (enabled && !c->close_loops) c->loop.reset();
+  c->close_loops = enabled != 0;
+  return SB_OK;
+}
+
+int sb_get_loop_info(sb_ctx* c, sb_loop_info* o) {
+  if (!c || !o) return SB_ERR_INVALID;
+  const suma_b200::loop::State& L = c->loop;
+  memset(o, 0, sizeof(*o));
+  o->enabled = c->close_loops ? 1u : 0u;
+  o->loop_count = L.loop_count;
+  o->time_without_loop_closure = L.time_without_loop_closure;
+  o->candidates_tested = L.candidates_tested;
+  o->loop_edges_added = L.loop_edges_added;
+  o->unverified = (uint32_t)L.unverified.size();
+  o->already_verified = L.already_verified ? 1u : 0u;
+  o->found_candidate = L.found_candidate ? 1u : 0u;
+  o->use_candidate = L.use_candidate ? 1u : 0u;
+  o->optimisation_requested = L.optimisation_requested ? 1u : 0u;
+  o->last_added_candidate = L.last_added_candidate;
+  o->n_edges = (uint32_t)L.graph.edges.size();
+  o->n_poses = (uint32_t)L.graph.poses.size();
+  o->valid_ratio = L.stat_valid_ratio;
+  o->outlier_ratio = L.stat_outlier_ratio;
+  o->rel_error = L.stat_rel_error;
+  o->residual_old = L.result_old.residual;
+  o->residual_new = L.result_new.residual;
+  memcpy(o->current_pose_old, c->currentPose_old, sizeof(o->current_pose_old));
+  return SB_OK;
+}
+
+int sb_get_loop_edges(sb_ctx* c, sb_loop_edge* dst, uint32_t cap, uint32_t* n) {
+  if (!c || (!dst && cap)) return SB_ERR_INVALID;
+  const auto& E = c->loop.graph.edges;
+  uint32_t k = (uint32_t)E.size() < cap ? (uint32_t)E.size() : cap;
+  for (uint32_t i = 0; i < k; ++i) {
+    dst[i].from = E[i].from;
+    dst[i].to = E[i].to;
+    memcpy(dst[i].rel_pose, E[i].rel.m, 128);
+  }
+  if (n) *n = (uint32_t)E.size();
+  return SB_OK;
+}
+
+int sb_set_current_pose(sb_ctx* c, const double pose[16]) {  // SurfelMapping::setCurrentPose, SurfelMapping.cpp:880-882
+  if (!c || !pose) return SB_ERR_INVALID;
+  cudaSetDevice(c->device);
+  memcpy(c->currentPose, pose, sizeof(c->currentPose));
+  // the pose also lives on the device (PoseDev::currentPose): the next scan chains its increment onto it
+  SB_CUDA(c, cudaMemcpyAsync((char*)c->pd + offsetof(PoseDev, currentPose), c->currentPose, sizeof(c->currentPose),
+                             cudaMemcpyHostToDevice, c->stream));
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->rkey_valid = false;
   return SB_OK;
 }
 

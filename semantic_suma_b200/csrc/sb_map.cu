@@ -177,34 +177,6 @@ __device__ __forceinline__ void quad_corners(const KParams& kp, const Cand& c, R
   }
 }
 
-// the same for two of the four corners (2*half, 2*half + 1): stage C splits a quad over a pair of lanes
-__device__ __forceinline__ void quad_corner_pair(const KParams& kp, const Cand& c, int half, RVert out[2]) {
-  const V3 pp = mk3(c.px, c.py, c.pz), nn = mk3(c.nx, c.ny, c.nz);
-  V3 u = normalize3(mk3(nn.y - nn.z, -nn.x, nn.x));
-  V3 v = normalize3(cross3(nn, u));
-  V3 ru = scale3(c.r, u), rv = scale3(c.r, v);
-  V3 corner[2];
-  if (half == 0) {
-    corner[0] = sub3(sub3(pp, ru), rv);
-    corner[1] = sub3(add3(pp, ru), rv);
-  } else {
-    corner[0] = add3(sub3(pp, ru), rv);
-    corner[1] = add3(add3(pp, ru), rv);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    float x, y, z;
-    project01(corner[i], kp.m_fov_up, kp.m_fov, kp.m_min_depth, kp.m_max_depth, x, y, z);
-    if (c.cx - x > 0.5f) x += 1.0f;  // .geom:68
-    if (x - c.cx > 0.5f) x -= 1.0f;  // .geom:69
-    float xw = (0.5f * (2.0f * x - 1.0f) + 0.5f) * (float)kp.Wm;
-    float yw = (0.5f * (2.0f * y - 1.0f) + 0.5f) * (float)kp.Hm;
-    out[i].z = 0.5f * (2.0f * z - 1.0f) + 0.5f;
-    out[i].X = __float2ll_rn(xw * 256.0f);
-    out[i].Y = __float2ll_rn(yw * 256.0f);
-  }
-}
-
 // fragment stage (render_surfels.frag:19-33) + depth test + key update, shared by both rasterisers
 __device__ __forceinline__ void emit_fragment(float tx, float ty, float z, size_t pix, uint32_t k, uint32_t flags,
                                               const RenderTargets& rt) {
@@ -418,92 +390,48 @@ __global__ void __launch_bounds__(kRenderThreads, kMinBlocks) k_render_scatter(K
     c_flags[slot] = (is_old ? 1u : 0u) | (is_new ? 2u : 0u) | (lequal ? 4u : 0u);
   }
   __syncthreads();
-  // ---- stage C, TWO lanes per survivor: lane pair (2i, 2i+1) shares quad i -- each lane projects two of the four corners
-  // (the pair exchanges them by shuffle) and sets up one of the two triangles. All eight warps work (a block keeps ~130
-  // of its 256 surfels; with one lane per quad half of the warps idled at the barrier below: 13 % of the stall samples).
-  for (int qb = 0; qb < total; qb += kRenderThreads / 2) {
-    const int qi = qb + (tid >> 1), half = tid & 1;
-    const bool act = qi < total;
-    RVert mine[2];
-    mine[0].X = mine[0].Y = mine[1].X = mine[1].Y = 0;
-    mine[0].z = mine[1].z = 0.f;
-    if (act) {
-      c.px = c_f[0][qi]; c.py = c_f[1][qi]; c.pz = c_f[2][qi]; c.nx = c_f[3][qi];
-      c.ny = c_f[4][qi]; c.nz = c_f[5][qi]; c.r = c_f[6][qi]; c.cx = c_f[7][qi];
-      quad_corner_pair(kp, c, half, mine);  // corners 2*half and 2*half + 1
-    }
-    RVert q[4], other[2];
+  // ---- stage C on dense lanes: one quad record per survivor ----
+  int npix = 0;
+  if (tid < total) {
+    c.px = c_f[0][tid]; c.py = c_f[1][tid]; c.pz = c_f[2][tid]; c.nx = c_f[3][tid];
+    c.ny = c_f[4][tid]; c.nz = c_f[5][tid]; c.r = c_f[6][tid]; c.cx = c_f[7][tid];
+    RVert q[4];
+    quad_corners(kp, c, q);
+    // pixel bounding box of the quad (union of the boxes of its two triangles), clamped to the image
+    long long minX = min(min(q[0].X, q[1].X), min(q[2].X, q[3].X)), maxX = max(max(q[0].X, q[1].X), max(q[2].X, q[3].X));
+    long long minY = min(min(q[0].Y, q[1].Y), min(q[2].Y, q[3].Y)), maxY = max(max(q[0].Y, q[1].Y), max(q[2].Y, q[3].Y));
+    long long i0 = ceil_div256(minX - 128), i1 = floor_div256(maxX - 128);
+    long long j0 = ceil_div256(minY - 128), j1 = floor_div256(maxY - 128);
+    if (i0 < 0) i0 = 0;
+    if (j0 < 0) j0 = 0;
+    if (i1 > kp.Wm - 1) i1 = kp.Wm - 1;
+    if (j1 > kp.Hm - 1) j1 = kp.Hm - 1;
+    if (i0 <= i1 && j0 <= j1) {  // otherwise the quad covers no pixel centre
+      const long long X0 = i0 * 256 + 128, Y0 = j0 * 256 + 128;
+      const int ni = (int)(i1 - i0), nj = (int)(j1 - j0);
+      bool small = ni < kSmallW && nj < kSmallH;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      other[j].X = __shfl_xor_sync(0xffffffffu, mine[j].X, 1);
-      other[j].Y = __shfl_xor_sync(0xffffffffu, mine[j].Y, 1);
-      other[j].z = __shfl_xor_sync(0xffffffffu, mine[j].z, 1);
-    }
-    q[0] = half ? other[0] : mine[0];
-    q[1] = half ? other[1] : mine[1];
-    q[2] = half ? mine[0] : other[0];
-    q[3] = half ? mine[1] : other[1];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      q[i].tx = (i & 1) ? 1.0f : -1.0f;
-      q[i].ty = (i & 2) ? 1.0f : -1.0f;
-    }
-    uint32_t m_mine = 0;
-    int ni = 0, nj = 0;
-    long long i0 = 0, j0 = 0;
-    bool small = false, covers = false;
-    if (act) {
-      // pixel bounding box of the quad (union of the boxes of its two triangles), clamped to the image
-      long long minX = min(min(q[0].X, q[1].X), min(q[2].X, q[3].X)), maxX = max(max(q[0].X, q[1].X), max(q[2].X, q[3].X));
-      long long minY = min(min(q[0].Y, q[1].Y), min(q[2].Y, q[3].Y)), maxY = max(max(q[0].Y, q[1].Y), max(q[2].Y, q[3].Y));
-      i0 = ceil_div256(minX - 128);
-      j0 = ceil_div256(minY - 128);
-      long long i1 = floor_div256(maxX - 128), j1 = floor_div256(maxY - 128);
-      if (i0 < 0) i0 = 0;
-      if (j0 < 0) j0 = 0;
-      if (i1 > kp.Wm - 1) i1 = kp.Wm - 1;
-      if (j1 > kp.Hm - 1) j1 = kp.Hm - 1;
-      covers = i0 <= i1 && j0 <= j1;  // otherwise the quad covers no pixel centre
-      if (covers) {
-        const long long X0 = i0 * 256 + 128, Y0 = j0 * 256 + 128;
-        ni = (int)(i1 - i0);
-        nj = (int)(j1 - j0);
-        small = ni < kSmallW && nj < kSmallH;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          long long dx = q[i].X - X0, dy = q[i].Y - Y0;
-          small = small && dx > -kSmallSpan && dx < kSmallSpan && dy > -kSmallSpan && dy < kSmallSpan;
-        }
-        if (small) {  // this lane's triangle: (q0, q1, q2) for the even lane, (q1, q2, q3) for the odd one
-          const TriSmall t = half ? tri_small(q[1], q[2], q[3], X0, Y0) : tri_small(q[0], q[1], q[2], X0, Y0);
-          if (t.valid) {
-            m_mine = t.ties | (t.swapped ? 8u : 0u) | 16u;
-            quad_store_tri(Q, qi, half, t);
-          }
-        }
+      for (int i = 0; i < 4; ++i) {
+        long long dx = q[i].X - X0, dy = q[i].Y - Y0;
+        small = small && dx > -kSmallSpan && dx < kSmallSpan && dy > -kSmallSpan && dy < kSmallSpan;
       }
-    }
-    const uint32_t m_other = __shfl_xor_sync(0xffffffffu, m_mine, 1);
-    if (act && half == 0) {
-      int npix = 0;
-      if (covers) {
-        if (small) {
-          const uint32_t m0 = m_mine, m1 = m_other;
-          if (m0 | m1) {
-            Q.z[0][qi] = q[0].z; Q.z[1][qi] = q[1].z; Q.z[2][qi] = q[2].z; Q.z[3][qi] = q[3].z;
-            Q.box[qi] = (uint32_t)i0 | ((uint32_t)j0 << 16);
-            Q.meta[qi] = (uint32_t)ni | ((uint32_t)nj << 8) | (m0 << 16) | (m1 << 21) | (c_flags[qi] << 26);
-            npix = (ni + 1) * (nj + 1);
-          }
-        } else {
-          s_big[atomicAdd(&s_nbig, 1)] = (uint16_t)qi;
+      if (small) {
+        const TriSmall t0 = tri_small(q[0], q[1], q[2], X0, Y0), t1 = tri_small(q[1], q[2], q[3], X0, Y0);
+        const uint32_t m0 = t0.valid ? (t0.ties | (t0.swapped ? 8u : 0u) | 16u) : 0u;
+        const uint32_t m1 = t1.valid ? (t1.ties | (t1.swapped ? 8u : 0u) | 16u) : 0u;
+        if (m0 | m1) {
+          if (t0.valid) quad_store_tri(Q, tid, 0, t0);
+          if (t1.valid) quad_store_tri(Q, tid, 1, t1);
+          Q.z[0][tid] = q[0].z; Q.z[1][tid] = q[1].z; Q.z[2][tid] = q[2].z; Q.z[3][tid] = q[3].z;
+          Q.box[tid] = (uint32_t)i0 | ((uint32_t)j0 << 16);
+          Q.meta[tid] = (uint32_t)ni | ((uint32_t)nj << 8) | (m0 << 16) | (m1 << 21) | (c_flags[tid] << 26);
+          npix = (ni + 1) * (nj + 1);
         }
+      } else {
+        s_big[atomicAdd(&s_nbig, 1)] = (uint16_t)tid;
       }
-      Q.prefix[qi + 1] = npix;  // raw count; turned into the exclusive prefix below
     }
   }
-  __syncthreads();
-  const int npix = tid < total ? Q.prefix[tid + 1] : 0;
   // ---- exclusive prefix of the pixel counts over the 256 slots ----
   int incl = npix;
 #pragma unroll

@@ -443,3 +443,46 @@ def test_cuda_equals_reference_shaders_directly():
     assert np.max(np.abs(m - e) / scale) < 1e-5
     assert (rf[42], rf[44], rf[46]) == (obj.out48[42], obj.out48[44], obj.out48[46])
     ctx.close()
+
+
+def test_loop_closure_detection_and_verification_bit_exact():
+    """SurfelMapping::checkLoopClosure (SurfelMapping.cpp:527-795) on a synthetic loop: a circle of 120 scans driven a
+    second time. Detection (render_inactive at the candidate pose + three Gauss-Newton runs against the old map frame),
+    the composed rendering, the verification over consecutive scans, the loop edges and the chained old pose must agree
+    with the oracle twin at every scan -- decisions, counters, float ratios and pose bits."""
+    from semantic_suma_b200 import synth
+    po, pp = both_params(**sized(900))
+    scene = synth.Scene(width=900, height=64)
+    N = 124
+    poses = synth.trajectory(N, step=0.2618, yaw_deg=3.0)
+    lp = dict(search_distance=3.0, min_trajectory_distance=15.0, min_verifications=2)
+    osl = O.Slam(po)
+    osl.enable_loop_closure(**lp)
+    gsl = api.SurfelMapping(pp)
+    gsl.enableLoopClosure(True, **lp)
+    keys = ("loop_count", "time_without_loop_closure", "candidates_tested", "loop_edges_added", "unverified",
+            "already_verified", "found_candidate", "use_candidate", "optimisation_requested", "last_added_candidate",
+            "n_edges", "n_poses")
+    for f in range(N):
+        pts, _, _ = scene.scan(f, poses[f])
+        osl.process_scan(pts)
+        gsl.processScan(pts)
+        assert_bits_equal(gsl.getCurrentPose(), osl.pose(), "t=%d pose" % f)
+        if f >= 100:
+            a, b = gsl.getLoopInfo(), osl.loop_info()
+            for k in keys:
+                assert a[k] == b[k], "t=%d %s: %r vs %r" % (f, k, a[k], b[k])
+            if b["found_candidate"]:
+                for k in ("valid_ratio", "outlier_ratio", "rel_error"):
+                    assert_bits_equal(np.float32(a[k]), np.float32(b[k]), "t=%d %s" % (f, k))
+                assert_bits_equal(a["current_pose_old"], b["current_pose_old"], "t=%d currentPose_old" % f)
+        assert gsl.getMap().size() == osl.map.size(), "t=%d surfel count" % f
+    info = osl.loop_info()
+    assert info["loop_edges_added"] >= 3 and info["already_verified"] == 1, "the sequence must close the loop: %r" % info
+    eg, eo = gsl.getLoopEdges(), osl.loop_edges()
+    assert len(eg) == len(eo)
+    for (f1, t1, r1), (f2, t2, r2) in zip(eg, eo):
+        assert (f1, t1) == (f2, t2)
+        assert_bits_equal(r1, r2, "edge %d->%d" % (f1, t1))
+    surfel_fields_equal(gsl.getMap().getAllSurfels(), osl.map.download(), "surfels after the loop")
+    gsl.ctx.close()
