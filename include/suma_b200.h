@@ -206,7 +206,9 @@ int sb_get_last_pose(sb_ctx* ctx, double pose[16]); /* getLastPose, core/SurfelM
 int sb_timestamp(sb_ctx* ctx, uint32_t* t);        /* timestamp() */
 int sb_slam_frame(sb_ctx* ctx, int which, sb_frame** out); /* getCurrentFrame / LastFrame / *ModelFrame (borrowed) */
 /* stats[16]: [0] icp iterations [1] F [2] inlier [3] outlier [4] invalid [5] inlier_residual [6] track losses
- * [7] surfels; wall seconds: [8] preprocessing [9] icp [10] mapping [11] complete (getStatistics keys) */
+ * [7] surfels; wall seconds: [8] preprocessing [9] icp [10] mapping [11] complete (getStatistics keys);
+ * [12] surfels dropped because the HBM cache of extracted submap tiles (16 M surfels) was full -- the reference's
+ * host-side submapCache_ is unbounded; sb_last_error carries the message */
 int sb_get_statistics(sb_ctx* ctx, double stats[16]);
 
 /* ---- per-kernel device time (CUDA events on the context's stream around every launch; off by default) ------------ */
@@ -217,8 +219,11 @@ const char* sb_profile_name(int id);
 int sb_profile_collect(sb_ctx* ctx, double* total_ms, uint64_t* count, int cap);
 
 /* ---- multi-GPU: row-striped K5 with a one-shot peer-memory all-reduce of the 32 fixed-point sums ---------------
- * Every rank calls sb_comm_export to obtain an opaque 64-byte handle of its mailbox, exchanges the handles out of
- * band (e.g. torch.distributed.all_gather) and passes all of them to sb_comm_init. Afterwards sb_icp_minimize /
+ * Every rank calls sb_comm_export to obtain an opaque 64-byte handle of its mailbox (each call clears the mailbox and
+ * starts a new session: export again before every sb_comm_init, and only after all ranks have left the previous
+ * session), exchanges the handles out of band (e.g. torch.distributed.all_gather) and passes all of them to
+ * sb_comm_init; a barrier between the ranks must follow before the first striped call. Waiting inside the kernel is
+ * bounded (10 s): a rank that never arrives makes the call fail with SB_ERR_STATE instead of hanging. Afterwards sb_icp_minimize /
  * sb_process_scan reduce the sums over ranks inside the Jacobian kernel. rows [row_begin,row_end) of the data image
  * belong to this rank. */
 int sb_comm_export(sb_ctx* ctx, uint8_t handle[64]);

@@ -281,6 +281,9 @@ int reset_state(sb_ctx* c) {
   c->tiles.clear();
   c->n_slots = 0;
   c->tiles_pending = false;
+  c->stats[12] = 0.0;
+  c->loop.reset();  // posegraph_->clear(); trajectory_distances_ ... (SurfelMapping.cpp:158-163)
+  for (int i = 0; i < 16; ++i) c->lastPose_old[i] = (i % 5 == 0) ? 1.0 : 0.0;
   SB_CUDA(c, cudaMemsetAsync(c->d_pool_top, 0, 64, c->stream));
   c->h_poses.assign((size_t)kMaxPoses * 16, 0.0f);
   for (uint32_t t = 0; t < kMaxPoses; ++t)
@@ -689,6 +692,14 @@ int refresh_tile_records(sb_ctx* c) {  // read back {base, count} of the tiles e
   SB_CUDA(c, cudaMemcpyAsync(rec.data(), c->d_tile_rec, (size_t)c->n_slots * sizeof(uint2), cudaMemcpyDeviceToHost,
                              c->stream));
   SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  {  // surfels that did not fit the 16 M-surfel HBM tile pool (the reference's host-side cache is unbounded)
+    uint32_t top[2] = {0, 0};
+    SB_CUDA(c, cudaMemcpy(top, c->d_pool_top, sizeof(top), cudaMemcpyDeviceToHost));
+    if (top[1] != (uint32_t)c->stats[12]) {
+      c->stats[12] = top[1];
+      c->err = "submap tile pool exhausted: " + std::to_string(top[1]) + " surfels of leaving tiles were dropped";
+    }
+  }
   for (auto& kv : c->tiles) {
     DevTile& t = kv.second;
     if (!t.known) {
@@ -1795,8 +1806,11 @@ int sb_comm_export(sb_ctx* c, uint8_t handle[64]) {
     // cudaMalloc requests are carved out of shared 2 MiB blocks, so a 5 KiB mailbox would be opened at the wrong
     // address on the peer. A 2 MiB allocation owns its block: exported pointer == base.
     SB_CUDA(c, cudaMalloc(&c->mailbox, 2u << 20));
-    SB_CUDA(c, cudaMemset(c->mailbox, 0, 2u << 20));
   }
+  // Every export starts a fresh session: stamps of an earlier session must not match the epochs of the next one (both
+  // restart at 1). Peers cannot write yet -- they only learn this mailbox's address from the handle returned here.
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  SB_CUDA(c, cudaMemset(c->mailbox, 0, 2u << 20));
   cudaIpcMemHandle_t h;
   SB_CUDA(c, cudaIpcGetMemHandle(&h, c->mailbox));
   static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");

@@ -1292,7 +1292,10 @@ void launch_compact(const Launch& L, SurfelPlanes src, const uint8_t* keep, cons
 __global__ void k_pool_alloc(uint2* __restrict__ rec, uint32_t* __restrict__ pool_top, uint32_t pool_cap) {
   uint32_t base = *pool_top, cnt = rec->y;
   if (base > pool_cap) base = pool_cap;
-  if (cnt > pool_cap - base) cnt = pool_cap - base;  // pool exhausted: the tail of the tile is lost
+  if (cnt > pool_cap - base) {  // pool exhausted: the tail of the tile is lost -- counted in pool_top[1], which the host
+    pool_top[1] += cnt - (pool_cap - base);  // reads with the tile records and reports (sb_get_statistics[12], sb_last_error)
+    cnt = pool_cap - base;
+  }
   rec->x = base;
   rec->y = cnt;
   *pool_top = base + cnt;

@@ -16,7 +16,15 @@ void surface(suma::SurfelMapping& slam, suma::Laserscan& scan, const suma::Param
                    f3 = slam.getLastModelFrame(), f4 = slam.getOldSurfelMap(), f5 = slam.getNewSurfelMap();
   suma::SurfelMapping::Stats st = slam.getStatistics();
   std::vector<suma::Matrix4d> poses = slam.getOptimizedPoses();
-  bool lc = slam.foundLoopClosureCandidate() || slam.useLoopClosureCandidate();
+  // "close-loops": checkLoopClosure runs inside processScan; the graph edges go to the caller's optimiser (gtsam)
+  sb_loop_params lp;
+  sb_default_loop_params(&lp);
+  slam.enableLoopClosure(true, &lp);
+  bool lc = slam.foundLoopClosureCandidate() || slam.useLoopClosureCandidate() || slam.optimisationRequested();
+  std::vector<sb_loop_edge> edges = slam.getLoopEdges();
+  sb_loop_info li = slam.getLoopInfo();
+  slam.setCurrentPose(cur);
+  (void)edges; (void)li;
   std::shared_ptr<suma::SurfelMap> map = slam.getMap();
   suma::Matrix4f P = cur.cast<float>();
   map->update(P, *f0);
