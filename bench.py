@@ -123,11 +123,17 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
+ITERS = [10]  # Gauss-Newton iterations of the workload (set by run_native)
+
+
 def algorithmic_bytes(kernel, P, S, N, semantic):
     """compulsory HBM bytes of one launch (DESIGN.md 'Kernels and their rooflines')"""
     t = {
         "fill_u64": 8 * P, "project_scatter": 16 * N, "preprocess_tile": 8 * P + 16 * N + (48 + 16) * P,
-        "icp_fused": (96 if semantic else 64) * P, "icp_jacobian": (96 if semantic else 64) * P,
+        # the persistent Gauss-Newton launch re-reads the six range images every iteration (SURVEY.md 8d: 64P / 96P per
+        # iteration); icp_post = the statistics pass of updatePose (one iteration's worth)
+        "icp_fused": ITERS[0] * (96 if semantic else 64) * P, "icp_post": (96 if semantic else 64) * P,
+        "icp_jacobian": (96 if semantic else 64) * P,
         "render_scatter": 48 * S, "render_resolve": 3 * 8 * P + 4 * 48 * P,
         "index_scatter": 48 * S, "radius": 48 * P, "update_surfels": 129 * S, "gen_surfels": 84 * P,
         "compact_scatter": 129 * S, "scan_blocks": 8 * (S // 256 + 1), "pose_products": 128 * 100,
@@ -160,6 +166,7 @@ def run_native(args, w, rank, world, local_rank):
     import torch
     from semantic_suma_b200 import api
 
+    ITERS[0] = w["iters"]
     pre = args.preroll + args.warmup            # scans processed before the timed region of every pass
     n_frames = pre + args.steps
     scans = generate_scans(w, n_frames, seed=1337 + 1000 * rank)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Fixed-load micro-benchmark of the surfel passes ("S = 1 000 000 synthetic surfels for K4/K6").
 
-bench.py measures whole scans on a growing map; here the map is frozen at exactly S surfels so that the per-kernel
+bench.py measures whole scans; here the map is frozen at exactly S surfels so that the per-kernel
 numbers of K4 (render_scatter / render_resolve) and K6 (index_scatter, update_surfels, compaction, generation) can be
 compared between builds. The load is produced by the product itself: the bench sequence is processed until the map
 holds at least S surfels, the first S records (buffer order) and all poses are copied into a fresh context, and every
@@ -9,7 +9,7 @@ repetition re-uploads them before the timed call. Per-kernel device time comes f
 
     python microbench.py [--surfels 1000000] [--reps 20]
 
-Prints one JSON line. (Written at the end of round 1 after the GPU budget was spent: not run on a GPU yet.)
+Prints one JSON line (round-2 results: profiles/r02_microbench_*.json).
 """
 import argparse
 import json

@@ -72,7 +72,9 @@ struct sb_ctx {
   void* h_pinned = nullptr;  // pinned staging for small read-backs (64 KiB)
   int icp_blocks = 296;
   int icp_coop_blocks = 0;  // > 0: the persistent cooperative Gauss-Newton kernel is available
-  unsigned int epoch_base = 0;  // epoch words of the persistent GN kernel: each launch owns a fresh range of values
+  unsigned int epoch_base = 1;  // epoch words of the persistent GN kernel: each launch owns a fresh range of values
+  unsigned long long* gn_pub = nullptr;  // 32 (half pose value, epoch tag) words published by every Gauss-Newton step
+  int gn_use_ll = 1, gn_use_cache = 1;   // SUMA_B200_GN_LL / SUMA_B200_GN_CACHE = 0 select the round-1 hand-over / reloads
   // loop closure (SurfelMapping::checkLoopClosure; include/suma_b200_loop.hpp): off unless sb_set_loop_closure enables it
   bool close_loops = false;
   suma_b200::loop::State loop;
@@ -251,7 +253,7 @@ int frame_create(sb_ctx* c, int w, int h, sb_frame** out) {
 int release_buffers(sb_ctx* c) {
   cudaFree(c->prep.img[0]); cudaFree(c->prep.img[1]);
   cudaFree(c->d_pts); cudaFree(c->d_labels); cudaFree(c->d_probs);
-  cudaFree(c->gn); cudaFree(c->gn2); cudaFree(c->acc_slots); cudaFree(c->ticket);
+  cudaFree(c->gn); cudaFree(c->gn2); cudaFree(c->acc_slots); cudaFree(c->ticket); cudaFree(c->gn_pub);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   free_planes(&c->A); free_planes(&c->T); free_planes(&c->G); free_planes(&c->X); free_planes(&c->pool);
   cudaFree(c->d_pool_top); cudaFree(c->d_tile_rec);
@@ -343,6 +345,10 @@ int alloc_buffers(sb_ctx* c) {
   SB_CUDA(c, cudaMalloc(&c->acc_slots, 1024 * 32 * sizeof(long long)));
   SB_CUDA(c, cudaMemsetAsync(c->acc_slots, 0, 1024 * 32 * sizeof(long long), c->stream));
   SB_CUDA(c, cudaMalloc(&c->ticket, 128));
+  SB_CUDA(c, cudaMalloc(&c->gn_pub, 64 * 8));
+  SB_CUDA(c, cudaMemsetAsync(c->gn_pub, 0, 64 * 8, c->stream));
+  if (const char* e = getenv("SUMA_B200_GN_LL")) c->gn_use_ll = atoi(e) != 0;
+  if (const char* e = getenv("SUMA_B200_GN_CACHE")) c->gn_use_cache = atoi(e) != 0;
   SB_CUDA(c, cudaMemsetAsync(c->ticket, 0, 128, c->stream));
   SB_CUDA(c, cudaMallocHost(&c->h_pinned, 65536));
   int r;
@@ -645,7 +651,9 @@ int icp_minimize_enqueue(sb_ctx* c, const sb_frame* data, const sb_frame* model,
     job.eps = eps;
     job.delta = delta;
     job.epoch_base = next_epoch_base(c, max_iter);
-    if (launch_gn_persistent(L, c->kp, job, c->acc_slots, c->ticket, c->ticket + 8, c->comm_on ? &c->comm : nullptr,
+    job.use_ll = c->gn_use_ll;
+    job.use_cache = c->gn_use_cache;
+    if (launch_gn_persistent(L, c->kp, job, c->acc_slots, c->ticket, c->ticket + 8, c->gn_pub, c->comm_on ? &c->comm : nullptr,
                              c->icp_coop_blocks) == 0)
       return SB_OK;
     cudaGetLastError();
@@ -974,7 +982,9 @@ int update_pose_enqueue(sb_ctx* c, bool* tables_ready) {
     job.eps = p.stopping_threshold;
     job.delta = p.delta;
     job.epoch_base = next_epoch_base(c, max_iter);
-    if (launch_gn_persistent(L, c->kp, job, c->acc_slots, c->ticket, c->ticket + 8, c->comm_on ? &c->comm : nullptr,
+    job.use_ll = c->gn_use_ll;
+    job.use_cache = c->gn_use_cache;
+    if (launch_gn_persistent(L, c->kp, job, c->acc_slots, c->ticket, c->ticket + 8, c->gn_pub, c->comm_on ? &c->comm : nullptr,
                              c->icp_coop_blocks) != 0) {
       cudaGetLastError();
       return fail(c, SB_ERR_CUDA, "cooperative launch of the Gauss-Newton kernel failed");
@@ -1002,7 +1012,9 @@ int update_pose_enqueue(sb_ctx* c, bool* tables_ready) {
     post.eps = p.stopping_threshold;
     post.delta = p.delta;
     post.epoch_base = next_epoch_base(c, max_iter);
-    if (launch_gn_persistent(L, c->kp, post, c->acc_slots, c->ticket, c->ticket + 8, c->comm_on ? &c->comm : nullptr,
+    post.use_ll = c->gn_use_ll;
+    post.use_cache = 0;
+    if (launch_gn_persistent(L, c->kp, post, c->acc_slots, c->ticket, c->ticket + 8, c->gn_pub, c->comm_on ? &c->comm : nullptr,
                              c->icp_coop_blocks) != 0) {
       cudaGetLastError();
       return fail(c, SB_ERR_CUDA, "cooperative launch of the Gauss-Newton kernel failed");

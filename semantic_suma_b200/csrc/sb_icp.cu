@@ -74,10 +74,8 @@ struct Acc {
 };
 
 // Frame2Model_jacobians.geom:84-200 for one data pixel
-__device__ __forceinline__ void icp_pixel(const KParams& kp, const IcpArgs& a, const float* M, int pix, int iteration,
-                                          Acc& acc) {
-  float4 Vd = __ldg(a.data_v + pix);
-  float4 Nd = __ldg(a.data_n + pix);
+__device__ __forceinline__ void icp_pixel_v(const KParams& kp, const IcpArgs& a, const float* M, int pix, float4 Vd, float4 Nd,
+                                            int iteration, Acc& acc) {
   float e_d = Vd.w + Nd.w;
   if (!(e_d > 1.5f)) {
     acc.n_invalid += 1;
@@ -161,6 +159,11 @@ __device__ __forceinline__ void icp_pixel(const KParams& kp, const IcpArgs& a, c
   } else {
     acc.n_outlier += 1;
   }
+}
+
+__device__ __forceinline__ void icp_pixel(const KParams& kp, const IcpArgs& a, const float* M, int pix, int iteration,
+                                          Acc& acc) {
+  icp_pixel_v(kp, a, M, pix, __ldg(a.data_v + pix), __ldg(a.data_n + pix), iteration, acc);
 }
 
 __device__ __forceinline__ long long warp_sum_ll(long long v) {
@@ -629,16 +632,36 @@ __device__ __forceinline__ void load_mat_cg(const float* table, int idx, float* 
   M[12] = d.x; M[13] = d.y; M[14] = d.z; M[15] = d.w;
 }
 
+constexpr int kGnCachePix = 2;  // data pixels per thread kept in shared memory across the iterations of one launch
+
 __global__ void __launch_bounds__(kIcpThreads, 2) k_gn_persistent(KParams kp, GnJob job, long long* __restrict__ slots,
-                                                               unsigned int* ticket, unsigned int* epoch_flag, CommDev cd) {
+                                                               unsigned int* ticket, unsigned int* epoch_flag,
+                                                               unsigned long long* pub, CommDev cd) {
   __shared__ GnShared sh;
   __shared__ bool is_last;
   __shared__ double s_pose[16];
   __shared__ int s_done, s_error;
+  __shared__ float4 s_dv[kGnCachePix][kIcpThreads], s_dn[kGnCachePix][kIcpThreads];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   GnState* st = job.st;
   PoseDev* pd = job.pd;
   if (threadIdx.x == 0) s_error = 0;
+  // The data frame does not change during a minimisation and a thread visits the same pixels in every iteration: keep
+  // their vertex / normal texels in shared memory (thread-private slots), which takes one dependent L2 round trip out of
+  // every iteration. Only when the whole stripe fits (<= kGnCachePix pixels per thread) and the objective is fixed.
+  const int px_begin = job.a.row_begin * kp.W, px_end = job.a.row_end * kp.W;
+  const int px_stride = gridDim.x * blockDim.x, px_first = px_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool cached = job.use_cache && job.mode != GN_POST && (px_end - px_begin) <= kGnCachePix * px_stride;
+  if (cached) {
+#pragma unroll
+    for (int j = 0; j < kGnCachePix; ++j) {
+      const int pix = px_first + j * px_stride;
+      if (pix < px_end) {
+        s_dv[j][threadIdx.x] = __ldg(job.a.data_v + pix);
+        s_dn[j][threadIdx.x] = __ldg(job.a.data_n + pix);
+      }
+    }
+  }
   for (unsigned int it = 0;; ++it) {
     // Warp 0 waits for the previous iteration's step (epoch word), then fetches the state written by that step with ONE
     // round of coherent loads spread over its lanes and broadcasts it through shared memory (every thread reading the
@@ -658,6 +681,30 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_gn_persistent(KParams kp, Gn
           }
           if (lane == 17) s_done = 0;
         }
+      } else if (job.use_ll) {
+        // The step publishes the new pose as 32 self-validating 8-byte words (half a double + the epoch tag, bit 31 of the
+        // tag = done): lane l polls word l, so pose AND release arrive in ONE L2 round trip (a flag followed by a fetch
+        // of the pose costs two).
+        const unsigned int want = (job.epoch_base + it) & 0x7fffffffu;
+        const unsigned long long t0 = globaltimer_ns();
+        unsigned int spins = 0;
+        unsigned long long w = *(volatile unsigned long long*)&pub[lane];
+        bool timed_out = false;
+        while ((((unsigned int)(w >> 32)) & 0x7fffffffu) != want) {
+          if ((++spins & 4095u) == 0u && globaltimer_ns() - t0 > kSpinTimeoutNs) {
+            timed_out = true;
+            break;
+          }
+          w = *(volatile unsigned long long*)&pub[lane];
+        }
+        if (__any_sync(0xffffffffu, timed_out)) {
+          if (lane == 0) s_error = 1;
+        }
+        __threadfence();
+        const unsigned int lo = __shfl_sync(0xffffffffu, (unsigned int)w, 2 * (lane & 15));
+        const unsigned int hi = __shfl_sync(0xffffffffu, (unsigned int)w, 2 * (lane & 15) + 1);
+        if (lane < 16) s_pose[lane] = __hiloint2double((int)hi, (int)lo);
+        if (lane == 17) s_done = (int)((w >> 63) & 1ull);
       } else {
         if (lane == 0) {
           const unsigned int want = job.epoch_base + it;
@@ -692,7 +739,18 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_gn_persistent(KParams kp, Gn
 #pragma unroll
     for (int i = 0; i < 16; ++i) M[i] = (float)s_pose[i];  // pose_.cast<float>(), Frame2Model.cpp:194
     Acc acc;
-    icp_accumulate(kp, recovery ? job.fb : job.a, M, stats_pass ? 0 : k, acc);
+    if (cached) {
+#pragma unroll
+      for (int i = 0; i < 29; ++i) acc.s[i] = 0;
+      acc.n_valid = acc.n_outlier = acc.n_invalid = 0;
+#pragma unroll
+      for (int j = 0; j < kGnCachePix; ++j) {
+        const int pix = px_first + j * px_stride;
+        if (pix < px_end) icp_pixel_v(kp, job.a, M, pix, s_dv[j][threadIdx.x], s_dn[j][threadIdx.x], k, acc);
+      }
+    } else {
+      icp_accumulate(kp, recovery ? job.fb : job.a, M, stats_pass ? 0 : k, acc);
+    }
     __syncthreads();
     block_reduce_to_replica(acc, slots);
     __syncthreads();
@@ -771,7 +829,16 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_gn_persistent(KParams kp, Gn
       }
       __threadfence();
       __syncwarp();
-      if (lane == 0) atomicExch(epoch_flag, job.epoch_base + it + 1u);
+      if (job.use_ll) {
+        double pv = 0.0;
+        if (lane < 16) pv = *(volatile double*)&st->pose[lane];  // the pose of the next pass (just written by this warp)
+        const double src = __shfl_sync(0xffffffffu, pv, lane >> 1);
+        const unsigned int half = (lane & 1) ? (unsigned int)__double2hiint(src) : (unsigned int)__double2loint(src);
+        const unsigned int tag = ((job.epoch_base + it + 1u) & 0x7fffffffu) | (done ? 0x80000000u : 0u);
+        *(volatile unsigned long long*)&pub[lane] = ((unsigned long long)tag << 32) | (unsigned long long)half;
+      } else if (lane == 0) {
+        atomicExch(epoch_flag, job.epoch_base + it + 1u);
+      }
     }
     // The last block's other warps wait for the step HERE, not at the loop-top barrier (is_last is block-uniform).
     if (is_last) __syncthreads();
@@ -803,7 +870,7 @@ int gn_persistent_max_blocks(int sm_count) {
 }
 
 int launch_gn_persistent(const Launch& L, const KParams& kp, const GnJob& job, long long* slots, unsigned int* ticket,
-                         unsigned int* epoch_flag, const CommDev* comm, int blocks) {
+                         unsigned int* epoch_flag, unsigned long long* pub, const CommDev* comm, int blocks) {
   CommDev cd;
   if (comm) {
     cd = *comm;
@@ -813,10 +880,10 @@ int launch_gn_persistent(const Launch& L, const KParams& kp, const GnJob& job, l
   }
   KParams kpv = kp;
   GnJob jv = job;
-  void* args[] = {&kpv, &jv, &slots, &ticket, &epoch_flag, &cd};
+  void* args[] = {&kpv, &jv, &slots, &ticket, &epoch_flag, &pub, &cd};
   cudaError_t e;
   {
-    ScopedKernel sk(L, K_ICP_FUSED);
+    ScopedKernel sk(L, job.mode == GN_POST ? K_ICP_POST : K_ICP_FUSED);
     e = cudaLaunchCooperativeKernel((void*)k_gn_persistent, dim3(blocks), dim3(kIcpThreads), args, 0, L.stream);
   }
   return e == cudaSuccess ? 0 : -1;

@@ -112,7 +112,7 @@ struct PoseDev {
 enum KernelId {
   K_FILL = 0, K_PROJECT_SCATTER, K_PREPROCESS_TILE, K_ICP_JACOBIAN, K_GN_INIT,
   K_ICP_FUSED, K_POSE_PRODUCTS, K_RENDER_SCATTER, K_RENDER_RESOLVE, K_INDEX_SCATTER, K_RADIUS, K_UPDATE_SURFELS,
-  K_GEN_SURFELS, K_EXTRACT_FLAGS, K_SCAN_BLOCKS, K_COMPACT_SCATTER, K_AOS_TO_SOA, K_SOA_TO_AOS, K_COUNT
+  K_GEN_SURFELS, K_EXTRACT_FLAGS, K_SCAN_BLOCKS, K_COMPACT_SCATTER, K_AOS_TO_SOA, K_SOA_TO_AOS, K_ICP_POST, K_COUNT
 };
 const char* kernel_name(int id);
 
@@ -187,10 +187,12 @@ struct GnJob {
   int max_iter;
   double eps, delta;
   unsigned int epoch_base;
+  int use_ll;     // publish the pose as self-validating (value, tag) words: one L2 round trip per iteration hand-over
+  int use_cache;  // keep the thread's data pixels in shared memory across iterations
 };
 void launch_gn_init(const Launch& L, GnState* st, const Mat4d& T0, long long* acc32);
 int launch_gn_persistent(const Launch& L, const KParams& kp, const GnJob& job, long long* slots, unsigned int* ticket,
-                         unsigned int* epoch_flag, const CommDev* comm, int blocks);
+                         unsigned int* epoch_flag, unsigned long long* pub, const CommDev* comm, int blocks);
 int gn_persistent_max_blocks(int sm_count);
 // one-thread bookkeeping kernels: first scan of a sequence and the host-callback exchange
 void launch_pose_after_icp(const Launch& L, const GnState* gn, PoseDev* pd, const Mat4d& T0, uint32_t timestamp,
@@ -233,9 +235,6 @@ void launch_gen_compact(const Launch& L, const KParams& kp, FrameDev frame, cons
                         float submap_extent, SurfelPlanes map, unsigned long long* desc, uint32_t* ticket, uint32_t gen,
                         uint32_t cap, uint32_t* counts);
 // ordered compaction: items flagged in keep[0..n) of src go to dst[base..) in order; *count_out = base + #kept
-void launch_compact(const Launch& L, SurfelPlanes src, const uint8_t* keep, const uint32_t* block_counts,
-                    uint32_t* block_offsets, const uint32_t* n_dev, uint32_t n_upper, SurfelPlanes dst,
-                    const uint32_t* base_dev, uint32_t cap, uint32_t* count_out, uint32_t* kept_out);
 void launch_extract_to_pool(const Launch& L, SurfelPlanes map, const uint32_t* n_dev, uint32_t n_upper, const float* poses,
                             float2 center, float extent, uint8_t* keep, uint32_t* block_counts, uint32_t* block_offsets,
                             SurfelPlanes pool, uint32_t pool_cap, uint32_t* pool_top, uint2* rec, uint32_t tile_cap);
@@ -243,6 +242,5 @@ void launch_extract_flags(const Launch& L, SurfelPlanes s, const uint32_t* n_dev
                           float2 center, float extent, uint8_t* keep, uint32_t* block_counts);
 void launch_aos_to_soa(const Launch& L, const sb_surfel* aos, SurfelPlanes s, uint32_t offset, uint32_t n);
 void launch_soa_to_aos(const Launch& L, SurfelPlanes s, sb_surfel* aos, uint32_t n);
-void launch_fill_u64(const Launch& L, unsigned long long* p, unsigned long long v, size_t n);
 
 }  // namespace sb

@@ -24,7 +24,7 @@ const char* kernel_name(int id) {
   static const char* names[K_COUNT] = {"fill_u64", "project_scatter", "preprocess_tile",
                                        "icp_jacobian", "gn_init", "icp_fused", "pose_products", "render_scatter",
                                        "render_resolve", "index_scatter", "radius", "update_surfels", "gen_surfels",
-                                       "extract_flags", "scan_blocks", "compact_scatter", "aos_to_soa", "soa_to_aos"};
+                                       "extract_flags", "scan_blocks", "compact_scatter", "aos_to_soa", "soa_to_aos", "icp_post"};
   return (id >= 0 && id < K_COUNT) ? names[id] : "?";
 }
 
@@ -1267,23 +1267,6 @@ void launch_compact_update(const Launch& L, SurfelPlanes src, const uint8_t* kee
     ScopedKernel sk(L, K_COMPACT_SCATTER);
     k_compact_update<<<blocks, kThreads, 0, L.stream>>>(src, keep, block_counts, group_counts, n_dev, dst, cap, count_out,
                                                        kept_out);
-  }
-}
-
-void launch_compact(const Launch& L, SurfelPlanes src, const uint8_t* keep, const uint32_t* block_counts,
-                    uint32_t* block_offsets, const uint32_t* n_dev, uint32_t n_upper, SurfelPlanes dst,
-                    const uint32_t* base_dev, uint32_t cap, uint32_t* count_out, uint32_t* kept_out) {
-  {
-    ScopedKernel sk(L, K_SCAN_BLOCKS);
-    k_scan_blocks<<<1, 1024, 0, L.stream>>>(block_counts, block_offsets, n_dev, n_upper, base_dev, cap, count_out,
-                                          kept_out);
-  }
-  if (n_upper == 0) return;
-  {
-    ScopedKernel sk(L, K_COMPACT_SCATTER);
-    k_compact_scatter<<<(n_upper + kThreads - 1) / kThreads, kThreads, 0, L.stream>>>(src, keep, block_offsets, n_dev,
-                                                                                   n_upper, dst, base_dev, cap,
-                                                                                   0xffffffffu);
   }
 }
 

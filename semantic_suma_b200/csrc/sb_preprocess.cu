@@ -12,22 +12,6 @@
 namespace sb {
 using namespace sbm;
 
-__global__ void k_fill_u64(unsigned long long* p, unsigned long long v, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) p[i] = v;
-}
-
-void launch_fill_u64(const Launch& L, unsigned long long* p, unsigned long long v, size_t n) {
-  int blocks = (int)((n + 1023) / 1024);
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  if (blocks < 1) blocks = 1;
-  {
-    ScopedKernel sk(L, K_FILL);
-    k_fill_u64<<<blocks, 256, 0, L.stream>>>(p, v, n);
-  }
-}
-
 // K1a: gen_vertexmap.vert:73-91 -- one thread per point, scatter-min into the key image
 __global__ void __launch_bounds__(256) k_project_scatter(KParams kp, const float4* __restrict__ pts, uint32_t n,
                                                          unsigned long long* __restrict__ keys) {
