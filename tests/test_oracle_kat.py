@@ -324,3 +324,25 @@ def test_movable_label_set_is_the_reference_shaders():
         src = open(os.path.join(root, path)).read()
         body = re.search(r"is_movable\(float l\)\s*\{(.*?)\}", src, flags=re.S).group(1)
         assert {float(x) for x in re.findall(r"l == ([\d.]+)f", body)} == movable, path
+
+
+def test_loop_closure_twin_bookkeeping_without_a_loop():
+    """oracle/orc_loop.cpp: with checkLoopClosure attached, a short straight drive records one odometry edge per scan,
+    never finds a candidate (nothing is 100 scans old) and leaves the poses untouched (SurfelMapping.cpp:460-471, 478-495)"""
+    p = O.default_params(**sized(360, 32))
+    sc, poses = scans(360, 32, n=5)
+    a, b = O.Slam(p), O.Slam(p)
+    b.enable_loop_closure(search_distance=3.0, min_trajectory_distance=1.0, min_verifications=1)
+    for s in sc:
+        a.process_scan(*s)
+        b.process_scan(*s)
+    assert np.array_equal(a.pose(), b.pose())
+    li = b.loop_info()
+    assert (li["n_edges"], li["n_poses"], li["candidates_tested"], li["found_candidate"]) == (4, 5, 0, 0)
+    assert li["time_without_loop_closure"] == 4
+    edges = b.loop_edges()
+    assert [(f, t) for f, t, _ in edges] == [(0, 1), (1, 2), (2, 3), (3, 4)]
+    chain = np.eye(4)
+    for _, _, rel in edges:
+        chain = chain @ rel
+    assert np.allclose(chain, b.pose(), atol=1e-9)
