@@ -270,13 +270,22 @@ def run_native(args, w, rank, world, local_rank):
         preroll(dev, True)
         ctx.profile(True)
         s_sum = 0
+        per_step_prof = []
         for i in range(args.steps):
             with torch.cuda.stream(stream):
                 flush.zero_()
             s_sum += slam.getMap().size()
             feed(dev, pre + i, True)
-        prof = ctx.profile_collect()
+            per_step_prof.append(ctx.profile_collect())
         ctx.profile(False)
+        # per kernel class: median over the steps of the step's mean launch time (one disturbed launch -- another
+        # process initialising on the box, a clock sample -- must not move a 15 us kernel's figure), times its launches
+        prof = {}
+        for k in {k for st in per_step_prof for k in st}:
+            per = [st[k][0] / st[k][1] for st in per_step_prof if k in st and st[k][1] > 0]
+            cnt = sum(st[k][1] for st in per_step_prof if k in st)
+            if per and cnt:
+                prof[k] = (statistics.median(per) * cnt, cnt)
         tot = sum(v[0] for v in prof.values())
         P = w["width"] * w["height"]
         S_avg = s_sum / max(1, args.steps)
@@ -308,6 +317,8 @@ def run_native(args, w, rank, world, local_rank):
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                     "avg_launch_us": round(us, 2), "surfels_avg": int(S_avg),
                     "step_share": kernel_table[top]["share"]}
+    if dist is not None:
+        dist.barrier()  # the other ranks stay quiet while rank 0 takes the per-kernel times
     slam.ctx.close()
     del dev, pin
     torch.cuda.empty_cache()

@@ -577,49 +577,48 @@ __device__ void gn_step_warp(GnShared& sh, long long raw, int lane, double last_
   __syncwarp();
 }
 
-// lane-parallel one-shot all-reduce of the 32 sums over the ranks' peer-mapped mailboxes (warp 0 of the last block):
-// every rank stores its sums + an epoch stamp into slot [epoch&1][rank] of EVERY rank's mailbox (plain stores over
-// NVLink), then waits for the stamps of all ranks in its own mailbox. Returns false on timeout.
+// lane-parallel one-shot all-reduce of the 32 sums over the ranks' peer-mapped mailboxes (warp 0 of the last block).
+// Every rank stores its sums into slot [epoch&1][rank] of EVERY rank's mailbox as 64 self-validating 8-byte words
+// (32-bit half of a sum | epoch stamp << 32; an aligned 8-byte store arrives whole over NVLink), so no fence separates
+// payload and flag and the cost is ONE one-way store latency: each lane then spins on its own two words per source rank
+// in its local mailbox. Two slots: a rank can only be one exchange ahead of the slowest reader. False on timeout.
 __device__ bool comm_allreduce32_warp(const CommDev& cd, long long& raw, int lane) {
-  int epoch = 0;
+  unsigned int epoch = 0;
   if (lane == 0) {
-    epoch = (int)(*cd.epoch) + 1;  // stamps start at 1: a zeroed mailbox never matches
-    *cd.epoch = (unsigned int)epoch;
+    epoch = *cd.epoch + 1u;  // stamps start at 1: a zeroed mailbox never matches
+    *cd.epoch = epoch;
   }
   epoch = __shfl_sync(0xffffffffu, epoch, 0);
-  const int slot = epoch & 1;
+  const int slot = (int)(epoch & 1u);
+  const unsigned long long tag = (unsigned long long)epoch << 32;
+  const unsigned long long w_lo = tag | (unsigned long long)(unsigned int)((unsigned long long)raw & 0xffffffffull);
+  const unsigned long long w_hi = tag | (unsigned long long)(unsigned int)((unsigned long long)raw >> 32);
   for (int r = 0; r < cd.nranks; ++r) {
-    volatile long long* dst = cd.mailbox[r] + ((size_t)(slot * 8 + cd.rank)) * 40;
-    dst[lane] = raw;
+    volatile unsigned long long* dst =
+        reinterpret_cast<volatile unsigned long long*>(cd.mailbox[r]) + ((size_t)(slot * 8 + cd.rank)) * 64;
+    dst[lane] = w_lo;
+    dst[32 + lane] = w_hi;
   }
-  __threadfence_system();
-  __syncwarp();
+  volatile unsigned long long* mine = reinterpret_cast<volatile unsigned long long*>(cd.mailbox[cd.rank]);
+  const unsigned long long t0 = globaltimer_ns();
+  unsigned long long tot = 0;
   int ok = 1;
-  if (lane == 0) {
-    for (int r = 0; r < cd.nranks; ++r) {
-      volatile long long* dst = cd.mailbox[r] + ((size_t)(slot * 8 + cd.rank)) * 40;
-      dst[32] = (long long)epoch;
-    }
-    __threadfence_system();
-    volatile long long* mine = cd.mailbox[cd.rank];
-    const unsigned long long t0 = globaltimer_ns();
-    for (int r = 0; r < cd.nranks && ok; ++r) {
-      volatile long long* src = mine + ((size_t)(slot * 8 + r)) * 40;
-      unsigned int spins = 0;
-      while (src[32] != (long long)epoch) {
-        if ((++spins & 1023u) == 0u && globaltimer_ns() - t0 > kSpinTimeoutNs) {
-          ok = 0;
-          break;
-        }
+  for (int r = 0; r < cd.nranks && ok; ++r) {
+    volatile unsigned long long* src = mine + ((size_t)(slot * 8 + r)) * 64;
+    unsigned long long lo = src[lane], hi = src[32 + lane];
+    unsigned int spins = 0;
+    while ((unsigned int)(lo >> 32) != epoch || (unsigned int)(hi >> 32) != epoch) {
+      if ((++spins & 1023u) == 0u && globaltimer_ns() - t0 > kSpinTimeoutNs) {
+        ok = 0;
+        break;
       }
+      lo = src[lane];
+      hi = src[32 + lane];
     }
-    __threadfence_system();
+    tot += (lo & 0xffffffffull) | (hi << 32);
   }
-  ok = __shfl_sync(0xffffffffu, ok, 0);
-  long long tot = 0;
-  volatile long long* mine = cd.mailbox[cd.rank];
-  for (int r = 0; r < cd.nranks; ++r) tot += mine[((size_t)(slot * 8 + r)) * 40 + lane];
-  raw = tot;
+  ok = __all_sync(0xffffffffu, ok);
+  raw = (long long)tot;
   return ok != 0;
 }
 
@@ -632,8 +631,11 @@ __device__ __forceinline__ void load_mat_cg(const float* table, int idx, float* 
   M[12] = d.x; M[13] = d.y; M[14] = d.z; M[15] = d.w;
 }
 
-constexpr int kGnCachePix = 2;  // data pixels per thread kept in shared memory across the iterations of one launch
-
+// kGnCachePix = data pixels per thread kept in shared memory across the iterations of one launch: 2 covers 64x2048 on
+// one GPU (1.7 pixels per thread); 4 is the instantiation a row stripe of a larger image takes (128x4096 over >= 2 GPUs
+// -- the aggregate shared memory of the GPUs holds what one GPU's does not). Measured: the 4-deep unrolled body costs the
+// 64x2048 launch 3.5 us, hence two instantiations instead of one.
+template <int kGnCachePix>
 __global__ void __launch_bounds__(kIcpThreads, 2) k_gn_persistent(KParams kp, GnJob job, long long* __restrict__ slots,
                                                                unsigned int* ticket, unsigned int* epoch_flag,
                                                                unsigned long long* pub, CommDev cd) {
@@ -865,8 +867,10 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_gn_persistent(KParams kp, Gn
 
 int gn_persistent_max_blocks(int sm_count) {
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gn_persistent, kIcpThreads, 0) != cudaSuccess) return 0;
-  return per_sm * sm_count;
+  int per_sm4 = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gn_persistent<2>, kIcpThreads, 0) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4, k_gn_persistent<4>, kIcpThreads, 0) != cudaSuccess) return 0;
+  return (per_sm < per_sm4 ? per_sm : per_sm4) * sm_count;
 }
 
 int launch_gn_persistent(const Launch& L, const KParams& kp, const GnJob& job, long long* slots, unsigned int* ticket,
@@ -884,7 +888,11 @@ int launch_gn_persistent(const Launch& L, const KParams& kp, const GnJob& job, l
   cudaError_t e;
   {
     ScopedKernel sk(L, job.mode == GN_POST ? K_ICP_POST : K_ICP_FUSED);
-    e = cudaLaunchCooperativeKernel((void*)k_gn_persistent, dim3(blocks), dim3(kIcpThreads), args, 0, L.stream);
+    // the deeper cache only where the shallow one does not hold the stripe but the deep one does
+    const long long px = (long long)(job.a.row_end - job.a.row_begin) * kp.W, per_pass = (long long)blocks * kIcpThreads;
+    const bool deep = job.use_cache && job.mode != GN_POST && px > 2 * per_pass && px <= 4 * per_pass;
+    e = cudaLaunchCooperativeKernel(deep ? (void*)k_gn_persistent<4> : (void*)k_gn_persistent<2>, dim3(blocks),
+                                    dim3(kIcpThreads), args, 0, L.stream);
   }
   return e == cudaSuccess ? 0 : -1;
 }

@@ -604,19 +604,9 @@ void launch_render_scatter(const Launch& L, const KParams& kp, SurfelPlanes s, c
   {
     ScopedKernel sk(L, K_RENDER_SCATTER);
     const unsigned grid = (n_upper + kRenderThreads - 1) / kRenderThreads;
-    // resident blocks per SM the register allocation aims at (2: 110 registers, 3: 80, 4: 64 with a few spills);
-    // TEMPORARY measurement switch, the winner becomes the only instantiation
-    static int occ = -1;
-    if (occ < 0) {
-      const char* e = getenv("SUMA_B200_RENDER_OCC");
-      occ = e ? atoi(e) : 4;
-    }
-    if (occ == 5)
-      k_render_scatter<5><<<grid, kRenderThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr, emit_old, emit_new, lequal, t);
-    else if (occ == 4)
-      k_render_scatter<4><<<grid, kRenderThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr, emit_old, emit_new, lequal, t);
-    else
-      k_render_scatter<3><<<grid, kRenderThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr, emit_old, emit_new, lequal, t);
+    // 4 resident blocks per SM (64 registers, 46.6 KB shared memory): measured against 3 and 5 at S = 10^6
+    // (profiles/r02_microbench_*), occupancy pays more than the few spills cost
+    k_render_scatter<4><<<grid, kRenderThreads, 0, L.stream>>>(kp, s, n_dev, M, conf_thr, t_thr, emit_old, emit_new, lequal, t);
   }
 }
 
