@@ -14,6 +14,7 @@ timed region). Every pass first pre-rolls the map with --preroll scans (steady-s
 all-reduce) on the same GPUs, against the same sequence without striping. Prints ONE JSON line on rank 0.
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -105,13 +106,19 @@ class ClockSampler(threading.Thread):
         f = [x.strip() for x in out.strip().split(",")]
         return [float(f[0]), float(f[1]), float(f[2])] + [x.lower().startswith("active") for x in f[3:7]]
 
-    def run(self):
+    def run(self):  # thread mode (not used by the timed passes any more, see sample_once)
         while not self.stop_flag:
-            try:
-                self.samples.append(self._sample_nvml() if self.nvml else self._sample_smi())
-            except Exception:  # noqa: BLE001
-                pass
-            time.sleep(0.005 if self.nvml else 0.2)
+            self.sample_once()
+            time.sleep(0.05 if self.nvml else 0.2)
+
+    def sample_once(self):
+        """One sample, taken synchronously by the caller BETWEEN two timed steps in the middle of the timed region (a
+        concurrent NVML thread polling every few ms during a 10 ms pass was the prime suspect for the isolated multi-ms
+        steps that the 4- and 8-GPU runs showed on single ranks -- eight processes queueing on the driver's global lock)."""
+        try:
+            self.samples.append(self._sample_nvml() if self.nvml else self._sample_smi())
+        except Exception:  # noqa: BLE001
+            pass
 
     def summary(self):
         if not self.samples:
@@ -179,6 +186,11 @@ def run_native(args, w, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # communicator set-up (lazy: first collective) long before anything is timed
+        warm = torch.zeros(1, device="cuda")
+        dist.all_reduce(warm)
+        dist.barrier()
+        torch.cuda.synchronize()
     pp = api.default_params(**param_kwargs(w))
     slam = api.SurfelMapping(pp, device=local_rank)
     ctx = slam.ctx
@@ -219,8 +231,9 @@ def run_native(args, w, rank, world, local_rank):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         launches0 = ctx.launch_count()
         barrier()
-        if sampler:
-            sampler.start()
+        host_split = []
+        gc_was = gc.isenabled()
+        gc.disable()  # no collector pause inside a 10 ms pass
         t_wall = time.time()
         for i in range(args.steps):
             with torch.cuda.stream(stream):
@@ -230,11 +243,20 @@ def run_native(args, w, rank, world, local_rank):
             if not on_device:
                 slam.getCurrentPose()  # the step's result, read on the host
             ev[i][1].record(stream)
+            st = slam.getStatistics()
+            host_split.append((st["preprocessing-time"], st["icp-time"], st["mapping-time"]))
+            if sampler and i == args.steps // 2:
+                sampler.sample_once()  # clocks / throttle reasons in the middle of the timed region, between two steps
         barrier()
         t_wall = time.time() - t_wall
-        if sampler:
-            sampler.stop_flag = True
+        if gc_was:
+            gc.enable()
         ms = [a.elapsed_time(b) for a, b in ev]
+        worst = max(range(len(ms)), key=lambda j: ms[j])
+        one_pass.worst_step = {"step": worst, "device_ms": round(ms[worst], 4),
+                               "host_enqueue_ms": round(1e3 * host_split[worst][0], 4),
+                               "host_wait_ms": round(1e3 * host_split[worst][1], 4),
+                               "host_post_ms": round(1e3 * host_split[worst][2], 4)}
         total_ms = worst_ms = float(sum(ms))
         if dist is not None:
             t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
@@ -251,13 +273,15 @@ def run_native(args, w, rank, world, local_rank):
             break
     sampler = ClockSampler(local_rank)
     ms_dev, launches, wall_dev, per_step = one_pass(dev, True, sampler)
+    worst_dev = dict(one_pass.worst_step)
     ms_e2e, _, wall_e2e, per_step_e2e = one_pass(pin, False)
     surfels = slam.getMap().size()
     gt = np.linalg.inv(synth.trajectory(1)[0]) @ synth.trajectory(n_frames)[-1]
     drift = float(np.linalg.norm(slam.getCurrentPose()[:3, 3] - gt[:3, 3]))
     mine = {"rank": rank, "step_ms_min_med_max": [round(min(per_step), 4), round(statistics.median(per_step), 4),
                                                   round(max(per_step), 4)],
-            "e2e_step_ms_med": round(statistics.median(per_step_e2e), 4), "clocks": sampler.summary(), "numa_cpus": numa}
+            "e2e_step_ms_med": round(statistics.median(per_step_e2e), 4), "slowest_step": worst_dev,
+            "clocks": sampler.summary(), "numa_cpus": numa}
     per_rank = [mine]
     if dist is not None:
         per_rank = [None] * world

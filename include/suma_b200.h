@@ -206,7 +206,9 @@ int sb_get_last_pose(sb_ctx* ctx, double pose[16]); /* getLastPose, core/SurfelM
 int sb_timestamp(sb_ctx* ctx, uint32_t* t);        /* timestamp() */
 int sb_slam_frame(sb_ctx* ctx, int which, sb_frame** out); /* getCurrentFrame / LastFrame / *ModelFrame (borrowed) */
 /* stats[16]: [0] icp iterations [1] F [2] inlier [3] outlier [4] invalid [5] inlier_residual [6] track losses
- * [7] surfels; wall seconds: [8] preprocessing [9] icp [10] mapping [11] complete (getStatistics keys);
+ * [7] surfels; wall seconds: [11] complete (getStatistics key "complete-time"); the reference's three stage timers have
+ * no counterpart -- the stages overlap on the stream -- so their slots [8] [9] [10] carry the host-side split of the
+ * call: enqueue / wait for the device / bookkeeping after the wait;
  * [12] surfels dropped because the HBM cache of extracted submap tiles (16 M surfels) was full -- the reference's
  * host-side submapCache_ is unbounded; sb_last_error carries the message */
 int sb_get_statistics(sb_ctx* ctx, double stats[16]);

@@ -74,7 +74,7 @@ struct sb_ctx {
   int icp_coop_blocks = 0;  // > 0: the persistent cooperative Gauss-Newton kernel is available
   unsigned int epoch_base = 1;  // epoch words of the persistent GN kernel: each launch owns a fresh range of values
   unsigned long long* gn_pub = nullptr;  // 32 (half pose value, epoch tag) words published by every Gauss-Newton step
-  int gn_use_ll = 1, gn_use_cache = 1;   // SUMA_B200_GN_LL / SUMA_B200_GN_CACHE = 0 select the round-1 hand-over / reloads
+  int gn_use_cache = 1;                  // SUMA_B200_GN_CACHE = 0: reload the data texels every iteration (measurement switch)
   // loop closure (SurfelMapping::checkLoopClosure; include/suma_b200_loop.hpp): off unless sb_set_loop_closure enables it
   bool close_loops = false;
   suma_b200::loop::State loop;
@@ -347,7 +347,6 @@ int alloc_buffers(sb_ctx* c) {
   SB_CUDA(c, cudaMalloc(&c->ticket, 128));
   SB_CUDA(c, cudaMalloc(&c->gn_pub, 64 * 8));
   SB_CUDA(c, cudaMemsetAsync(c->gn_pub, 0, 64 * 8, c->stream));
-  if (const char* e = getenv("SUMA_B200_GN_LL")) c->gn_use_ll = atoi(e) != 0;
   if (const char* e = getenv("SUMA_B200_GN_CACHE")) c->gn_use_cache = atoi(e) != 0;
   SB_CUDA(c, cudaMemsetAsync(c->ticket, 0, 128, c->stream));
   SB_CUDA(c, cudaMallocHost(&c->h_pinned, 65536));
@@ -516,6 +515,16 @@ int render_single(sb_ctx* c, const float* pose, float conf_thr, int which, const
 // ---------------------------------------------------------------------------------------------------------
 // every launch of the persistent Gauss-Newton kernel publishes epoch values base+1 .. base+max_iter+2: hand out disjoint
 // ranges so that the epoch word never has to be reset between launches
+// A Gauss-Newton launch that gave up (bounded spin: a block or a peer GPU never arrived) leaves its arrival ticket and
+// accumulator replicas mid-pass: return them to the state every launch starts from, so that the context stays usable.
+int gn_fail(sb_ctx* c) {
+  cudaMemsetAsync(c->ticket, 0, 128, c->stream);
+  cudaMemsetAsync(c->acc_slots, 0, 1024 * 32 * sizeof(long long), c->stream);
+  cudaMemsetAsync(&c->pd->gn_error, 0, sizeof(int), c->stream);
+  cudaStreamSynchronize(c->stream);
+  return fail(c, SB_ERR_STATE, "Gauss-Newton kernel timed out waiting for a block or a peer GPU");
+}
+
 unsigned int next_epoch_base(sb_ctx* c, int max_iter) {
   unsigned int b = c->epoch_base;
   c->epoch_base += (unsigned int)max_iter + 8u;
@@ -651,9 +660,8 @@ int icp_minimize_enqueue(sb_ctx* c, const sb_frame* data, const sb_frame* model,
     job.eps = eps;
     job.delta = delta;
     job.epoch_base = next_epoch_base(c, max_iter);
-    job.use_ll = c->gn_use_ll;
     job.use_cache = c->gn_use_cache;
-    if (launch_gn_persistent(L, c->kp, job, c->acc_slots, c->ticket, c->ticket + 8, c->gn_pub, c->comm_on ? &c->comm : nullptr,
+    if (launch_gn_persistent(L, c->kp, job, c->acc_slots, c->ticket, c->gn_pub, c->comm_on ? &c->comm : nullptr,
                              c->icp_coop_blocks) == 0)
       return SB_OK;
     cudaGetLastError();
@@ -668,7 +676,7 @@ int icp_minimize_fetch(sb_ctx* c, double* pose_out, double* out48, int* iters, d
   SB_CUDA(c, cudaStreamSynchronize(c->stream));
   GnHead h;
   memcpy(&h, c->h_pinned, sizeof(h));
-  if (h.error) return fail(c, SB_ERR_STATE, "Gauss-Newton kernel timed out waiting for a block or a peer GPU");
+  if (h.error) return gn_fail(c);
   if (pose_out) memcpy(pose_out, h.pose, sizeof(h.pose));
   if (out48) memcpy(out48, h.out48, sizeof(h.out48));
   if (iters) *iters = h.k;
@@ -984,9 +992,8 @@ int update_pose_enqueue(sb_ctx* c, bool* tables_ready) {
     job.eps = p.stopping_threshold;
     job.delta = p.delta;
     job.epoch_base = next_epoch_base(c, max_iter);
-    job.use_ll = c->gn_use_ll;
     job.use_cache = c->gn_use_cache;
-    if (launch_gn_persistent(L, c->kp, job, c->acc_slots, c->ticket, c->ticket + 8, c->gn_pub, c->comm_on ? &c->comm : nullptr,
+    if (launch_gn_persistent(L, c->kp, job, c->acc_slots, c->ticket, c->gn_pub, c->comm_on ? &c->comm : nullptr,
                              c->icp_coop_blocks) != 0) {
       cudaGetLastError();
       return fail(c, SB_ERR_CUDA, "cooperative launch of the Gauss-Newton kernel failed");
@@ -1014,9 +1021,8 @@ int update_pose_enqueue(sb_ctx* c, bool* tables_ready) {
     post.eps = p.stopping_threshold;
     post.delta = p.delta;
     post.epoch_base = next_epoch_base(c, max_iter);
-    post.use_ll = c->gn_use_ll;
     post.use_cache = 0;
-    if (launch_gn_persistent(L, c->kp, post, c->acc_slots, c->ticket, c->ticket + 8, c->gn_pub, c->comm_on ? &c->comm : nullptr,
+    if (launch_gn_persistent(L, c->kp, post, c->acc_slots, c->ticket, c->gn_pub, c->comm_on ? &c->comm : nullptr,
                              c->icp_coop_blocks) != 0) {
       cudaGetLastError();
       return fail(c, SB_ERR_CUDA, "cooperative launch of the Gauss-Newton kernel failed");
@@ -1130,10 +1136,12 @@ int loop_closure_step(sb_ctx* c) {
   if (c->comm_on || c->comm_cb) return fail(c, SB_ERR_STATE, "loop closure is not available in row-striped multi-GPU mode");
   char* hp = (char*)c->h_pinned;
   SB_CUDA(c, cudaMemcpyAsync(hp, c->result_block, 8192 + 64, cudaMemcpyDeviceToHost, c->stream));
+  const double t_enqueued = now_s();
   SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  const double t_synced = now_s();
   PoseDev pdh;
   memcpy(&pdh, hp, sizeof(pdh));
-  if (pdh.gn_error) return fail(c, SB_ERR_STATE, "Gauss-Newton kernel timed out waiting for a block or a peer GPU");
+  if (pdh.gn_error) return gn_fail(c);
   absorb_pose_block(c, pdh, hp, true);
   lp::Poses P;
   memcpy(P.current.m, c->currentPose, 128);
@@ -1590,11 +1598,13 @@ int sb_process_scan(sb_ctx* c, const float* pts4, const float* labels, const flo
   // ---- the scan's results: pose block, statistics sums, surfel counts ----
   char* hp = (char*)c->h_pinned;
   SB_CUDA(c, cudaMemcpyAsync(hp, c->result_block, 8192 + 64, cudaMemcpyDeviceToHost, c->stream));
+  const double t_enqueued = now_s();
   SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  const double t_synced = now_s();
   SB_CUDA(c, cudaGetLastError());
   PoseDev pdh;
   memcpy(&pdh, hp, sizeof(pdh));
-  if (pdh.gn_error) return fail(c, SB_ERR_STATE, "Gauss-Newton kernel timed out waiting for a block or a peer GPU");
+  if (pdh.gn_error) return gn_fail(c);
   if (!loop_ran) absorb_pose_block(c, pdh, hp, had_icp);  // (the loop-closure step has already done it, and chose currentPose_old_)
   uint32_t cnt[4];
   memcpy(cnt, hp + 8192, sizeof(cnt));
@@ -1629,8 +1639,13 @@ int sb_process_scan(sb_ctx* c, const float* pts4, const float* labels, const flo
     }
   }
   c->stats[7] = c->n_host;
-  c->stats[11] = now_s() - t_all;
-  c->stats[8] = c->stats[9] = c->stats[10] = 0.0;  // stages overlap on the stream; only complete-time is meaningful
+  // The reference's three stage timers (preprocessing / icp / mapping) have no meaning here -- the stages overlap on
+  // the stream; the slots carry the host-side split of the call instead: enqueue, wait for the device, bookkeeping.
+  const double t_end = now_s();
+  c->stats[8] = t_enqueued - t_all;
+  c->stats[9] = t_synced - t_enqueued;
+  c->stats[10] = t_end - t_synced;
+  c->stats[11] = t_end - t_all;
   c->timestamp += 1;
   return SB_OK;
 }

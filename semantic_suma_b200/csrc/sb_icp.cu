@@ -241,18 +241,19 @@ __device__ __forceinline__ void block_reduce_to_replica(Acc& acc, long long* __r
   }
 }
 
-// executed by warp 0 of the last block: lane l returns the total of value l over the replicas and clears them
-__device__ __forceinline__ long long sum_replicas(long long* __restrict__ replicas, int lane) {
+// executed by warp 0 of the last block: lane l returns the total of value l over the replicas
+__device__ __forceinline__ long long sum_replicas(const long long* __restrict__ replicas, int lane) {
   long long r[kAccReplicas];
 #pragma unroll
-  for (int i = 0; i < kAccReplicas; ++i) r[i] = *(volatile long long*)(replicas + (size_t)i * 32 + lane);
+  for (int i = 0; i < kAccReplicas; ++i) r[i] = *(const volatile long long*)(replicas + (size_t)i * 32 + lane);
   long long tot = 0;
 #pragma unroll
-  for (int i = 0; i < kAccReplicas; ++i) {
-    tot += r[i];
-    replicas[(size_t)i * 32 + lane] = 0;
-  }
+  for (int i = 0; i < kAccReplicas; ++i) tot += r[i];
   return tot;
+}
+__device__ __forceinline__ void clear_replicas(long long* __restrict__ replicas, int lane) {
+#pragma unroll
+  for (int i = 0; i < kAccReplicas; ++i) replicas[(size_t)i * 32 + lane] = 0;
 }
 
 __device__ __forceinline__ void icp_accumulate(const KParams& kp, const IcpArgs& a, const float* M, int iteration,
@@ -286,6 +287,7 @@ __global__ void __launch_bounds__(kIcpThreads) k_icp_jacobian(KParams kp, IcpArg
   if (!is_last || threadIdx.x >= 32) return;
   __threadfence();
   long long tot = sum_replicas(slots, threadIdx.x);
+  clear_replicas(slots, threadIdx.x);
   g_acc[threadIdx.x] = tot;
   if (threadIdx.x == 0) *ticket = 0;
 }
@@ -637,11 +639,12 @@ __device__ __forceinline__ void load_mat_cg(const float* table, int idx, float* 
 // 64x2048 launch 3.5 us, hence two instantiations instead of one.
 template <int kGnCachePix>
 __global__ void __launch_bounds__(kIcpThreads, 2) k_gn_persistent(KParams kp, GnJob job, long long* __restrict__ slots,
-                                                               unsigned int* ticket, unsigned int* epoch_flag,
-                                                               unsigned long long* pub, CommDev cd) {
+                                                               unsigned int* ticket, unsigned long long* pub,
+                                                               CommDev cd) {
   __shared__ GnShared sh;
   __shared__ bool is_last;
   __shared__ double s_pose[16];
+  __shared__ double s_last_error;  // travels with the pose: the block that performs the next step is not the same one
   __shared__ int s_done, s_error;
   __shared__ float4 s_dv[kGnCachePix][kIcpThreads], s_dn[kGnCachePix][kIcpThreads];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -683,46 +686,35 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_gn_persistent(KParams kp, Gn
           }
           if (lane == 17) s_done = 0;
         }
-      } else if (job.use_ll) {
+      } else {
         // The step publishes the new pose as 32 self-validating 8-byte words (half a double + the epoch tag, bit 31 of the
         // tag = done): lane l polls word l, so pose AND release arrive in ONE L2 round trip (a flag followed by a fetch
-        // of the pose costs two).
+        // of the pose costs two) and no fence is needed on either side of the hand-over.
         const unsigned int want = (job.epoch_base + it) & 0x7fffffffu;
         const unsigned long long t0 = globaltimer_ns();
         unsigned int spins = 0;
         unsigned long long w = *(volatile unsigned long long*)&pub[lane];
+        unsigned long long w2 = lane < 2 ? *(volatile unsigned long long*)&pub[32 + lane] : 0ull;  // last_error halves
         bool timed_out = false;
-        while ((((unsigned int)(w >> 32)) & 0x7fffffffu) != want) {
+        while ((((unsigned int)(w >> 32)) & 0x7fffffffu) != want ||
+               (lane < 2 && (((unsigned int)(w2 >> 32)) & 0x7fffffffu) != want)) {
           if ((++spins & 4095u) == 0u && globaltimer_ns() - t0 > kSpinTimeoutNs) {
             timed_out = true;
             break;
           }
           w = *(volatile unsigned long long*)&pub[lane];
+          if (lane < 2) w2 = *(volatile unsigned long long*)&pub[32 + lane];
         }
         if (__any_sync(0xffffffffu, timed_out)) {
           if (lane == 0) s_error = 1;
         }
-        __threadfence();
         const unsigned int lo = __shfl_sync(0xffffffffu, (unsigned int)w, 2 * (lane & 15));
         const unsigned int hi = __shfl_sync(0xffffffffu, (unsigned int)w, 2 * (lane & 15) + 1);
         if (lane < 16) s_pose[lane] = __hiloint2double((int)hi, (int)lo);
         if (lane == 17) s_done = (int)((w >> 63) & 1ull);
-      } else {
-        if (lane == 0) {
-          const unsigned int want = job.epoch_base + it;
-          const unsigned long long t0 = globaltimer_ns();
-          unsigned int spins = 0;
-          while (*(volatile unsigned int*)epoch_flag != want) {
-            if ((++spins & 4095u) == 0u && globaltimer_ns() - t0 > kSpinTimeoutNs) {
-              s_error = 1;
-              break;
-            }
-          }
-          __threadfence();
-        }
-        __syncwarp();
-        if (lane < 16) s_pose[lane] = *(volatile double*)&st->pose[lane];
-        if (lane == 17) s_done = *(volatile int*)&st->done;
+        const unsigned int e_lo = __shfl_sync(0xffffffffu, (unsigned int)w2, 0);
+        const unsigned int e_hi = __shfl_sync(0xffffffffu, (unsigned int)w2, 1);
+        if (lane == 18) s_last_error = __hiloint2double((int)e_hi, (int)e_lo);
       }
     }
     __syncthreads();
@@ -733,7 +725,15 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_gn_persistent(KParams kp, Gn
       }
       return;
     }
-    if (s_done) break;
+    if (s_done) {
+      __threadfence();  // the finishing step fenced its pose-block writes before the done tag; acquire them
+      break;
+    }
+    // Two sets of accumulator replicas, alternating per pass: the set of pass p is cleared by the block that consumed it
+    // AFTER it has released pass p + 1 (nobody adds to it before pass p + 2, and that block's own arrival fence of pass
+    // p + 1 orders the clearing stores before the release of p + 2). The arrival ticket counts on across the passes of a
+    // launch for the same reason: no reset, hence no fence, between the step and the release.
+    long long* const my_slots = slots + (size_t)(it & 1u) * kAccReplicas * 32;
     const bool stats_pass = job.mode == GN_POST && it == 0;
     const bool recovery = job.mode == GN_POST && it > 0;
     const int k = job.mode == GN_POST ? (int)it - 1 : (int)it;  // k_ of LieGaussNewton: one increment per completed step
@@ -754,24 +754,28 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_gn_persistent(KParams kp, Gn
       icp_accumulate(kp, recovery ? job.fb : job.a, M, stats_pass ? 0 : k, acc);
     }
     __syncthreads();
-    block_reduce_to_replica(acc, slots);
+    block_reduce_to_replica(acc, my_slots);
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();  // cumulative: orders this block's slot adds (observed through the barrier) before the ticket
       unsigned int t = atomicAdd(ticket, 1u);
-      is_last = (t == gridDim.x - 1);
+      is_last = (t == (it + 1u) * gridDim.x - 1u);
     }
     __syncthreads();
     if (is_last && warp == 0) {
       __threadfence();
-      long long raw = sum_replicas(slots, lane);
+      long long raw = sum_replicas(my_slots, lane);
       int done = 0, error = 0;
+      double pv = 0.0;  // lanes 0..15: the pose of the next pass
       if (stats_pass) {
         // result_new_ (SurfelMapping.cpp:415-423): the host unpacks these 32 sums after the scan
         job.stats32[lane] = raw;
         const int fb = job.fallback_mode ? *(volatile int*)&pd->fallback : 0;
         if (fb) {  // recovery_->setData(currentFrame_, lastFrame_); gn_->minimize(*recovery_, T0)   :442-444
-          if (lane < 16) st->pose[lane] = pd->T0[lane];
+          if (lane < 16) {
+            pv = pd->T0[lane];
+            st->pose[lane] = pv;
+          }
           if (lane == 0) {
             st->last_error = (double)3.402823466e+38f;
             st->k = 0;
@@ -782,8 +786,7 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_gn_persistent(KParams kp, Gn
         }
       } else {
         double last_error = (double)3.402823466e+38f;  // LieGaussNewton.cpp:48
-        if (k > 0 && lane == 16) last_error = *(volatile double*)&st->last_error;
-        last_error = __shfl_sync(0xffffffffu, last_error, 16);
+        if (k > 0) last_error = s_last_error;          // published with the pose by the previous step
         if (cd.epoch) error = comm_allreduce32_warp(cd, raw, lane) ? 0 : 1;
         if (lane < 16) sh.P[lane] = s_pose[lane];
         int hl = k;  // one pose has been pushed per completed iteration
@@ -791,7 +794,10 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_gn_persistent(KParams kp, Gn
         ++hl;
         __syncwarp();
         gn_step_warp(sh, raw, lane, last_error, job.eps, job.delta);
-        if (lane < 16) st->pose[lane] = sh.P[lane];
+        if (lane < 16) {
+          pv = sh.P[lane];
+          st->pose[lane] = pv;
+        }
         for (int i = lane; i < 48; i += 32) st->out48[i] = sh.O[i];
         int kk = k;
         if (sh.result == 0) {
@@ -827,20 +833,26 @@ __global__ void __launch_bounds__(kIcpThreads, 2) k_gn_persistent(KParams kp, Gn
           if (pd) pd->gn_error = 1;
         }
         st->done = done;
-        *ticket = 0;
+        if (done) *ticket = 0;  // the next launch counts from 0 again
       }
-      __threadfence();
+      if (done) {  // the finishing step: every write of this launch is visible before the done tag
+        clear_replicas(my_slots, lane);
+        __threadfence();
+      }
       __syncwarp();
-      if (job.use_ll) {
-        double pv = 0.0;
-        if (lane < 16) pv = *(volatile double*)&st->pose[lane];  // the pose of the next pass (just written by this warp)
+      // release: the pose straight from the registers of this warp (the state stores above drain in the background)
+      {
         const double src = __shfl_sync(0xffffffffu, pv, lane >> 1);
         const unsigned int half = (lane & 1) ? (unsigned int)__double2hiint(src) : (unsigned int)__double2loint(src);
         const unsigned int tag = ((job.epoch_base + it + 1u) & 0x7fffffffu) | (done ? 0x80000000u : 0u);
         *(volatile unsigned long long*)&pub[lane] = ((unsigned long long)tag << 32) | (unsigned long long)half;
-      } else if (lane == 0) {
-        atomicExch(epoch_flag, job.epoch_base + it + 1u);
+        if (lane < 2) {
+          const double le = stats_pass ? 0.0 : sh.O[43];  // this step's error = last_error of the next one
+          const unsigned int eh = lane ? (unsigned int)__double2hiint(le) : (unsigned int)__double2loint(le);
+          *(volatile unsigned long long*)&pub[32 + lane] = ((unsigned long long)tag << 32) | (unsigned long long)eh;
+        }
       }
+      if (!done) clear_replicas(my_slots, lane);  // behind the release, see above
     }
     // The last block's other warps wait for the step HERE, not at the loop-top barrier (is_last is block-uniform).
     if (is_last) __syncthreads();
@@ -874,7 +886,7 @@ int gn_persistent_max_blocks(int sm_count) {
 }
 
 int launch_gn_persistent(const Launch& L, const KParams& kp, const GnJob& job, long long* slots, unsigned int* ticket,
-                         unsigned int* epoch_flag, unsigned long long* pub, const CommDev* comm, int blocks) {
+                         unsigned long long* pub, const CommDev* comm, int blocks) {
   CommDev cd;
   if (comm) {
     cd = *comm;
@@ -884,7 +896,7 @@ int launch_gn_persistent(const Launch& L, const KParams& kp, const GnJob& job, l
   }
   KParams kpv = kp;
   GnJob jv = job;
-  void* args[] = {&kpv, &jv, &slots, &ticket, &epoch_flag, &pub, &cd};
+  void* args[] = {&kpv, &jv, &slots, &ticket, &pub, &cd};
   cudaError_t e;
   {
     ScopedKernel sk(L, job.mode == GN_POST ? K_ICP_POST : K_ICP_FUSED);

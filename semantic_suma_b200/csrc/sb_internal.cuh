@@ -187,12 +187,11 @@ struct GnJob {
   int max_iter;
   double eps, delta;
   unsigned int epoch_base;
-  int use_ll;     // publish the pose as self-validating (value, tag) words: one L2 round trip per iteration hand-over
   int use_cache;  // keep the thread's data pixels in shared memory across iterations
 };
 void launch_gn_init(const Launch& L, GnState* st, const Mat4d& T0, long long* acc32);
 int launch_gn_persistent(const Launch& L, const KParams& kp, const GnJob& job, long long* slots, unsigned int* ticket,
-                         unsigned int* epoch_flag, unsigned long long* pub, const CommDev* comm, int blocks);
+                         unsigned long long* pub, const CommDev* comm, int blocks);
 int gn_persistent_max_blocks(int sm_count);
 // one-thread bookkeeping kernels: first scan of a sequence and the host-callback exchange
 void launch_pose_after_icp(const Launch& L, const GnState* gn, PoseDev* pd, const Mat4d& T0, uint32_t timestamp,
