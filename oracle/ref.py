@@ -160,3 +160,129 @@ class Map:
         self.L.ref_map_get_update_debug(self.h, _p(idx, C.c_uint32), _p(rad), _p(integ, C.c_uint8), C.byref(nu),
                                         C.byref(nn))
         return idx, rad, integ, nu.value, nn.value
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# libsuma_ref_host.so: the reference's own HOST sources (core/lie_algebra.cpp, core/LieGaussNewton.cpp + Objective.h,
+# util/kitti_utils.cpp, rv/ParameterList + XML parser) compiled where they lie against stand-ins for Eigen / Boost
+# (oracle/ref_harness/host/). Compared within tolerances, never bit for bit: Eigen's own operation order is not ours.
+# ------------------------------------------------------------------------------------------------------------------
+def host_available():
+    return have_reference() or os.path.exists(lib_path("host"))
+
+
+_host = None
+PRODUCTS_FN = C.CFUNCTYPE(C.c_double, C.c_void_p, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double),
+                          C.POINTER(C.c_double))
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        build()
+        L = C.CDLL(lib_path("host"))
+        L.ref_kitti_rotation_error.restype = C.c_float
+        L.ref_kitti_translation_error.restype = C.c_float
+        _host = L
+    return _host
+
+
+def se3_exp(x):
+    x = np.ascontiguousarray(x, np.float64); T = np.zeros(16, np.float64)
+    host_lib().ref_se3_exp(_p(x, C.c_double), _p(T, C.c_double))
+    return O.from_colmajor(T)
+
+
+def se3_log(T):
+    Tc = colmajor(T, np.float64); x = np.zeros(6, np.float64)
+    host_lib().ref_se3_log(_p(Tc, C.c_double), _p(x, C.c_double))
+    return x
+
+
+def gn_minimize(products, T0, max_iter, eps, delta, hist_cap=512):
+    """LieGaussNewton::minimize of the reference on an objective whose jacobianProducts is `products(pose 4x4, iteration)
+    -> (JtJ 6x6, Jtf 6, F)`. Returns dict(pose, history, iterations, residual, ret)."""
+    def cb(_user, pose, iteration, A, b):
+        P = O.from_colmajor(np.array([pose[i] for i in range(16)], np.float64))
+        JtJ, Jtf, F = products(P, iteration)
+        JtJ = np.asarray(JtJ, np.float64); Jtf = np.asarray(Jtf, np.float64).reshape(6)
+        for c in range(6):
+            for r in range(6):
+                A[6 * c + r] = JtJ[r, c]
+        for r in range(6):
+            b[r] = Jtf[r]
+        return float(F)
+
+    fn = PRODUCTS_FN(cb)
+    pose = np.zeros(16, np.float64); hist = np.zeros(16 * hist_cap, np.float64)
+    hl, it, res = C.c_int(0), C.c_int(0), C.c_double(0)
+    ret = host_lib().ref_gn_minimize(fn, None, _p(colmajor(T0, np.float64), C.c_double), C.c_int(max_iter),
+                                     C.c_double(eps), C.c_double(delta), _p(pose, C.c_double), _p(hist, C.c_double),
+                                     C.c_int(hist_cap), C.byref(hl), C.byref(it), C.byref(res))
+    return {"pose": O.from_colmajor(pose), "history": [O.from_colmajor(hist[16 * i:16 * i + 16]) for i in range(min(hl.value, hist_cap))],
+            "history_len": hl.value, "iterations": it.value, "residual": res.value, "ret": ret}
+
+
+def param_lookup(xml_file, name):
+    buf = C.create_string_buffer(4096)
+    r = host_lib().ref_param_lookup(str(xml_file).encode(), name.encode(), buf, C.c_int(4096))
+    return buf.value.decode() if r == 0 else None
+
+
+def param_names(xml_file):
+    buf = C.create_string_buffer(1 << 16)
+    n = host_lib().ref_param_names(str(xml_file).encode(), buf, C.c_int(1 << 16))
+    if n < 0:
+        raise RuntimeError("reference XML parser failed on %s" % xml_file)
+    return [s for s in buf.value.decode().split("\n") if s]
+
+
+def _poses_rowmajor(poses):
+    return np.ascontiguousarray(np.asarray([np.asarray(P, np.float32) for P in poses], np.float32).reshape(-1, 16))
+
+
+def kitti_load_poses(path, cap=100000):
+    out = np.zeros((cap, 16), np.float32)
+    n = host_lib().ref_kitti_load_poses(str(path).encode(), _p(out), C.c_int(cap))
+    if n < 0:
+        return None  # the reference throws (boost::bad_lexical_cast)
+    return [out[i].reshape(4, 4).copy() for i in range(min(n, cap))]
+
+
+def kitti_calibration(path, name):
+    out = np.zeros(16, np.float32)
+    r = host_lib().ref_kitti_calibration(str(path).encode(), name.encode(), _p(out))
+    return out.reshape(4, 4) if r == 0 else None
+
+
+def kitti_trajectory_distances(poses):
+    P = _poses_rowmajor(poses); d = np.zeros(P.shape[0], np.float32)
+    host_lib().ref_kitti_trajectory_distances(_p(P), C.c_int(P.shape[0]), _p(d))
+    return d
+
+
+def kitti_rotation_error(E):
+    return float(host_lib().ref_kitti_rotation_error(_p(_poses_rowmajor([E]))))
+
+
+def kitti_translation_error(E):
+    return float(host_lib().ref_kitti_translation_error(_p(_poses_rowmajor([E]))))
+
+
+def kitti_last_frame(dist, first_frame, length):
+    d = np.ascontiguousarray(dist, np.float32)
+    return int(host_lib().ref_kitti_last_frame(_p(d), C.c_int(d.shape[0]), C.c_int(first_frame), C.c_float(length)))
+
+
+def kitti_sequence_errors(gt, res, cap=200000):
+    G, R_ = _poses_rowmajor(gt), _poses_rowmajor(res)
+    out = np.zeros((cap, 5), np.float32)
+    n = host_lib().ref_kitti_sequence_errors(_p(G), _p(R_), C.c_int(G.shape[0]), _p(out), C.c_int(cap))
+    return out[:min(n, cap)].copy()
+
+
+def kitti_save_stats(rows, directory):
+    rows = np.ascontiguousarray(rows, np.float32)
+    host_lib().ref_kitti_save_stats(_p(rows), C.c_int(rows.shape[0]), str(directory).encode())
+    t, r = open(os.path.join(str(directory), "stats.txt")).read().split()
+    return float(t), float(r)
