@@ -100,6 +100,8 @@ void orc_icp_jacobian(const orc_params* p, const float* data_v, const float* dat
                       int32_t iteration, float max_distance, float max_angle_deg, int32_t row_begin,
                       int32_t row_end, double out48[48], int64_t raw32[32]);
 void orc_icp_unpack(const int64_t raw32[32], double out48[48]);
+/* 1: sum the way the reference's GL path does (see orc_core.c); returns the previous mode. Test infrastructure. */
+int orc_set_gl_sums(int on);
 /* same sums, accumulated the way the GL path does (fp32 partial sums of 64 pixels, then fp32 adds): used only to
  * show that the reference's own arithmetic lies within the 1e-5 band around the exact sums. */
 void orc_icp_jacobian_fp32gl(const orc_params* p, const float* data_v, const float* data_n, const float* data_s,

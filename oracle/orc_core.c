@@ -367,10 +367,30 @@ void orc_icp_unpack(const int64_t raw[32], double out48[48]) {
   out48[47] = 0.0;
 }
 
+/* Summation mode of the 48 values. 0 (default): exact Q33.30 fixed-point sums -- the contract of the CUDA path.
+ * 1: the reference's own accumulation (fp32 partial sums of 64 pixels in the geometry shader, fp32 ROP adds in primitive
+ * order = orc_icp_jacobian_fp32gl), so that whole runs can be compared bit for bit with the reference's classes running
+ * on the software GL (oracle/_ref/libsuma_ref_full.so). Test infrastructure only. */
+static int orc_gl_sums_ = 0;
+int orc_set_gl_sums(int on) {
+  int old = orc_gl_sums_;
+  orc_gl_sums_ = on ? 1 : 0;
+  return old;
+}
+
 void orc_icp_jacobian(const orc_params* p, const float* data_v, const float* data_n, const float* data_s,
                       const float* model_v, const float* model_n, const float* model_s, const double pose[16],
                       int32_t iteration, float max_distance, float max_angle_deg, int32_t row_begin,
                       int32_t row_end, double out48[48], int64_t raw32[32]) {
+  if (orc_gl_sums_ && row_begin == 0 && row_end == p->data_height) {
+    float f48[48];
+    orc_icp_jacobian_fp32gl(p, data_v, data_n, data_s, model_v, model_n, model_s, pose, iteration, max_distance,
+                            max_angle_deg, f48);
+    if (out48)
+      for (int i = 0; i < 48; ++i) out48[i] = (double)f48[i];
+    if (raw32) memset(raw32, 0, 32 * sizeof(int64_t));
+    return;
+  }
   float Mf[16];
   for (int i = 0; i < 16; ++i) Mf[i] = (float)pose[i]; /* pose_.cast<float>(), Frame2Model.cpp:194 */
   float dthr, athr;

@@ -6,6 +6,7 @@
 // this directory. This file only marshals plain arrays in and out of those classes; it restates none of their logic.
 // What is NOT the reference here: glow + the GL implementation (sgl.hpp, glow/glow_all.hpp), Eigen (../host/eigen3),
 // Boost (../host/boost), the gtsam-backed pose graph (posegraph_stub.cpp: stores poses and edges, optimises nothing).
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -66,6 +67,7 @@ rv::ParameterList make_params(const orc_params* p, const char* xml) {
   // reference's file was parsed above these are already present and stay)
   if (!L.hasParam("cutoff_threshold")) F("cutoff_threshold", 10.0);
   if (!L.hasParam("close-loops")) B("close-loops", false);
+  if (!L.hasParam("approach")) L.insert(rv::StringParameter("approach", "frame-to-model"));
   return L;
 }
 
@@ -188,6 +190,131 @@ int reffull_icp_jacobian(reffull* h, const float* data_v, const float* data_n, c
   }
 }
 
+// LieGaussNewton::minimize (core/LieGaussNewton.cpp:13-36) on Frame2Model with the list's parameters; history: the poses
+// pushed per iteration (column-major), errors: residual() after the run. Returns iterationCount().
+int reffull_icp_minimize(reffull* h, const float* data_v, const float* data_n, const float* data_s, const float* model_v,
+                         const float* model_n, const float* model_s, const double T0[16], double pose_out[16],
+                         double* history, int hist_cap, int* hist_len) {
+  try {
+    Frame2Model f(h->params);
+    auto cur = std::make_shared<Frame>(h->p.data_width, h->p.data_height);
+    auto mod = std::make_shared<Frame>(h->p.model_width, h->p.model_height);
+    upload(cur->vertex_map, data_v); upload(cur->normal_map, data_n); upload(cur->semantic_map, data_s);
+    upload(mod->vertex_map, model_v); upload(mod->normal_map, model_n); upload(mod->semantic_map, model_s);
+    f.setData(cur, mod);
+    LieGaussNewton gn;
+    gn.setParameters(h->params);
+    gn.minimize(f, m4d(T0));
+    for (int i = 0; i < 16; ++i) pose_out[i] = gn.pose().data()[i];
+    const std::vector<Eigen::Matrix4d>& hs = gn.history();
+    if (hist_len) *hist_len = (int)hs.size();
+    for (int k = 0; k < (int)hs.size() && k < hist_cap; ++k)
+      for (int i = 0; i < 16; ++i) history[16 * (size_t)k + i] = hs[k].data()[i];
+    return (int)gn.iterationCount();
+  } catch (const std::exception& e) {
+    h->error = e.what();
+    return -1;
+  }
+}
+
 uint64_t reffull_draw_calls(void) { return sgl::ctx().draw_calls; }
+
+// ---------------------------------------------------------------------------------------------- SurfelMap (core/SurfelMap.cpp)
+static SurfelMap* the_map(reffull* h) {
+  if (h->slam) return h->slam->getMap().get();
+  if (!h->map) h->map.reset(new SurfelMap(h->params));
+  return h->map.get();
+}
+static void frame_from(Frame& f, const float* v, const float* n, const float* s) {
+  upload(f.vertex_map, v); upload(f.normal_map, n); upload(f.semantic_map, s);
+  f.valid = true;
+}
+static void frame_to(const Frame& f, float* v, float* n, float* s) {
+  download(f.vertex_map, v); download(f.normal_map, n); download(f.semantic_map, s);
+}
+#define REFFULL_TRY(body) try { body; return 0; } catch (const std::exception& e) { h->error = e.what(); return -1; }
+
+uint32_t reffull_map_size(reffull* h) { return the_map(h)->size(); }
+uint32_t reffull_map_download(reffull* h, orc_surfel* dst, uint32_t cap) {
+  std::vector<Surfel> all = the_map(h)->getAllSurfels();
+  static_assert(sizeof(Surfel) == sizeof(orc_surfel), "Surfel record layout (core/Surfel.h:5-15)");
+  uint32_t k = std::min<uint32_t>(cap, (uint32_t)all.size());
+  if (k) memcpy(dst, all.data(), sizeof(orc_surfel) * k);
+  return k;
+}
+// SurfelMap::update (SurfelMap.cpp:492-584), including updateActiveSubmaps
+int reffull_map_update(reffull* h, const float pose[16], const float* fv, const float* fn, const float* fs) {
+  REFFULL_TRY({
+    Frame frame(h->p.data_width, h->p.data_height);
+    frame_from(frame, fv, fn, fs);
+    the_map(h)->update(m4f(pose), frame);
+  })
+}
+int reffull_map_render(reffull* h, const float pose_old[16], const float pose_new[16], float conf_thr, float* fv, float* fn,
+                       float* fs) {
+  REFFULL_TRY({
+    Frame frame(h->p.model_width, h->p.model_height);
+    the_map(h)->render(m4f(pose_old), m4f(pose_new), frame, conf_thr);
+    frame_to(frame, fv, fn, fs);
+  })
+}
+int reffull_map_render_active(reffull* h, const float pose[16], float conf_thr) { REFFULL_TRY(the_map(h)->render_active(m4f(pose), conf_thr)) }
+int reffull_map_render_inactive(reffull* h, const float pose[16], float conf_thr) { REFFULL_TRY(the_map(h)->render_inactive(m4f(pose), conf_thr)) }
+int reffull_map_render_composed(reffull* h, const float pose_old[16], const float pose_new[16], float conf_thr) {
+  REFFULL_TRY(the_map(h)->render_composed(m4f(pose_old), m4f(pose_new), conf_thr))
+}
+int reffull_map_get_frame(reffull* h, int which, float* v, float* n, float* s) {
+  REFFULL_TRY({
+    std::shared_ptr<Frame>& f = which == 0 ? the_map(h)->oldMapFrame() : which == 1 ? the_map(h)->newMapFrame() : the_map(h)->composedFrame();
+    frame_to(*f, v, n, s);
+  })
+}
+
+// ---------------------------------------------------------------------------------------------- SurfelMapping (core/SurfelMapping.cpp)
+int reffull_slam_create(reffull* h) { REFFULL_TRY(h->slam.reset(new SurfelMapping(h->params))) }
+// SurfelMapping::processScan (SurfelMapping.cpp:175-210); labels / probs may be null (geometric run: zeros)
+int reffull_slam_process_scan(reffull* h, const float* pts4, const float* labels, const float* probs, uint32_t n) {
+  REFFULL_TRY({
+    if (!h->slam) h->slam.reset(new SurfelMapping(h->params));
+    rv::Laserscan scan;
+    scan.points().resize(n);
+    for (uint32_t i = 0; i < n; ++i) scan.points()[i] = rv::Point3f(pts4[4 * i], pts4[4 * i + 1], pts4[4 * i + 2]);
+    scan.labels_float.assign(n, 0.0f);
+    scan.labels_prob.assign(n, 0.0f);
+    if (labels) scan.labels_float.assign(labels, labels + n);
+    if (probs) scan.labels_prob.assign(probs, probs + n);
+    h->slam->processScan(scan);
+  })
+}
+uint32_t reffull_slam_timestamp(reffull* h) { return h->slam ? h->slam->timestamp() : 0; }
+void reffull_slam_pose(reffull* h, double pose[16]) {
+  const Eigen::Matrix4d& P = h->slam->getCurrentPose();
+  for (int i = 0; i < 16; ++i) pose[i] = P.data()[i];
+}
+void reffull_slam_last_pose(reffull* h, double pose[16]) {
+  const Eigen::Matrix4d& P = h->slam->getLastPose();
+  for (int i = 0; i < 16; ++i) pose[i] = P.data()[i];
+}
+// which: 0 currentFrame, 1 lastFrame, 2 currentModelFrame, 3 lastModelFrame
+int reffull_slam_frame(reffull* h, int which, float* v, float* n, float* s) {
+  REFFULL_TRY({
+    Frame::Ptr f = which == 0 ? h->slam->getCurrentFrame() : which == 1 ? h->slam->getLastFrame()
+                 : which == 2 ? h->slam->getCurrentModelFrame() : h->slam->getLastModelFrame();
+    frame_to(*f, v, n, s);
+  })
+}
+// one entry of SurfelMapping::getStatistics() (NaN if absent)
+double reffull_slam_statistic(reffull* h, const char* name) {
+  const SurfelMapping::Stats& st = h->slam->getStatistics();
+  auto it = st.find(name);
+  return it == st.end() ? std::nan("") : (double)it->second;
+}
+int reffull_slam_found_loop_candidate(reffull* h) { return h->slam->foundLoopClosureCandidate() ? 1 : 0; }
+int reffull_slam_use_loop_candidate(reffull* h) { return h->slam->useLoopClosureCandidate() ? 1 : 0; }
+uint32_t reffull_slam_edges(reffull* h, int32_t* from_to, uint32_t cap) {
+  const std::vector<Posegraph::Edge>& e = h->slam->getPosegraph()->getEdges();
+  for (uint32_t i = 0; i < e.size() && i < cap; ++i) { from_to[2 * i] = e[i].from; from_to[2 * i + 1] = e[i].to; }
+  return (uint32_t)e.size();
+}
 
 }  // extern "C"

@@ -462,9 +462,10 @@ inline void draw_arrays(unsigned mode, int first, int count) {
     for (size_t e = 0; e <= ends.size(); ++e) {
       int end = e < ends.size() ? ends[e] : n;
       if (strips) {
-        for (int t = begin; t + 2 < end; ++t) {
-          if ((t - begin) & 1) pl.triangle(t + 1, t, t + 2); else pl.triangle(t, t + 1, t + 2);
-        }
+        // triangle t of a strip = vertices (t, t+1, t+2). GL swaps the first two for odd t to keep the winding; with
+        // face culling off that only renames the vertices -- the barycentric rule of DESIGN.md section 2 is stated for
+        // (t, t+1, t+2), as ../ref_pipeline.cpp, oracle/ and the CUDA path evaluate it
+        for (int t = begin; t + 2 < end; ++t) pl.triangle(t, t + 1, t + 2);
       } else {
         for (int t = begin; t < end; ++t) {
           pl.capture(p.gs->emitted_data(t));
