@@ -88,6 +88,12 @@ def lib():
     return _lib
 
 
+def gl_sums(on):
+    """sum the 48 ICP values the way the reference's GL path does (orc_core.c orc_set_gl_sums) instead of exactly; returns
+    the previous mode. Only for comparisons with oracle/_ref/libsuma_ref_full.so."""
+    return int(lib().orc_set_gl_sums(int(bool(on))))
+
+
 def set_threads(n=0):
     """host threads for the oracle's loops (0 = all cores, capped at 64); results do not depend on it"""
     return int(lib().orc_set_threads(int(n)))

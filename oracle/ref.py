@@ -286,3 +286,169 @@ def kitti_save_stats(rows, directory):
     host_lib().ref_kitti_save_stats(_p(rows), C.c_int(rows.shape[0]), str(directory).encode())
     t, r = open(os.path.join(str(directory), "stats.txt")).read().split()
     return float(t), float(r)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# libsuma_ref_full.so: the reference's own CORE CLASSES -- Preprocessing, Frame2Model, LieGaussNewton, SurfelMap,
+# SurfelMapping (the whole processScan incl. track-loss fallback, submap paging and checkLoopClosure) -- compiled where
+# they lie against a stand-in glow on a generic software GL (oracle/ref_harness/full/) and driving the reference's own
+# transpiled shaders. What the GL / Eigen / libm implementations leave open is pinned to the oracle's rules
+# (REF_MATH_PINNED, MINI_EIGEN_PINNED, pinned_libm.h), and the oracle can sum the 48 ICP values the GL way
+# (O.gl_sums): then reference and oracle must agree BIT FOR BIT over whole runs.
+# ------------------------------------------------------------------------------------------------------------------
+def full_available():
+    return have_reference() or os.path.exists(lib_path("full"))
+
+
+DEFAULT_XML = os.path.join(REFERENCE, "config", "default.xml")
+_full = None
+
+
+def full_lib():
+    global _full
+    if _full is None:
+        build()
+        L = C.CDLL(lib_path("full"))
+        L.reffull_create.restype = C.c_void_p
+        L.reffull_error.restype = C.c_char_p
+        for f in ("reffull_map_size", "reffull_map_download", "reffull_slam_timestamp", "reffull_slam_edges"):
+            getattr(L, f).restype = C.c_uint32
+        L.reffull_slam_statistic.restype = C.c_double
+        L.reffull_draw_calls.restype = C.c_uint64
+        _full = L
+    return _full
+
+
+class Full:
+    """one parameter list + lazily constructed Preprocessing / SurfelMap / SurfelMapping of the reference"""
+
+    def __init__(self, p, zero_stale_tail=True, **extra):
+        self.p = p
+        self.L = full_lib()
+        xml = DEFAULT_XML if os.path.exists(DEFAULT_XML) else ""
+        self.h = C.c_void_p(self.L.reffull_create(C.byref(p), xml.encode()))
+        self._check(0)
+        self.L.reffull_zero_stale_tail(C.c_int(1 if zero_stale_tail else 0))
+        for k, v in extra.items():
+            name = k.encode()
+            if isinstance(v, bool):
+                self.L.reffull_set_bool(self.h, name, C.c_int(int(v)))
+            elif isinstance(v, int):
+                self.L.reffull_set_int(self.h, name, C.c_int(v))
+            else:
+                self.L.reffull_set_float(self.h, name, C.c_double(float(v)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.reffull_destroy(self.h); self.h = None
+
+    def _check(self, r):
+        err = self.L.reffull_error(self.h).decode()
+        if r != 0 or err:
+            raise RuntimeError("reference (full): " + err)
+
+    def param(self, name):
+        buf = C.create_string_buffer(1024)
+        r = self.L.reffull_param(self.h, name.encode(), buf, C.c_int(1024))
+        return buf.value.decode() if r == 0 else None
+
+    def _dframe(self):
+        return [np.zeros((self.p.data_height, self.p.data_width, 4), np.float32) for _ in range(3)]
+
+    def _mframe(self):
+        return [np.zeros((self.p.model_height, self.p.model_width, 4), np.float32) for _ in range(3)]
+
+    # ---- Preprocessing / Frame2Model / LieGaussNewton ----
+    def preprocess(self, pts, labels=None, probs=None, timestamp=100):
+        pts = _f32(pts); n = pts.shape[0]
+        labels = _f32(labels) if labels is not None else None; probs = _f32(probs) if probs is not None else None
+        v, nm, s = self._dframe()
+        self._check(self.L.reffull_preprocess(self.h, _p(pts), _p(labels) if labels is not None else None,
+                                              _p(probs) if probs is not None else None, C.c_uint32(n),
+                                              C.c_uint32(timestamp), _p(v), _p(nm), _p(s)))
+        return v, nm, s
+
+    def icp_jacobian(self, data, model, pose, iteration=0, max_distance=None, max_angle=None):
+        a = [_f32(x) for x in list(data) + list(model)]
+        out = np.zeros(48, np.float64)
+        self._check(self.L.reffull_icp_jacobian(self.h, *[_p(x) for x in a], _p(colmajor(pose, np.float64), C.c_double),
+                                                C.c_int32(iteration),
+                                                C.c_float(self.p.icp_max_distance if max_distance is None else max_distance),
+                                                C.c_float(self.p.icp_max_angle if max_angle is None else max_angle),
+                                                _p(out, C.c_double)))
+        return out
+
+    def icp_minimize(self, data, model, T0, hist_cap=300):
+        a = [_f32(x) for x in list(data) + list(model)]
+        pose = np.zeros(16, np.float64); hist = np.zeros(16 * hist_cap, np.float64); hl = C.c_int(0)
+        k = self.L.reffull_icp_minimize(self.h, *[_p(x) for x in a], _p(colmajor(T0, np.float64), C.c_double),
+                                        _p(pose, C.c_double), _p(hist, C.c_double), C.c_int(hist_cap), C.byref(hl))
+        self._check(0 if k >= 0 else -1)
+        return O.from_colmajor(pose), k, [O.from_colmajor(hist[16 * i:16 * i + 16]) for i in range(min(hl.value, hist_cap))]
+
+    # ---- SurfelMap ----
+    def map_size(self):
+        return int(self.L.reffull_map_size(self.h))
+
+    def map_download(self):
+        n = self.map_size()
+        a = np.zeros(max(n, 1), O.SURFEL_DTYPE)
+        k = self.L.reffull_map_download(self.h, a.ctypes.data_as(C.c_void_p), C.c_uint32(n))
+        return a[:k]
+
+    def map_update(self, pose, frame):
+        fv, fn, fs = [_f32(a) for a in frame]
+        self._check(self.L.reffull_map_update(self.h, _p(colmajor(pose, np.float32)), _p(fv), _p(fn), _p(fs)))
+
+    def map_render(self, pose_old, pose_new, conf_thr):
+        v, n, s = self._mframe()
+        self._check(self.L.reffull_map_render(self.h, _p(colmajor(pose_old, np.float32)), _p(colmajor(pose_new, np.float32)),
+                                              C.c_float(conf_thr), _p(v), _p(n), _p(s)))
+        return v, n, s
+
+    def map_render_active(self, pose, conf_thr):
+        self._check(self.L.reffull_map_render_active(self.h, _p(colmajor(pose, np.float32)), C.c_float(conf_thr)))
+
+    def map_render_inactive(self, pose, conf_thr):
+        self._check(self.L.reffull_map_render_inactive(self.h, _p(colmajor(pose, np.float32)), C.c_float(conf_thr)))
+
+    def map_render_composed(self, pose_old, pose_new, conf_thr):
+        self._check(self.L.reffull_map_render_composed(self.h, _p(colmajor(pose_old, np.float32)),
+                                                       _p(colmajor(pose_new, np.float32)), C.c_float(conf_thr)))
+
+    def map_frame(self, which):
+        v, n, s = self._mframe()
+        self._check(self.L.reffull_map_get_frame(self.h, C.c_int(which), _p(v), _p(n), _p(s)))
+        return v, n, s
+
+    # ---- SurfelMapping ----
+    def process_scan(self, pts, labels=None, probs=None):
+        pts = _f32(pts)
+        labels = _f32(labels) if labels is not None else None; probs = _f32(probs) if probs is not None else None
+        self._check(self.L.reffull_slam_process_scan(self.h, _p(pts), _p(labels) if labels is not None else None,
+                                                     _p(probs) if probs is not None else None, C.c_uint32(pts.shape[0])))
+
+    def pose(self):
+        a = np.zeros(16, np.float64)
+        self.L.reffull_slam_pose(self.h, _p(a, C.c_double))
+        return O.from_colmajor(a)
+
+    def timestamp(self):
+        return int(self.L.reffull_slam_timestamp(self.h))
+
+    def statistic(self, name):
+        return float(self.L.reffull_slam_statistic(self.h, name.encode()))
+
+    def slam_frame(self, which):
+        """0 currentFrame, 1 lastFrame (data size); 2 currentModelFrame, 3 lastModelFrame (model size)"""
+        v, n, s = self._dframe() if which < 2 else self._mframe()
+        self._check(self.L.reffull_slam_frame(self.h, C.c_int(which), _p(v), _p(n), _p(s)))
+        return v, n, s
+
+    def loop_flags(self):
+        return bool(self.L.reffull_slam_found_loop_candidate(self.h)), bool(self.L.reffull_slam_use_loop_candidate(self.h))
+
+    def edges(self, cap=4096):
+        ft = np.zeros((cap, 2), np.int32)
+        n = self.L.reffull_slam_edges(self.h, _p(ft, C.c_int32), C.c_uint32(cap))
+        return [(int(ft[i, 0]), int(ft[i, 1])) for i in range(min(n, cap))]

@@ -179,6 +179,7 @@ class GlBuffer {
     st_->buf->ensure(data.size() * Pod<T>::size);
     for (size_t i = 0; i < data.size(); ++i) Pod<T>::store(st_->buf->bytes.data() + i * Pod<T>::size, data[i]);
     st_->size = data.size();
+    zero_tail();
   }
   void assign(const GlBuffer<T>& other) {
     if (other.st_ == st_) return;
@@ -188,6 +189,7 @@ class GlBuffer {
     other.st_->buf->ensure(n);
     memcpy(st_->buf->bytes.data(), other.st_->buf->bytes.data(), n);
     st_->size = other.st_->size;
+    zero_tail();
   }
   void insert(uint32_t offset, const T& value) {
     if (offset >= st_->capacity) return;
@@ -229,6 +231,11 @@ class GlBuffer {
   const std::shared_ptr<sgl::Buffer>& object() const { return st_->buf; }
 
  private:
+  void zero_tail() {  // see sgl::Context::zero_stale_tail
+    const size_t used = st_->size * Pod<T>::size;
+    if (sgl::ctx().zero_stale_tail && st_->buf->bytes.size() > used)
+      memset(st_->buf->bytes.data() + used, 0, st_->buf->bytes.size() - used);
+  }
   struct State {
     std::shared_ptr<sgl::Buffer> buf;
     size_t size = 0, capacity = 0;

@@ -218,6 +218,8 @@ int reffull_icp_minimize(reffull* h, const float* data_v, const float* data_n, c
 }
 
 uint64_t reffull_draw_calls(void) { return sgl::ctx().draw_calls; }
+// 1: attribute reads behind the last uploaded element return 0 instead of the previous upload's data (sgl.hpp)
+void reffull_zero_stale_tail(int on) { sgl::ctx().zero_stale_tail = on != 0; }
 
 // ---------------------------------------------------------------------------------------------- SurfelMap (core/SurfelMap.cpp)
 static SurfelMap* the_map(reffull* h) {

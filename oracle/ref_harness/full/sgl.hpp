@@ -192,6 +192,12 @@ struct Context : Units {
   std::map<const Framebuffer*, int> fbo_id_of;
   int next_fbo_id = 1;
   uint64_t draw_calls = 0;
+  bool binding_fragment_stage = false;
+  // Attribute fetches past the last element written by GlBuffer::assign but inside the buffer object's data store return
+  // what the store holds: with glow's assign (glBufferSubData into a store that only grows) that is the PREVIOUS, larger
+  // upload's data. true = return zeros instead (what oracle/ and the CUDA path define for the label / probability
+  // attributes whose pointer offset runs 4 / 5 elements past the end).
+  bool zero_stale_tail = false;
 
   glsl::sampler2DRect rect(int unit) const override {
     glsl::sampler2DRect s;
@@ -201,6 +207,7 @@ struct Context : Units {
     // level of detail 0 on a texture without mipmaps selects the MAGNIFICATION filter (OpenGL 3.3 section 3.8.11:
     // lambda <= c with c = 0 unless the minification filter uses mipmaps)
     s.linear = unit_sampler[unit] ? unit_sampler[unit]->lin_mag : t.lin_mag;
+    s.snap8 = binding_fragment_stage;  // see glsl_types.hpp
     return s;
   }
   glsl::samplerBuffer buffer(int unit) const override {
@@ -437,7 +444,11 @@ inline void draw_arrays(unsigned mode, int first, int count) {
   Pipeline pl(c, p);
   p.vs->bind_samplers(c);
   if (p.gs) p.gs->bind_samplers(c);
-  if (p.fs) p.fs->bind_samplers(c);
+  if (p.fs) {
+    c.binding_fragment_stage = true;
+    p.fs->bind_samplers(c);
+    c.binding_fragment_stage = false;
+  }
   const std::vector<Var> vs_outs = p.vs->outs();
   for (int k = 0; k < count; ++k) {
     const int vid = first + k;

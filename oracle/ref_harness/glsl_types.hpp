@@ -317,6 +317,11 @@ struct sampler2DRect {
   const float* data = nullptr;  // [H][W][C]
   int W = 0, H = 0, C = 4;
   bool linear = false;
+  // LINEAR lookups of the generic software GL in FRAGMENT stages (full/sgl.hpp): the texture coordinate comes out of the
+  // rasteriser's fp32 interpolation, ~1e-4 texel off the pixel centre it means. Hardware filter weights have 8 fractional
+  // bits, so within 1/512 texel of a texel centre a GPU returns that texel itself; so does this flag. (The K5 lookups of
+  // the geometry stage keep the full-precision weights DESIGN.md section 2 pins.)
+  bool snap8 = false;
   vec4 texel(int i, int j) const {
     if (i < 0 || j < 0 || i >= W || j >= H || !data) return vec4(0.0f);
     const float* p = data + ((size_t)j * W + i) * C;
@@ -331,6 +336,10 @@ inline vec4 texture(const sampler2DRect& s, const vec2& c) {
   float fu = std::floor(u), fv = std::floor(v);
   int i0 = (int)fu, j0 = (int)fv;
   float a = u - fu, b = v - fv;
+  if (s.snap8) {
+    int a8 = (int)std::lround((double)a * 256.0), b8 = (int)std::lround((double)b * 256.0);
+    if ((a8 == 0 || a8 == 256) && (b8 == 0 || b8 == 256)) return s.texel(i0 + (a8 == 256), j0 + (b8 == 256));
+  }
   vec4 t00 = s.texel(i0, j0), t10 = s.texel(i0 + 1, j0), t01 = s.texel(i0, j0 + 1), t11 = s.texel(i0 + 1, j0 + 1);
   vec4 r;
 #ifdef REF_MATH_PINNED
