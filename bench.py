@@ -493,6 +493,40 @@ def cpu_baseline(w, scans, budget_s=15.0, max_frames=None):
             "seconds": round(dt, 2), "host_cpus": os.cpu_count()}
 
 
+def reference_itself_sample(w, scans, budget_s=12.0, max_frames=6):
+    """informational: the reference's OWN classes and shaders (oracle/_ref/libsuma_ref_full.so -- core/*.cpp compiled where
+    they lie, running on a single-thread software GL) on the first scans of the sequence. Not the timed arm: a GL
+    emulation says nothing about the reference's speed on a GPU; the multi-threaded port above is the stricter baseline."""
+    try:
+        from oracle import oracle as O
+        from oracle import ref as R
+        if not R.full_available():
+            return None
+        sys.stdout.flush()
+        saved, null = os.dup(1), os.open(os.devnull, os.O_WRONLY)
+        os.dup2(null, 1)  # the reference's classes print progress to stdout; this process prints ONE JSON line there
+        try:
+            f = R.Full(O.default_params(**param_kwargs(w)))
+            t0 = time.time()
+            n = 0
+            for p, l, q in scans[:max_frames]:
+                f.process_scan(p, l, q)
+                n += 1
+                if time.time() - t0 > budget_s:
+                    break
+            dt = time.time() - t0
+            del f
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+            os.close(null)
+        return {"value": round(n / dt, 3), "unit": "scans/s", "cores": 1, "kind": "reference",
+                "sample": "first %d scans (map grows from empty): SurfelMapping::processScan of the reference itself, its "
+                          "GLSL shaders transpiled, on a software GL" % n}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e)[:200]}
+
+
 def run_reference(args, w, rank, world):
     """--impl reference: the reference has no CPU (or buildable GL) path in this environment; the arm times the
     oracle's restatement of it (C + OpenMP, thread-count independent results) on the same workload, same pre-rolled map."""
@@ -521,13 +555,14 @@ def run_reference(args, w, rank, world):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "range_image": "%dx%d" % (w["height"], w["width"]),
                    "icp_iterations": w["iters"], "semantic": w["semantic"], "map_preroll_scans": args.preroll,
-                   "note": "reference OpenGL path not runnable here (no GL/EGL, glow/gtsam/rangenet_lib absent); "
-                           "this is the CPU restatement in oracle/ (kind=port), pinned bit for bit to the reference's "
-                           "shader text (oracle/_ref)"},
+                   "note": "no GL/EGL on the box: the reference's OpenGL path cannot run on the GPU. Timed here: the CPU "
+                           "restatement in oracle/ (kind=port, OpenMP), which equals the reference's own classes + shaders "
+                           "run on a software GL bit for bit (oracle/_ref, tests/test_ref_full.py); that run itself is "
+                           "reported as cpu_baseline.reference_itself (single thread, far slower -- not the timed arm)"},
         "cpu_baseline": {"value": round(v, 3), "unit": "scans/s", "cores": threads, "kind": "port",
                          "sample": "%d scans after %d pre-roll + %d warm-up scans, %d OpenMP threads (physical cores of "
                                    "one socket)" % (done, args.preroll, args.warmup, threads),
-                         "host_cpus": os.cpu_count()},
+                         "host_cpus": os.cpu_count(), "reference_itself": reference_itself_sample(w, scans)},
         "e2e": {"value": round(v, 3), "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
