@@ -1,6 +1,7 @@
 """Generates tests/golden/oracle_golden.json: SHA-256 digests (and a few scalars) of the oracle's outputs on seeded
-synthetic inputs. The reference ships no golden vectors for this path and cannot be built or imported here (OpenGL /
-GLSL + un-vendored dependencies), so these goldens pin the ORACLE against regressions -- they are not reference outputs.
+synthetic inputs. The reference ships no golden vectors for this path; these digests pin the ORACLE (exact sums -- the
+CUDA path's contract) against regressions. Digests of the outputs of the reference itself are in reference_golden.json
+(make_reference_golden.py).
 
     python tests/golden/make_golden.py            # rewrites the JSON (run only when the oracle changes on purpose)
 """

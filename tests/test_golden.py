@@ -1,5 +1,6 @@
-"""The oracle against its committed golden digests (tests/golden/oracle_golden.json, made by make_golden.py), and --
-on a GPU -- the CUDA path against the same digests."""
+"""The oracle against its committed golden digests (tests/golden/oracle_golden.json, made by make_golden.py), against the
+digests of the outputs of THE REFERENCE ITSELF (tests/golden/reference_golden.json, made by make_reference_golden.py from
+oracle/_ref/libsuma_ref_full.so where /root/reference exists), and -- on a GPU -- the CUDA path against the oracle's."""
 import json
 import os
 
@@ -14,6 +15,22 @@ GOLD = json.load(open(os.path.join(HERE, "golden", "oracle_golden.json")))
 
 def test_oracle_matches_golden():
     assert G.compute() == GOLD
+
+
+def test_oracle_matches_the_reference_generated_golden():
+    """preprocessing, map update / rendering through a paging tour, and whole processScan runs (48 ICP values added the GL
+    way): the oracle reproduces the digests the reference's own classes and shaders produced in the build container"""
+    from golden import make_reference_golden as RG
+    from oracle import oracle as O
+    ref = json.load(open(os.path.join(HERE, "golden", "reference_golden.json")))
+    old = O.gl_sums(1)
+    try:
+        got = RG.compute(RG.OracleEngine)
+    finally:
+        O.gl_sums(old)
+    assert sorted(got) == sorted(ref)
+    for k in ref:
+        assert got[k] == ref[k], k
 
 
 @pytest.mark.gpu
