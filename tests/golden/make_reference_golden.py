@@ -44,6 +44,12 @@ class OracleEngine:
     def preprocess(self, pts, lab, prb, timestamp):
         return O.preprocess(self.p, pts, lab, prb, timestamp=timestamp)
 
+    def maps(self, frame):
+        return frame
+
+    def close(self):
+        pass
+
     def map_update(self, T, frame):
         self.map.update(T, frame)
 
@@ -70,6 +76,12 @@ class ReferenceEngine:
     def preprocess(self, pts, lab, prb, timestamp):
         return self.f.preprocess(pts, lab, prb, timestamp=timestamp)
 
+    def maps(self, frame):
+        return frame
+
+    def close(self):
+        pass
+
     def map_update(self, T, frame):
         self.f.map_update(T, frame)
 
@@ -87,7 +99,8 @@ class ReferenceEngine:
         return self.f.pose(), self.f.map_download(), 0.0 if it != it else it
 
 
-def compute(make_engine):
+def compute(make_engine, process_scan=True):
+    """process_scan=False: only what does not involve the 48 blended ICP values (what the CUDA path must reproduce too)"""
     out = {}
     for semantic in (False, True):
         tag = "semantic" if semantic else "geometric"
@@ -95,13 +108,16 @@ def compute(make_engine):
         sc, _ = scans(900, n=4, semantic=semantic)
         e = make_engine(p)
         frames = [e.preprocess(*s, timestamp=t * 7) for t, s in enumerate(sc)]
-        out["preprocess_%s" % tag] = [digest(x) for f in frames for x in f]
+        out["preprocess_%s" % tag] = [digest(x) for f in frames for x in e.maps(f)]
         sizes = []
         for t, (x, y) in enumerate(TOUR):
             e.map_update(pose_at(x, y), frames[t % 4])
             sizes.append(int(e.map_surfels().shape[0]))
         out["map_%s" % tag] = {"sizes": sizes, "surfel_digest": surfel_digest(e.map_surfels()),
                                "render": [digest(x) for x in e.map_render(pose_at(10, 2), -5.0)]}
+        e.close()
+        if not process_scan:
+            continue
         e = make_engine(p)
         run = []
         for s in sc:
