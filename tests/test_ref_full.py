@@ -109,6 +109,40 @@ def test_process_scan_of_the_reference_equals_oracle(width, semantic, frames):
             assert_bits_equal(a, b, "map frame %d %s" % (w, name))
 
 
+VARIANTS = [dict(weighting=1), dict(weighting=2), dict(weighting=0), dict(bilinear_sampling=0), dict(compose_rendering=0),
+            dict(initialize_identity=1), dict(initialize_identity=0), dict(update_always=1), dict(weighting_scheme=1),
+            dict(weighting_scheme=2), dict(averaging_scheme=1), dict(confidence_mode=0), dict(confidence_mode=1),
+            dict(confidence_mode=2), dict(use_stability=0), dict(unstable_age=1, confidence_threshold=5.0),
+            dict(max_iterations=3), dict(fallback_mode=0), dict(active_timestamps=1), dict(min_radius=0.05, max_radius=0.2),
+            dict(max_angle=60.0), dict(map_max_distance=0.05, map_max_angle=5.0), dict(partial_extraction=0),
+            dict(submap_extent=3.0, submap_dimension=1)]
+
+
+def test_parameter_branches_of_the_reference_equal_oracle():
+    """every parameter the classes read (robust weighting by name, sampling, compose rendering on/off, initial guess,
+    surfel weighting / averaging schemes, confidence modes, stability, thresholds, submap layout): four semantic scans at
+    64x450 per variant, poses and surfel records bit-identical"""
+    sc, _ = scans(450, n=4, semantic=True)
+    for kw in VARIANTS:
+        p = O.default_params(**sized(450), **kw)
+        f, osl = _both(p)
+        for t in range(4):
+            _step_equal(f, osl, sc[t], "%r t=%d" % (kw, t))
+
+
+def test_ouster_size_of_the_reference_equals_oracle():
+    """BASELINE.json configs[3]: 128x4096, +-22.5 degrees, 15 iterations -- two scans"""
+    kw = dict(data_width=4096, model_width=4096, data_height=128, model_height=128, data_fov_up=22.5, data_fov_down=-22.5,
+              model_fov_up=22.5, model_fov_down=-22.5, max_iterations=15, stopping_threshold=0.0, delta=0.0)
+    p = O.default_params(**kw)
+    sc = synth.Scene(width=4096, height=128, fov_up=22.5, fov_down=-22.5)
+    poses = synth.trajectory(2)
+    f, osl = _both(p)
+    for t in range(2):
+        _step_equal(f, osl, sc.scan(t, poses[t]), "t=%d" % t)
+    assert f.statistic("num_iterations") == 15
+
+
 def test_stale_attribute_tail_of_the_reference_is_the_one_known_deviation():
     """Q1 reads labels[i+4] / probs[i+5]: for the last 4 / 5 points of a scan that is past the data just uploaded. glow's
     GlBuffer::assign keeps the larger data store of an earlier upload, so the reference reads the PREVIOUS scan's values
