@@ -4,17 +4,25 @@
  * every function cites the file:line it follows, relative to /root/reference/src). It exists to CHECK the CUDA
  * path; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
  *
- * PARITY STATUS: pinned to the reference's own shader text. The reference ships no tests, golden vectors or fixtures
- * for this path and its build (OpenGL + un-vendored glow/gtsam/rangenet_lib + Qt) cannot run here,
- * but its GLSL sources compile: oracle/ref_harness rewrites them mechanically to C++ where they lie under
- * /root/reference and drives them with a minimal software GL (oracle/_ref, git-ignored). With GLSL built-ins following
- * the rules of orc_math.h (a legal GL: the specification leaves their precision open) every image, sum, surfel record and
- * the surfel order of this oracle equal the transpiled shaders' BIT FOR BIT (tests/test_ref_shaders.py, including
- * adversarial random inputs); with fp64/libm built-ins (an independent GL) they agree to the tolerances stated there.
- * Round 2 found and fixed one deviation that way (update_surfels.geom:35: the integrated flag of a surfel that is removed
- * in the same pass). Not covered by shader text and therefore still "by construction": the fixed-function GL rules
- * (rasterisation, depth test, blending order -- listed in DESIGN.md section 2), Eigen's LDLT / SE3 (orc_core.c) and the
- * host-side orchestration of SurfelMapping.cpp (orc_slam.c).
+ * PARITY STATUS: pinned to THE REFERENCE ITSELF, run here. The reference ships no tests, golden vectors or fixtures for
+ * this path and its GPU build (OpenGL + un-vendored glow/gtsam/rangenet_lib + Qt) cannot run in
+ * this environment, but its sources compile from where they lie under /root/reference (oracle/ref_harness/Makefile ->
+ * oracle/_ref/, git-ignored):
+ *   libsuma_ref_full.so    the core classes themselves (Preprocessing, Frame2Model, LieGaussNewton, SurfelMap,
+ *                          SurfelMapping::processScan ...) driving the reference's own transpiled shaders on a stand-in
+ *                          glow over a generic software GL. With what GL / Eigen / libm leave open pinned to the rules
+ *                          of orc_math.h / DESIGN.md section 2, and this oracle adding the 48 ICP values the way the GL
+ *                          path does (orc_set_gl_sums), oracle and reference agree BIT FOR BIT over whole runs -- poses,
+ *                          iteration counts, frames, every surfel record -- incl. the track-loss fallback, submap paging,
+ *                          loop-closure detection, 24 parameter variants, 64x900 / 64x2048 / 128x4096
+ *                          (tests/test_ref_full.py); tests/golden/reference_golden.json holds digests of its outputs.
+ *   libsuma_ref_pinned.so / _precise.so   the shaders per operator, also on adversarial random inputs
+ *                          (tests/test_ref_shaders.py); _host.so: the host sources unpinned (tests/test_ref_host.py).
+ * The default mode of this oracle (exact Q33.30 sums of the 48 values) is the contract of the CUDA path; it differs from
+ * the reference's fp32 blending by < 1e-5 of the matrix scale per evaluation (test_jacobian_sums_equal_reference_shader).
+ * Deviations found by running the reference, all documented in DESIGN.md section 2: update_surfels.geom:35 (fixed), the
+ * stale attribute tail of quirk Q1 (kept: the reference reads the previous upload's data there, we read 0).
+ * Still "by construction": the fixed-function GL rules themselves (no GL implementation exists here to test them against).
  *
  * Conventions: images are [H][W][4] float32, row 0 = lowest beam; 4x4 matrices are column-major (Eigen/GL).
  */
