@@ -301,7 +301,10 @@ int reset_state(sb_ctx* c) {
   c->trackLoss = 0;
   c->n_upper = 0;
   {
-    static PoseDev h;  // static: the async copy below reads it until the synchronize at the end of this function
+    // staged in the context's own pinned buffer (read by the async copy until the synchronize at the end of this
+    // function; no other transfer of this context is in flight here): contexts reset concurrently share nothing
+    static_assert(sizeof(PoseDev) <= 4096, "pinned staging");
+    PoseDev& h = *reinterpret_cast<PoseDev*>(c->h_pinned);
     memset(&h, 0, sizeof(h));
     ident_d(h.currentPose); ident_d(h.lastPose); ident_d(h.lastIncrement); ident_d(h.increment); ident_d(h.T0);
     for (int i = 0; i < 4; ++i) h.P_active.m[5 * i] = h.invP_active.m[5 * i] = h.P_cur.m[5 * i] = h.invP_cur.m[5 * i] = 1.0f;
@@ -616,11 +619,11 @@ int icp_minimize_callback(sb_ctx* c, const sb_frame* data, const sb_frame* model
   }
   h.k = k;
   h.done = 1;
-  h.history_len = (int)(hist.size() / 16);
+  size_t hb = hist.size() * sizeof(double);
+  if (hb > 32768) hb = 32768;  // staging room: 256 poses (a run of all kMaxGnIter = 256 iterations pushes 257)
+  h.history_len = (int)(hb / 128);
   char* hp = (char*)c->h_pinned + 16384;
   memcpy(hp, &h, sizeof(h));
-  size_t hb = hist.size() * sizeof(double);
-  if (hb > 32768) hb = 32768;
   memcpy(hp + 1024, hist.data(), hb);
   SB_CUDA(c, cudaMemcpyAsync(c->gn, hp, sizeof(h), cudaMemcpyHostToDevice, c->stream));
   SB_CUDA(c, cudaMemcpyAsync((char*)c->gn + offsetof(GnState, history), hp + 1024, hb, cudaMemcpyHostToDevice, c->stream));
@@ -1263,6 +1266,11 @@ int sb_destroy(sb_ctx* c) {
     if (sl.released) cudaEventDestroy(sl.released);
   }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (auto& r : c->prof.recs) {  // events of the per-kernel profiler (sb_profile_*)
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  for (cudaEvent_t e : c->prof.pool) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
   return SB_OK;
