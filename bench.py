@@ -490,7 +490,8 @@ def cpu_baseline(w, scans, budget_s=15.0, max_frames=None):
             "sample": "first %d scans of the same synthetic sequence (map grows from empty), oracle/ C port, %d OpenMP "
                       "threads = physical cores of one socket" % (n, threads),
             "single_thread": {"value": round(single, 3), "unit": "scans/s", "cores": 1, "sample": "first %d scans" % n1},
-            "seconds": round(dt, 2), "host_cpus": os.cpu_count()}
+            "seconds": round(dt, 2), "host_cpus": os.cpu_count(),
+            "reference_itself": reference_itself_sample(w, scans, budget_s=8.0, max_frames=4)}
 
 
 def reference_itself_sample(w, scans, budget_s=12.0, max_frames=6):
