@@ -172,8 +172,8 @@ int sb_prefetch_scan(sb_ctx* ctx, const float* pts4, const float* labels, const 
  * residual comparison, verification over consecutive scans, and the chained "old" pose (currentPose_old_) that the next
  * scan's composed rendering uses. The pose-graph OPTIMISATION (gtsam, core/Posegraph.cpp) stays with the host application:
  * the library records what the reference feeds into gtsam (sb_get_loop_edges: odometry + loop edges; initial poses =
- * the odometry chain) and raises optimisation_requested; optimised poses come back through sb_map_update_poses /
- * sb_set_current_pose (integrateLoopClosures, :212-258). */
+ * the odometry chain) and raises optimisation_requested; optimised poses come back through
+ * sb_integrate_loop_closures (integrateLoopClosures, :212-258). */
 typedef struct sb_loop_params {
   float search_distance;         /* loop-search-distance (default.xml: 50) */
   float min_trajectory_distance; /* loop-min-trajectory-distance (SurfelMapping.h:224: 200) */
@@ -199,6 +199,12 @@ void sb_default_loop_params(sb_loop_params* p);
 int sb_set_loop_closure(sb_ctx* ctx, int enabled, const sb_loop_params* p /* NULL = defaults */);
 int sb_get_loop_info(sb_ctx* ctx, sb_loop_info* out);
 int sb_get_loop_edges(sb_ctx* ctx, sb_loop_edge* dst, uint32_t cap, uint32_t* n_total);
+/* SurfelMapping::integrateLoopClosures, core/SurfelMapping.cpp:212-258, called by the reference at the top of processScan
+ * once its asynchronous gtsam run has finished: poses16 = the optimised poses of scans 0 .. n-1 (column-major doubles; n >=
+ * the scan the request was raised at + 1; NULL = leave the graph's poses as they are). Later poses and the current pose are
+ * carried along, loop_count and the trajectory distances are updated, the map's pose table is rewritten
+ * (SurfelMap::updatePoses). *integrated = number of poses written, 0 if no request was pending. */
+int sb_integrate_loop_closures(sb_ctx* ctx, const double* poses16, uint32_t n, uint32_t* integrated);
 int sb_set_current_pose(sb_ctx* ctx, const double pose[16]); /* SurfelMapping::setCurrentPose, core/SurfelMapping.h:66 */
 
 int sb_get_pose(sb_ctx* ctx, double pose[16]);     /* getCurrentPose */

@@ -474,7 +474,7 @@ class SurfelMapping {
    * (SurfelMapping.cpp:527-795), run by the library between updatePose() and updateMap(). The pose-graph optimisation
    * (gtsam, core/Posegraph.cpp) stays with the caller: getLoopEdges() returns the odometry and
    * loop edges the reference feeds into gtsam, optimisationRequested() mirrors the reference's trigger (:658-663); feed
-   * the optimised poses back with SurfelMap::updatePoses() + setCurrentPose() (integrateLoopClosures, :212-258). */
+   * the optimised poses back with integrateLoopClosures() (:212-258) before the next processScan. */
   void enableLoopClosure(bool on, const sb_loop_params* lp = nullptr) {
     check(sb_set_loop_closure(ctx_->get(), on ? 1 : 0, lp), ctx_->get(), "SurfelMapping::enableLoopClosure");
   }
@@ -493,6 +493,16 @@ class SurfelMapping {
   bool foundLoopClosureCandidate() const { return getLoopInfo().found_candidate != 0; }  // SurfelMapping.h:88
   bool useLoopClosureCandidate() const { return getLoopInfo().use_candidate != 0; }      // SurfelMapping.h:89
   bool optimisationRequested() const { return getLoopInfo().optimisation_requested != 0; }
+  /** SurfelMapping::integrateLoopClosures (:212-258) with the optimised poses of scans 0 .. poses.size()-1 (empty: the
+   * graph's own poses); returns the number of poses written to the map's pose table, 0 if no request was pending */
+  uint32_t integrateLoopClosures(const std::vector<Matrix4d>& poses = std::vector<Matrix4d>()) {
+    std::vector<double> a(poses.size() * 16);
+    for (size_t i = 0; i < poses.size(); ++i) std::memcpy(&a[16 * i], poses[i].m, 128);
+    uint32_t n = 0;
+    check(sb_integrate_loop_closures(ctx_->get(), poses.empty() ? nullptr : a.data(), static_cast<uint32_t>(poses.size()), &n),
+          ctx_->get(), "SurfelMapping::integrateLoopClosures");
+    return n;
+  }
   /** SurfelMapping::setCurrentPose, SurfelMapping.h:66 */
   void setCurrentPose(const Matrix4d& pose) {
     check(sb_set_current_pose(ctx_->get(), pose.m), ctx_->get(), "SurfelMapping::setCurrentPose");

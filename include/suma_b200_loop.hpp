@@ -10,8 +10,8 @@
 //
 // Out of scope: the pose-graph OPTIMISATION itself (gtsam Levenberg-Marquardt, Posegraph.cpp:90-101).
 // PoseGraphLite below only stores what the reference feeds into gtsam (initial poses, odometry and loop edges); a host
-// application optimises those with gtsam and hands the result back through LoopState::apply_optimized_poses() -- the
-// counterpart of SurfelMapping::integrateLoopClosures (:212-258).
+// application optimises those with gtsam and hands the result back through State::integrate() -- the body of
+// SurfelMapping::integrateLoopClosures (:212-258).
 //
 // Backend concept (all matrices column-major 4x4):
 //   float  confidence_threshold();                                            // getConfidenceThreshold()
@@ -154,6 +154,9 @@ struct State {
     already_verified = false;
     time_without_loop_closure = loop_count = 0;
     found_candidate = use_candidate = optimisation_requested = false;
+    before_id = -1;
+    before_loop_count = 0;
+    requested_size = 0;
     last_added_candidate = -1;
     candidates_tested = loop_edges_added = 0;
   }
@@ -171,19 +174,51 @@ struct State {
     trajectory_distances[timestamp] = distance;
   }
 
-  // integrateLoopClosures(), :212-258, for a host application that optimised `graph` elsewhere (gtsam)
-  void apply_optimized_poses(const std::vector<M4>& optimized) {
-    for (size_t i = 0; i < optimized.size() && i < graph.poses.size(); ++i) graph.poses[i] = optimized[i];
+  // What optimizeAsync() (:818-825) records when the optimisation is requested: the scan, its pose and the loop count.
+  int32_t before_id = -1;
+  uint32_t before_loop_count = 0;
+  M4 before_pose = identity();
+  size_t requested_size = 0;  // poses in the graph at that moment = what the host application optimises
+
+  void request_optimisation(uint32_t timestamp) {
+    optimisation_requested = true;
+    before_id = (int32_t)timestamp;
+    before_loop_count = loop_count;
+    before_pose = graph.pose((int32_t)timestamp);
+    requested_size = graph.poses.size();
+  }
+
+  // integrateLoopClosures(), :212-258, for a host application that optimised the first `requested_size` poses of `graph`
+  // elsewhere (gtsam). Later poses and the current pose are carried along by the correction of the pose the request was
+  // made at. Returns every pose of the graph afterwards -- what the reference hands to SurfelMap::updatePoses (as float).
+  std::vector<M4> integrate(const std::vector<M4>& poses_opt, M4& current, M4& current_old, M4& current_new) {
+    std::vector<M4> all;
+    if (!optimisation_requested || before_id < 0 || (size_t)before_id >= poses_opt.size()) return all;
+    const std::vector<M4> before = graph.poses;  // posegraph_->poses()
+    for (size_t i = 0; i < poses_opt.size(); ++i) {
+      all.push_back(poses_opt[i]);
+      graph.set_initial((int32_t)i, poses_opt[i]);
+    }
+    loop_count -= before_loop_count;                                                    // :223
+    const M4 difference = mul(poses_opt[(size_t)before_id], rigid_inverse(before_pose)); // :224
+    for (size_t i = poses_opt.size(); i < before.size(); ++i) {
+      const M4 moved = mul(difference, before[i]);
+      all.push_back(moved);
+      graph.set_initial((int32_t)i, moved);
+    }
+    optimisation_requested = false;           // currentlyOptimizing_ = false
+    current = mul(difference, current);       // :236
+    current_new = current_old = current;      // :240
+    trajectory_distances.resize(graph.poses.size());
     M4 last = graph.pose(0);
     float distance = 0;
-    trajectory_distances.resize(graph.poses.size());
-    for (size_t t = 0; t < graph.poses.size(); ++t) {
-      distance += (float)translation_distance(last, graph.poses[t]);
+    for (size_t t = 0; t < graph.poses.size(); ++t) {  // :242-250 (float += double)
+      distance = (float)((double)distance + translation_distance(last, graph.poses[t]));
       trajectory_distances[t] = distance;
       last = graph.poses[t];
     }
-    loop_count = 0;
-    optimisation_requested = false;
+    before_id = -1;
+    return all;
   }
 };
 
@@ -306,7 +341,8 @@ void check_loop_closure(State& s, Backend& be, uint32_t timestamp, Poses& P) {
   }
   s.verified.clear();
   // :658-663 -- the reference clones the graph and optimises it asynchronously with gtsam; here: a flag for the host
-  if (s.loop_count > 6 || (s.loop_count > 0 && s.time_without_loop_closure > 3)) s.optimisation_requested = true;
+  if (!s.optimisation_requested && (s.loop_count > 6 || (s.loop_count > 0 && s.time_without_loop_closure > 3)))
+    s.request_optimisation(timestamp);
 
   // 3. search a new candidate (:665-776)
   if (s.time_without_loop_closure > 3) {

@@ -85,6 +85,7 @@ def lib():
         L.orc_set_threads.restype = C.c_int; L.orc_set_threads.argtypes = [C.c_int]
         L.orc_loop_attach.restype = C.c_void_p
         L.orc_loop_edges.restype = C.c_uint32
+        L.orc_loop_integrate.restype = C.c_uint32
     return _lib
 
 
@@ -312,6 +313,13 @@ class Slam:
         d.update(valid_ratio=np.float32(ratios[0]), outlier_ratio=np.float32(ratios[1]), rel_error=np.float32(ratios[2]),
                  residual_old=ratios[3], residual_new=ratios[4], current_pose_old=from_colmajor(pose))
         return d
+
+    def integrate_loop_closures(self, poses=None):
+        """SurfelMapping::integrateLoopClosures before the next scan; poses=None: the identity "optimiser" """
+        if poses is None:
+            return int(lib().orc_loop_integrate(self.loop, None, C.c_uint32(0)))
+        a = np.ascontiguousarray([colmajor(P, np.float64) for P in poses], np.float64)
+        return int(lib().orc_loop_integrate(self.loop, _p(a, C.c_double), C.c_uint32(a.shape[0])))
 
     def loop_edges(self):
         n = int(self.loop_info()["n_edges"])

@@ -116,6 +116,37 @@ void orc_loop_info(const orc_loop* L, int64_t info[12], double ratios[5], double
   ratios[3] = S.result_old.residual; ratios[4] = S.result_new.residual;
   memcpy(current_pose_old, L->current_pose_old, 128);
 }
+/* SurfelMapping::integrateLoopClosures (SurfelMapping.cpp:212-258) at the start of a scan, with the optimiser replaced by
+ * the identity (poses16 == NULL: the poses the graph held when the optimisation was requested) or by the caller's poses
+ * (n x 16 doubles, column-major). Returns the number of poses handed to SurfelMap::updatePoses, 0 if nothing was pending. */
+uint32_t orc_loop_integrate(orc_loop* L, const double* poses16, uint32_t n) {
+  lp::State& S = L->st;
+  if (!S.optimisation_requested) return 0;
+  std::vector<lp::M4> opt;
+  if (poses16) {
+    opt.resize(n);
+    for (uint32_t i = 0; i < n; ++i) memcpy(opt[i].m, poses16 + 16 * (size_t)i, 128);
+  } else {
+    opt.assign(S.graph.poses.begin(), S.graph.poses.begin() + (long)S.requested_size);
+  }
+  lp::M4 cur, cold, cnew;
+  memcpy(cur.m, orc_slam_pose_member(L->slam, 0), 128);
+  memcpy(cold.m, orc_slam_pose_member(L->slam, 1), 128);
+  memcpy(cnew.m, orc_slam_pose_member(L->slam, 2), 128);
+  std::vector<lp::M4> all = S.integrate(opt, cur, cold, cnew);
+  if (all.empty()) return 0;
+  memcpy(orc_slam_pose_member(L->slam, 0), cur.m, 128);
+  memcpy(orc_slam_pose_member(L->slam, 1), cold.m, 128);
+  memcpy(orc_slam_pose_member(L->slam, 2), cnew.m, 128);
+  memcpy(L->current_pose_old, cold.m, 128);
+  for (size_t t = 0; t < all.size(); ++t) {  // map_->updatePoses(casted_poses), SurfelMap.cpp:485-490
+    float pf[16];
+    lp::to_float(all[t], pf);
+    orc_map_set_pose(orc_slam_map(L->slam), (uint32_t)t, pf);
+  }
+  return (uint32_t)all.size();
+}
+
 uint32_t orc_loop_edges(const orc_loop* L, int32_t* from_to, double* rel16, uint32_t cap) {
   const auto& E = L->st.graph.edges;
   uint32_t k = (uint32_t)E.size() < cap ? (uint32_t)E.size() : cap;

@@ -136,6 +136,7 @@ def lib(build_if_missing=True):
         "sb_process_scan": [vp, vp, vp, vp, u32, C.c_int], "sb_prefetch_scan": [vp, vp, vp, vp, u32],
         "sb_set_loop_closure": [vp, C.c_int, vp], "sb_get_loop_info": [vp, vp], "sb_get_loop_edges": [vp, vp, u32, C.POINTER(u32)],
         "sb_set_current_pose": [vp, pd], "sb_default_loop_params": [vp],
+        "sb_integrate_loop_closures": [vp, pd, u32, C.POINTER(u32)],
         "sb_get_pose": [vp, pd], "sb_get_last_pose": [vp, pd], "sb_timestamp": [vp, C.POINTER(u32)], "sb_slam_frame": [vp, C.c_int, pv],
         "sb_get_statistics": [vp, pd],
         "sb_comm_export": [vp, vp], "sb_comm_init": [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int],
@@ -170,7 +171,7 @@ EXPORTED_SYMBOLS = [
     "sb_map_update_debug", "sb_map_submap_origin", "sb_process_scan", "sb_prefetch_scan", "sb_get_pose", "sb_get_last_pose", "sb_timestamp", "sb_slam_frame",
     "sb_get_statistics", "sb_comm_export", "sb_comm_init", "sb_comm_shutdown", "sb_comm_set_callback",
     "sb_profile_enable", "sb_default_loop_params", "sb_set_loop_closure", "sb_get_loop_info", "sb_get_loop_edges",
-    "sb_set_current_pose",
+    "sb_set_current_pose", "sb_integrate_loop_closures",
     "sb_profile_kernels", "sb_profile_name", "sb_profile_collect",
 ]
 
@@ -563,6 +564,19 @@ class SurfelMapping:
         arr = (LoopEdge * max(n.value, 1))()
         self.ctx.check(lib().sb_get_loop_edges(self.ctx.h, arr, n.value, C.byref(n)), "get_loop_edges")
         return [(arr[i].from_, arr[i].to, from_colmajor(np.array(arr[i].rel_pose))) for i in range(n.value)]
+
+    def integrateLoopClosures(self, poses=None):
+        """SurfelMapping::integrateLoopClosures (SurfelMapping.cpp:212-258) before the next processScan: `poses` = the
+        optimised 4x4 poses of scans 0..n-1 (None: the graph's own); returns the number of poses written, 0 if no
+        optimisation request was pending"""
+        n = C.c_uint32(0)
+        if poses is None:
+            self.ctx.check(lib().sb_integrate_loop_closures(self.ctx.h, None, 0, C.byref(n)), "integrate_loop_closures")
+        else:
+            a = np.ascontiguousarray([colmajor(P, np.float64) for P in poses], np.float64)
+            self.ctx.check(lib().sb_integrate_loop_closures(self.ctx.h, _dp(a), a.shape[0], C.byref(n)),
+                           "integrate_loop_closures")
+        return int(n.value)
 
     def setCurrentPose(self, pose):
         """SurfelMapping::setCurrentPose (core/SurfelMapping.h:66)"""

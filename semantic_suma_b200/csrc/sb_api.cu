@@ -1765,6 +1765,42 @@ int sb_get_loop_edges(sb_ctx* c, sb_loop_edge* dst, uint32_t cap, uint32_t* n) {
   return SB_OK;
 }
 
+// SurfelMapping::integrateLoopClosures (SurfelMapping.cpp:212-258): the host application optimised the pose graph the
+// library recorded (sb_get_loop_edges / sb_get_optimisation_request) and hands the poses of scans 0 .. n-1 back. The
+// bookkeeping is State::integrate of include/suma_b200_loop.hpp (shared with the oracle twin and checked there against the
+// reference's own code); here only its consequences reach the device: SurfelMap::updatePoses and the current pose.
+int sb_integrate_loop_closures(sb_ctx* c, const double* poses16, uint32_t n, uint32_t* integrated) {
+  namespace lp = suma_b200::loop;
+  if (integrated) *integrated = 0;
+  if (!c) return SB_ERR_INVALID;
+  cudaSetDevice(c->device);
+  lp::State& S = c->loop;
+  if (!c->close_loops || !S.optimisation_requested) return SB_OK;  // nothing pending (the reference: !currentlyOptimizing_)
+  std::vector<lp::M4> opt;
+  if (poses16) {
+    if (n <= (uint32_t)S.before_id) return fail(c, SB_ERR_INVALID, "integrate_loop_closures: fewer poses than the graph held at the request");
+    opt.resize(n);
+    for (uint32_t i = 0; i < n; ++i) memcpy(opt[i].m, poses16 + 16 * (size_t)i, 128);
+  } else {  // identity "optimiser": the poses the graph held when the optimisation was requested
+    opt.assign(S.graph.poses.begin(), S.graph.poses.begin() + (long)S.requested_size);
+  }
+  lp::M4 cur, cold, cnew;
+  memcpy(cur.m, c->currentPose, 128);
+  memcpy(cold.m, c->currentPose_old, 128);
+  memcpy(cnew.m, c->currentPose_new, 128);
+  std::vector<lp::M4> all = S.integrate(opt, cur, cold, cnew);
+  if (all.empty()) return fail(c, SB_ERR_STATE, "integrate_loop_closures: no optimisation request pending");
+  std::vector<float> pf(all.size() * 16);
+  for (size_t t = 0; t < all.size(); ++t) lp::to_float(all[t], &pf[16 * t]);
+  int r = sb_map_update_poses(c, pf.data(), (uint32_t)all.size());  // map_->updatePoses(casted_poses)   :232
+  if (r) return r;
+  memcpy(c->currentPose_old, cold.m, 128);  // currentPose_new_ = currentPose_old_ = currentPose_   :240
+  memcpy(c->currentPose_new, cnew.m, 128);
+  if ((r = sb_set_current_pose(c, cur.m))) return r;  // currentPose_ = difference * currentPose_   :236 (host + device copy)
+  if (integrated) *integrated = (uint32_t)all.size();
+  return SB_OK;
+}
+
 int sb_set_current_pose(sb_ctx* c, const double pose[16]) {  // SurfelMapping::setCurrentPose, SurfelMapping.cpp:880-882
   if (!c || !pose) return SB_ERR_INVALID;
   cudaSetDevice(c->device);

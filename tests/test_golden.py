@@ -51,44 +51,3 @@ def test_cuda_matches_golden():
         assert [G.digest(x) for x in sl.getLastModelFrame().maps()] == g["frame"]
         sl.ctx.close()
 
-
-@pytest.mark.gpu
-def test_cuda_matches_the_reference_generated_golden():
-    """the CUDA path against digests of what THE REFERENCE ITSELF computed (oracle/_ref/libsuma_ref_full.so in the build
-    container): preprocessing of four scans and a map update / rendering tour that shifts the submap window -- everything
-    on the path that does not pass through the reference's fp32 blending of the 48 ICP values"""
-    from semantic_suma_b200 import api
-    from golden import make_reference_golden as RG
-    from helpers import sized
-    ref = json.load(open(os.path.join(HERE, "golden", "reference_golden.json")))
-
-    class CudaEngine:
-        def __init__(self, p):
-            self.ctx = api.Context(api.default_params(**sized(900)))
-            self.map = api.SurfelMap(self.ctx)
-
-        def preprocess(self, pts, lab, prb, timestamp):
-            f = api.Frame(self.ctx, 900, 64)
-            api.Preprocessing(self.ctx).process(pts, f, lab, prb, timestamp)
-            return f
-
-        def maps(self, frame):
-            return frame.maps()
-
-        def map_update(self, T, frame):
-            self.map.update(T, frame)
-
-        def map_render(self, T, ct):
-            out = api.Frame(self.ctx, 900, 64)
-            self.map.render(T, T, out, ct)
-            return out.maps()
-
-        def map_surfels(self):
-            return self.map.getAllSurfels()
-
-        def close(self):
-            self.ctx.close()
-
-    got = RG.compute(CudaEngine, process_scan=False)
-    for k in got:
-        assert got[k] == ref[k], k
