@@ -87,7 +87,7 @@ def test_gauss_newton_on_the_reference_classes_equals_oracle():
     assert_bits_equal(pose, opose, "final pose")
 
 
-@pytest.mark.parametrize("width,semantic,frames", [(900, False, 6), (900, True, 5), (2048, False, 3)])
+@pytest.mark.parametrize("width,semantic,frames", [(900, False, 6), (900, True, 5), (2048, False, 3), (2048, True, 3)])
 def test_process_scan_of_the_reference_equals_oracle(width, semantic, frames):
     """SurfelMapping::processScan with config/default.xml: initialize, preprocess, render (old / new / composed + compose
     pass), updatePose (Gauss-Newton, render_active, statistics pass), updateMap (index map, radius, update, generate, copy
