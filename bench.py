@@ -3,7 +3,9 @@
 HDL-64E-shaped scans: 64 x 2048 range images, exactly 10 Gauss-Newton iterations (BASELINE.json configs[1]).
 
   python bench.py --gpus N --steps K --warmup W            # N > 1: launched under torchrun, one rank per GPU
-  python bench.py --impl reference --steps K --warmup W    # the CPU restatement of the reference on the host cores
+  python bench.py --impl reference --steps K --warmup W    # the CPU restatement of the reference (oracle/, OpenMP) on the host
+                                                           # cores; --reference-kind itself: the reference's own classes
+                                                           # and shaders on the single-thread software GL (oracle/_ref)
 
 One step = one scan through the whole path (K1-K3 preprocessing, model rendering, 10 x (K5 + GN step), post-ICP
 rendering + statistics pass, K6 map update, model re-render). `value` is measured with the scans already resident in
@@ -528,6 +530,47 @@ def reference_itself_sample(w, scans, budget_s=12.0, max_frames=6):
         return {"unavailable": str(e)[:200]}
 
 
+def run_reference_itself(args, w, world, scans, pre):
+    """--impl reference --reference-kind itself: SurfelMapping::processScan of the reference (oracle/_ref/libsuma_ref_full.so)
+    on the same pre-rolled sequence; single thread, software GL"""
+    from oracle import oracle as O
+    from oracle import ref as R
+    sys.stdout.flush()
+    saved, null = os.dup(1), os.open(os.devnull, os.O_WRONLY)
+    os.dup2(null, 1)  # the reference's classes print to stdout
+    try:
+        f = R.Full(O.default_params(**param_kwargs(w)))
+        for i in range(pre):
+            f.process_scan(*scans[i])
+        t0 = time.time()
+        done = 0
+        for i in range(args.steps):
+            f.process_scan(*scans[pre + i])
+            done += 1
+            if time.time() - t0 > args.ref_budget:
+                break
+        dt = time.time() - t0
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(null)
+    v = done / dt
+    return {
+        "impl": "reference", "metric": "scans_per_sec", "value": round(v, 3), "unit": "scans/s", "n_gpus": world,
+        "steps": done, "warmup": args.warmup, "ms_per_step": round(1e3 * dt / done, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "range_image": "%dx%d" % (w["height"], w["width"]),
+                   "icp_iterations": w["iters"], "semantic": w["semantic"], "map_preroll_scans": args.preroll,
+                   "note": "the reference's own core classes and GLSL shaders (compiled / transpiled from /root/reference, "
+                           "oracle/_ref) on a single-thread software GL -- an emulation of its GPU path, not its speed on a GPU"},
+        "cpu_baseline": {"value": round(v, 3), "unit": "scans/s", "cores": 1, "kind": "reference",
+                         "sample": "%d scans after %d pre-roll + %d warm-up scans, one thread" % (done, args.preroll, args.warmup),
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": round(v, 3), "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
 def run_reference(args, w, rank, world):
     """--impl reference: the reference has no CPU (or buildable GL) path in this environment; the arm times the
     oracle's restatement of it (C + OpenMP, thread-count independent results) on the same workload, same pre-rolled map."""
@@ -535,6 +578,8 @@ def run_reference(args, w, rank, world):
         return None
     pre = args.preroll + args.warmup
     scans = generate_scans(w, pre + args.steps, seed=1337)
+    if args.reference_kind == "itself":
+        return run_reference_itself(args, w, world, scans, pre)
     from oracle import oracle as O
     threads = O.set_threads(oracle_threads())
     po = O.default_params(**param_kwargs(w))
@@ -593,6 +638,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ref-budget", type=float, default=240.0)
+    ap.add_argument("--reference-kind", default="port", choices=["port", "itself"],
+                    help="--impl reference: 'port' times oracle/ (C + OpenMP, the stricter baseline, default); 'itself' times "
+                         "the reference's own classes and shaders on the single-thread software GL (oracle/_ref)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
