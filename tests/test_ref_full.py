@@ -130,6 +130,29 @@ def test_parameter_branches_of_the_reference_equal_oracle():
             _step_equal(f, osl, sc[t], "%r t=%d" % (kw, t))
 
 
+GEOMETRIES = [dict(data_width=450, data_height=64, model_width=512, model_height=64),      # model image != data image
+              dict(data_width=450, data_height=64, model_width=450, model_height=96),
+              dict(data_width=600, data_height=32, model_width=300, model_height=32),
+              dict(data_width=450, data_height=64, model_width=450, model_height=64, data_fov_up=10.0, data_fov_down=-30.0,
+                   model_fov_up=10.0, model_fov_down=-30.0),
+              dict(data_width=450, data_height=64, model_width=450, model_height=64, min_depth=1.0, max_depth=40.0,
+                   model_min_depth=1.0, model_max_depth=40.0),
+              dict(data_width=450, data_height=64, model_width=450, model_height=64, model_fov_up=5.0, model_fov_down=-28.0)]
+
+
+def test_image_geometries_of_the_reference_equal_oracle():
+    """model image size / field of view / depth range different from the data image's (the classes take them from separate
+    parameters): three semantic scans each"""
+    for kw in GEOMETRIES:
+        p = O.default_params(**kw)
+        scene = synth.Scene(width=kw["data_width"], height=kw["data_height"], fov_up=kw.get("data_fov_up", 3.0),
+                            fov_down=kw.get("data_fov_down", -25.0), semantic=True)
+        poses = synth.trajectory(3)
+        f, osl = _both(p)
+        for t in range(3):
+            _step_equal(f, osl, scene.scan(t, poses[t]), "%r t=%d" % (kw, t))
+
+
 def test_ouster_size_of_the_reference_equals_oracle():
     """BASELINE.json configs[3]: 128x4096, +-22.5 degrees, 15 iterations -- two scans"""
     kw = dict(data_width=4096, model_width=4096, data_height=128, model_height=128, data_fov_up=22.5, data_fov_down=-22.5,
