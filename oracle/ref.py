@@ -301,30 +301,31 @@ def full_available():
 
 
 DEFAULT_XML = os.path.join(REFERENCE, "config", "default.xml")
-_full = None
+_full = {}
 
 
-def full_lib():
-    global _full
-    if _full is None:
+def full_lib(mode="pinned"):
+    """mode "pinned": what GL / Eigen / libm leave open follows the oracle's rules (bit-for-bit comparisons); "precise": nothing
+    is pinned -- GLSL built-ins in fp64/libm, general matrix inverse, left-looking LDLT, libm sin/cos (tolerance comparisons)"""
+    if mode not in _full:
         build()
-        L = C.CDLL(lib_path("full"))
+        L = C.CDLL(lib_path("full" if mode == "pinned" else "full_precise"))
         L.reffull_create.restype = C.c_void_p
         L.reffull_error.restype = C.c_char_p
         for f in ("reffull_map_size", "reffull_map_download", "reffull_slam_timestamp", "reffull_slam_edges"):
             getattr(L, f).restype = C.c_uint32
         L.reffull_slam_statistic.restype = C.c_double
         L.reffull_draw_calls.restype = C.c_uint64
-        _full = L
-    return _full
+        _full[mode] = L
+    return _full[mode]
 
 
 class Full:
     """one parameter list + lazily constructed Preprocessing / SurfelMap / SurfelMapping of the reference"""
 
-    def __init__(self, p, zero_stale_tail=True, **extra):
+    def __init__(self, p, zero_stale_tail=True, mode="pinned", **extra):
         self.p = p
-        self.L = full_lib()
+        self.L = full_lib(mode)
         xml = DEFAULT_XML if os.path.exists(DEFAULT_XML) else ""
         self.h = C.c_void_p(self.L.reffull_create(C.byref(p), xml.encode()))
         self._check(0)

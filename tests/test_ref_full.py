@@ -231,6 +231,28 @@ def test_submap_paging_of_the_reference_equals_oracle():
             assert_bits_equal(a, b, "map frame %d %s" % (w, name))
 
 
+def test_unpinned_reference_agrees_with_the_cuda_contract_within_tolerances():
+    """libsuma_ref_full_precise.so: the same classes and shaders with NOTHING pinned to the oracle's rules (GLSL built-ins in
+    fp64 / libm, the stand-in Eigen's general inverse and left-looking LDLT, libm's sin / cos, fp32 blending of the 48 values)
+    against the oracle in its default mode -- exact sums, the contract of the CUDA path. An independent legal implementation
+    of everything OpenGL / Eigen / libm leave open: decisions flip only within rounding of a threshold, so poses stay within
+    2e-3 m (the Gauss-Newton stop tests are 1e-4) and surfel counts within 0.2 % over eight scans, without drift."""
+    old = O.gl_sums(0)
+    try:
+        for width, semantic, frames, kw in ((900, True, 8, {}), (900, False, 6, dict(max_iterations=10, stopping_threshold=0.0, delta=0.0))):
+            p = O.default_params(**sized(width), **kw)
+            sc, _ = scans(width, n=frames, semantic=semantic)
+            f, osl = R.Full(p, mode="precise"), O.Slam(p)
+            for t in range(frames):
+                f.process_scan(*sc[t])
+                osl.process_scan(*sc[t])
+                assert np.abs(f.pose() - osl.pose()).max() < 2e-3, "t=%d pose" % t
+                assert abs(f.map_size() - osl.map.size()) <= 2e-3 * osl.map.size(), "t=%d surfel count" % t
+            assert_bits_equal(R.Full(p, mode="precise").preprocess(*sc[0])[0], O.preprocess(p, *sc[0])[0], "vertex map")
+    finally:
+        O.gl_sums(old)
+
+
 def test_loop_closure_of_the_reference_equals_oracle_twin():
     """SurfelMapping::checkLoopClosure (:527-795) and integrateLoopClosures (:212-258) on the synthetic loop of the GPU
     test (64x300 here): the candidate is found at the same scan, verified, the same loop edges enter the pose graph, the
