@@ -15,7 +15,8 @@
  *                          path does (orc_set_gl_sums), oracle and reference agree BIT FOR BIT over whole runs -- poses,
  *                          iteration counts, frames, every surfel record -- incl. the track-loss fallback, submap paging,
  *                          loop-closure detection, 24 parameter variants, 64x900 / 64x2048 / 128x4096
- *                          (tests/test_ref_full.py); tests/golden/reference_golden.json holds digests of its outputs.
+ *                          (tests/test_ref_full.py); tests/golden/reference_golden.json holds digests of its outputs. An UNPINNED build of the same
+ *                          library (libsuma_ref_full_precise.so) agrees with this oracle within 2e-3 m / 0.2 %.
  *   libsuma_ref_pinned.so / _precise.so   the shaders per operator, also on adversarial random inputs
  *                          (tests/test_ref_shaders.py); _host.so: the host sources unpinned (tests/test_ref_host.py).
  * The default mode of this oracle (exact Q33.30 sums of the 48 values) is the contract of the CUDA path; it differs from
