@@ -38,7 +38,8 @@ def build(force=False):
     """(re)build oracle/_ref from the reference's sources where they lie; no-op when /root/reference is absent"""
     if not have_reference():
         return available()
-    cmd = ["make", "-C", _HARNESS, "-s", "REFERENCE=" + REFERENCE] + (["-B"] if force else [])
+    cmd = ["make", "-C", _HARNESS, "-s", "-j%d" % max(1, min(8, os.cpu_count() or 1)), "REFERENCE=" + REFERENCE] + \
+        (["-B"] if force else [])
     subprocess.check_call(cmd)
     return True
 
