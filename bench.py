@@ -355,7 +355,8 @@ def run_native(args, w, rank, world, local_rank):
 
     out = None
     if rank == 0:
-        cpu = None if args.no_cpu_baseline else cpu_baseline(w, scans, budget_s=args.cpu_budget)
+        # the CPU baseline is timed at N = 1 only (rank 0); the N > 1 lines carry null
+        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(w, scans, budget_s=args.cpu_budget)
         value = world * args.steps / (ms_dev * 1e-3)
         e2e_value = world * args.steps / (ms_e2e * 1e-3)
         out = {
