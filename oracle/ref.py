@@ -398,6 +398,13 @@ class Full:
         k = self.L.reffull_map_download(self.h, a.ctypes.data_as(C.c_void_p), C.c_uint32(n))
         return a[:k]
 
+    def map_upload(self, surfels, timestamp):
+        a = np.ascontiguousarray(surfels, O.SURFEL_DTYPE)
+        self._check(self.L.reffull_map_upload(self.h, a.ctypes.data_as(C.c_void_p), C.c_uint32(a.shape[0]), C.c_uint32(timestamp)))
+
+    def map_set_pose(self, t, pose):
+        self._check(self.L.reffull_map_set_pose(self.h, C.c_uint32(t), _p(colmajor(pose, np.float32))))
+
     def map_update(self, pose, frame):
         fv, fn, fs = [_f32(a) for a in frame]
         self._check(self.L.reffull_map_update(self.h, _p(colmajor(pose, np.float32)), _p(fv), _p(fn), _p(fs)))

@@ -222,9 +222,23 @@ uint64_t reffull_draw_calls(void) { return sgl::ctx().draw_calls; }
 void reffull_zero_stale_tail(int on) { sgl::ctx().zero_stale_tail = on != 0; }
 
 // ---------------------------------------------------------------------------------------------- SurfelMap (core/SurfelMap.cpp)
+// test access to two protected members of SurfelMap (the class itself is untouched): put a given surfel set and pose
+// table in place, as a sequence of update() calls would have
+struct MapAccess : public SurfelMap {
+  using SurfelMap::SurfelMap;
+  void upload(const std::vector<Surfel>& s, uint32_t timestamp) {
+    surfels_.assign(s);
+    timestamp_ = timestamp;
+  }
+  void set_pose(uint32_t t, const Eigen::Matrix4f& P) {  // what update() does for its own timestamp (SurfelMap.cpp:494-495)
+    if (t >= poses_.size()) return;
+    poses_[t] = P;
+    poseBuffer_.insert(t, P);
+  }
+};
 static SurfelMap* the_map(reffull* h) {
   if (h->slam) return h->slam->getMap().get();
-  if (!h->map) h->map.reset(new SurfelMap(h->params));
+  if (!h->map) h->map.reset(new MapAccess(h->params));
   return h->map.get();
 }
 static void frame_from(Frame& f, const float* v, const float* n, const float* s) {
@@ -243,6 +257,22 @@ uint32_t reffull_map_download(reffull* h, orc_surfel* dst, uint32_t cap) {
   uint32_t k = std::min<uint32_t>(cap, (uint32_t)all.size());
   if (k) memcpy(dst, all.data(), sizeof(orc_surfel) * k);
   return k;
+}
+int reffull_map_upload(reffull* h, const orc_surfel* src, uint32_t n, uint32_t timestamp) {
+  REFFULL_TRY({
+    if (h->slam) throw std::runtime_error("map_upload: only for a stand-alone SurfelMap");
+    the_map(h);
+    std::vector<Surfel> v(n);
+    if (n) memcpy(v.data(), src, sizeof(Surfel) * n);
+    static_cast<MapAccess*>(h->map.get())->upload(v, timestamp);
+  })
+}
+int reffull_map_set_pose(reffull* h, uint32_t t, const float pose[16]) {
+  REFFULL_TRY({
+    if (h->slam) throw std::runtime_error("map_set_pose: only for a stand-alone SurfelMap");
+    the_map(h);
+    static_cast<MapAccess*>(h->map.get())->set_pose(t, m4f(pose));
+  })
 }
 // SurfelMap::update (SurfelMap.cpp:492-584), including updateActiveSubmaps
 int reffull_map_update(reffull* h, const float pose[16], const float* fv, const float* fn, const float* fs) {

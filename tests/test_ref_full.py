@@ -231,6 +231,48 @@ def test_submap_paging_of_the_reference_equals_oracle():
             assert_bits_equal(a, b, "map frame %d %s" % (w, name))
 
 
+@pytest.mark.parametrize("t_now,compose", [(150, 1), (40, 1), (150, 0)])
+def test_random_surfel_clouds_through_the_reference_classes(t_now, compose):
+    """the adversarial map inputs of tests/test_ref_shaders.py (random surfels of any orientation, huge and tiny discs across
+    the azimuth seam, negative confidences, old and new creation times, movable labels; points outside the field of view)
+    through SurfelMap::render / render_active / render_inactive / render_composed / update of the reference itself"""
+    from test_ref_shaders import _random_cloud, _random_surfels
+    rng = np.random.default_rng(t_now + compose)
+    p = O.default_params(**sized(360, 32), compose_rendering=compose)
+    pts, lab, prob = _random_cloud(rng, 30000, p)
+    lab[:] = rng.choice(np.array((0, 10, 30, 40, 50), np.float32), lab.shape[0])
+    om, f = O.Map(p), R.Full(p)
+    S = _random_surfels(rng, 20000, t_now)
+    pose = np.eye(4)
+    pose[:3, 3] = (0.3, -0.2, 0.1)
+    a = np.deg2rad(3.0)
+    pose[:2, :2] = [[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]
+    om.upload(S, t_now)
+    f.map_upload(S, t_now)
+    for t in range(0, t_now + 1, 7):
+        T = np.eye(4); T[:3, 3] = (0.01 * t, 0.002 * t, 0.0)
+        om.set_pose(t, T)
+        f.map_set_pose(t, T)
+    data = O.preprocess(p, pts, lab, prob, timestamp=t_now)
+    for g, o, name in zip(f.preprocess(pts, lab, prob, timestamp=t_now), data, "vns"):
+        assert_bits_equal(g, o, "preprocess " + name)
+    for g, o, name in zip(f.map_render(np.eye(4), pose, 0.5), om.render(np.eye(4), pose, 0.5), "vns"):
+        assert_bits_equal(g, o, "render " + name)
+    for w in range(3):
+        for g, o, name in zip(f.map_frame(w), om.frame(w), "vns"):
+            assert_bits_equal(g, o, "frame %d %s" % (w, name))
+    om.render_active(pose, 0.2); f.map_render_active(pose, 0.2)
+    om.render_inactive(pose, 0.2); f.map_render_inactive(pose, 0.2)
+    om.render_composed(np.eye(4), pose, 0.2); f.map_render_composed(np.eye(4), pose, 0.2)
+    for w in range(3):
+        for g, o, name in zip(f.map_frame(w)[:2], om.frame(w)[:2], "vn"):
+            assert_bits_equal(g, o, "single-view frame %d %s" % (w, name))
+    om.update(pose, data)
+    f.map_update(pose, data)
+    assert f.map_size() == om.size() > 0
+    surfel_fields_equal(f.map_download(), om.download(), "surfels after the update")
+
+
 def test_unpinned_reference_agrees_with_the_cuda_contract_within_tolerances():
     """libsuma_ref_full_precise.so: the same classes and shaders with NOTHING pinned to the oracle's rules (GLSL built-ins in
     fp64 / libm, the stand-in Eigen's general inverse and left-looking LDLT, libm's sin / cos, fp32 blending of the 48 values)
