@@ -538,6 +538,13 @@ class SurfelMapping {
     st["outlier"] = static_cast<float>(s[3]);
     st["invalid"] = static_cast<float>(s[4]);
     st["surfels"] = static_cast<float>(s[7]);
+    const sb_loop_info li = getLoopInfo();
+    if (li.enabled) {  // the keys checkLoopClosure writes (SurfelMapping.cpp:784-788)
+      st["residual_old"] = static_cast<float>(li.residual_old);
+      st["loop_outlier_ratio"] = li.outlier_ratio;
+      st["loop_valid_ratio"] = li.valid_ratio;
+      st["loop_relative_error_all"] = li.rel_error;
+    }
     return st;
   }
   const ContextPtr& context() const { return ctx_; }
