@@ -91,3 +91,54 @@ def test_loop_closure_integration_bit_exact():
     assert integrations == 2
     surfel_fields_equal(gsl.getMap().getAllSurfels(), osl.map.download(), "surfels after two integrations")
     gsl.ctx.close()
+
+
+def _pipeline_equal(po, pp, sc, what):
+    """tests/test_gpu_parity.py::_pipeline_equal (verified on B200s), repeated here so that this file stands alone"""
+    from oracle import oracle as O
+    from semantic_suma_b200 import api
+    osl = O.Slam(po)
+    gsl = api.SurfelMapping(pp)
+    try:
+        for t, (pts, lab, prb) in enumerate(sc):
+            osl.process_scan(pts, lab, prb)
+            gsl.processScan(pts, lab, prb)
+            assert_bits_equal(gsl.getCurrentPose(), osl.pose(), "%s t=%d pose" % (what, t))
+            so, sg = osl.stats(), gsl.getStatistics()
+            assert sg["num_iterations"] == so["iterations"], "%s t=%d iterations" % (what, t)
+            assert (sg["F"], sg["inlier"], sg["outlier"], sg["invalid"]) == (so["F"], so["inlier"], so["outlier"], so["invalid"]), \
+                "%s t=%d statistics pass" % (what, t)
+            assert gsl.getMap().size() == osl.map.size(), "%s t=%d surfel count" % (what, t)
+        surfel_fields_equal(gsl.getMap().getAllSurfels(), osl.map.download(), what + " surfels")
+        for g, o in zip(gsl.getCurrentFrame().maps(), osl.frame(0)):
+            assert_bits_equal(g, o, what + " current frame")
+        for g, o in zip(gsl.getLastModelFrame().maps(), osl.frame(1)):
+            assert_bits_equal(g, o, what + " model frame")
+    finally:
+        gsl.ctx.close()
+
+
+def test_parameter_branches_bit_exact():
+    """the 24 parameter variants tests/test_ref_full.py holds the oracle to the reference with (robust weighting, sampling,
+    compose rendering on / off, initial guess, surfel weighting / averaging schemes, confidence modes, stability, thresholds,
+    submap layout): the CUDA path against the oracle, four semantic scans at 64x450 each"""
+    from semantic_suma_b200 import synth
+    from test_ref_full import VARIANTS
+    scene = synth.Scene(width=450, height=64, semantic=True)
+    poses = synth.trajectory(4)
+    sc = [scene.scan(t, poses[t]) for t in range(4)]
+    for kw in VARIANTS:
+        po, pp = both_params(**sized(450), **kw)
+        _pipeline_equal(po, pp, sc, repr(kw))
+
+
+def test_image_geometries_bit_exact():
+    """model image size / field of view / depth range different from the data image's, through the whole pipeline"""
+    from semantic_suma_b200 import synth
+    from test_ref_full import GEOMETRIES
+    for kw in GEOMETRIES:
+        po, pp = both_params(**kw)
+        scene = synth.Scene(width=kw["data_width"], height=kw["data_height"], fov_up=kw.get("data_fov_up", 3.0),
+                            fov_down=kw.get("data_fov_down", -25.0), semantic=True)
+        poses = synth.trajectory(3)
+        _pipeline_equal(po, pp, [scene.scan(t, poses[t]) for t in range(3)], repr(kw))
