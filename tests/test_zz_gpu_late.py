@@ -2,7 +2,8 @@
 purpose, so that `pytest -x` reaches them only after the suite that was verified on B200s (tests/test_gpu_*.py,
 tests/test_golden.py). Everything they compare against is CPU-verified: the digests were computed by the reference itself
 (tests/golden/make_reference_golden.py), the loop-closure integration by the oracle twin, which tests/test_ref_full.py
-holds to the reference's own SurfelMapping::integrateLoopClosures bit for bit."""
+holds to the reference's own SurfelMapping::integrateLoopClosures bit for bit. The test LOGIC itself (keys, call order, counts,
+digests) was dry-run on the CPU with oracle-backed stand-ins for the api classes (scratch/dry_run_late_gpu_tests.py)."""
 import json
 import os
 
