@@ -17,6 +17,16 @@ def test_oracle_matches_golden():
     assert G.compute() == GOLD
 
 
+def test_reference_generated_golden_is_what_the_reference_produces():
+    """the committed digests are reproduced by running the reference itself (oracle/_ref/libsuma_ref_full.so) again"""
+    from golden import make_reference_golden as RG
+    from oracle import ref as R
+    if not R.full_available():
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    ref = json.load(open(os.path.join(HERE, "golden", "reference_golden.json")))
+    assert RG.compute(RG.ReferenceEngine) == ref
+
+
 def test_oracle_matches_the_reference_generated_golden():
     """preprocessing, map update / rendering through a paging tour, and whole processScan runs (48 ICP values added the GL
     way): the oracle reproduces the digests the reference's own classes and shaders produced in the build container"""
