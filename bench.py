@@ -349,10 +349,6 @@ def run_native(args, w, rank, world, local_rank):
     del dev, pin
     torch.cuda.empty_cache()
 
-    striped = None
-    if dist is not None and not args.no_striped:
-        striped = striped_record(striped_scans, rank, world, local_rank, dist)
-
     out = None
     if rank == 0:
         # the CPU baseline is timed at N = 1 only (rank 0); the N > 1 lines carry null
@@ -380,12 +376,49 @@ def run_native(args, w, rank, world, local_rank):
             "clocks": per_rank[0]["clocks"],
             "roofline": roofline, "kernels": kernel_table, "cpu_baseline": cpu,
         }
-        if striped is not None:
-            out["striped"] = striped
+    if dist is not None and not args.no_striped:
+        # The extra record must never cost the replica line: it runs AFTER that line is complete, under a per-rank
+        # deadline. If a rank fails or the ranks lose each other (one raised, the others wait in a collective), every
+        # rank's deadline fires: rank 0 prints the line it already has (striped = the error) and all ranks exit 0.
+        guard = StripedGuard(rank, out, args.striped_deadline)
+        guard.start()
+        try:
+            striped = striped_record(striped_scans, rank, world, local_rank, dist)
+        except Exception as e:  # noqa: BLE001
+            striped = {"error": "%s: %s" % (type(e).__name__, str(e)[:300]), "rank": rank}
+        errs = [None] * world
+        dist.all_gather_object(errs, striped.get("error") if isinstance(striped, dict) else "no record")
+        if rank == 0:
+            bad = [(r, e) for r, e in enumerate(errs) if e]
+            out["striped"] = striped if not bad else {"error": "; ".join("rank %d: %s" % be for be in bad)}
+        dist.barrier()
+        guard.cancel()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return out
+
+
+class StripedGuard(threading.Thread):
+    """deadline for the optional `striped` record of the N > 1 runs (see run_native)"""
+
+    def __init__(self, rank, out, seconds):
+        super().__init__(daemon=True)
+        self.rank, self.out, self.seconds = rank, out, seconds
+        self.done = threading.Event()
+
+    def cancel(self):
+        self.done.set()
+
+    def run(self):
+        if self.done.wait(self.seconds):
+            return
+        if self.rank == 0 and self.out is not None:
+            self.out["striped"] = {"error": "no result within %.0f s (a rank failed or the ranks lost each other); the "
+                                            "replica figures above were complete before it started" % self.seconds}
+            sys.stdout.write(json.dumps(self.out) + "\n")
+            sys.stdout.flush()
+        os._exit(0)
 
 
 STRIPED_PRE, STRIPED_STEPS = 10, 10
@@ -632,6 +665,8 @@ def main():
     ap.add_argument("--no-striped", action="store_true",
                     help="N > 1: skip the extra `striped` record (128x4096, 15 iterations, row-striped K5 with the in-kernel "
                          "peer-memory all-reduce, BASELINE.json configs[3])")
+    ap.add_argument("--striped-deadline", type=float, default=240.0,
+                    help="N > 1: seconds the `striped` record may take before the line is printed without it")
     ap.add_argument("--no-prefetch", dest="prefetch", action="store_false",
                     help="e2e pass: do not stage scan i+1 on the copy stream while scan i is processed (sb_prefetch_scan); "
                          "with or without it every copy is inside the timed region")
