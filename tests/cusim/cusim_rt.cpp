@@ -1,0 +1,363 @@
+// cusim_rt.cpp -- TEST INFRASTRUCTURE (see cusim.hpp): fibers, the block scheduler, the worker pool and the handful of CUDA
+// runtime calls libsuma_b200's host code makes, all on the CPU. "Device memory" is host memory, streams are synchronous.
+#include "cusim.hpp"
+
+#include <sys/mman.h>
+#include <time.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+extern "C" void cusim_switch(void** save_sp, void* load_sp);
+__asm__(R"(
+.text
+.globl cusim_switch
+.type cusim_switch,@function
+cusim_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  subq $8, %rsp
+  stmxcsr (%rsp)
+  fnstcw 4(%rsp)
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  ldmxcsr (%rsp)
+  fldcw 4(%rsp)
+  addq $8, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size cusim_switch,.-cusim_switch
+)");
+
+namespace cusim {
+
+enum { ST_READY = 0, ST_WARP = 1, ST_BLOCK = 2, ST_DONE = 3 };
+constexpr size_t kStack = 128 * 1024;
+constexpr int kMaxThreads = 1024;
+constexpr int kWorkers = 16;
+
+struct Warp {
+  uint64_t slot[2][32];
+  unsigned active[2];
+  unsigned gen;
+  int n;
+};
+struct Block {
+  int nthreads = 0, nwarps = 0;
+  Fiber fibers[kMaxThreads];
+  int pred[kMaxThreads];
+  Warp warps[kMaxThreads / 32];
+  void* sched_sp = nullptr;
+  int count_result = 0;
+  const std::function<void()>* body = nullptr;
+  char* stacks = nullptr;
+  const char* kernel = "";
+};
+
+thread_local Fiber* cur = nullptr;
+thread_local BlockIdx* blkid = nullptr;
+static thread_local Block* tblk = nullptr;
+
+static inline void yield_to_scheduler() {
+  Fiber* f = cur;
+  cusim_switch(&f->sp, f->blk->sched_sp);
+}
+
+static void fiber_main() {
+  Fiber* f = cur;
+  (*f->blk->body)();
+  f = cur;
+  f->state = ST_DONE;
+  yield_to_scheduler();
+  abort();  // a finished fiber is never resumed
+}
+
+void sync_block() {
+  cur->state = ST_BLOCK;
+  yield_to_scheduler();
+}
+int sync_block_count(int p) {
+  Fiber* f = cur;
+  Block* b = f->blk;
+  b->pred[f - b->fibers] = p ? 1 : 0;
+  f->state = ST_BLOCK;
+  yield_to_scheduler();
+  return b->count_result;
+}
+unsigned warp_exchange(uint64_t payload, const uint64_t** slots) {
+  Fiber* f = cur;
+  Warp* w = f->warp;
+  const unsigned g = w->gen & 1u;
+  w->slot[g][f->lane] = payload;
+  f->state = ST_WARP;
+  yield_to_scheduler();
+  *slots = w->slot[g];
+  return w->active[g];
+}
+unsigned long long globaltimer() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+}
+void ptx_unavailable(const char* what) {
+  fprintf(stderr, "cusim: %s is not available in the CPU executor\n", what);
+  abort();
+}
+
+static void deadlock(Block* b) {
+  int c[4] = {0, 0, 0, 0};
+  for (int i = 0; i < b->nthreads; ++i) c[b->fibers[i].state]++;
+  fprintf(stderr, "cusim: deadlock in kernel %s, block (%u,%u): %d ready, %d in a warp collective, %d at __syncthreads, %d done\n",
+          b->kernel, blkid->bid.x, blkid->bid.y, c[0], c[1], c[2], c[3]);
+  abort();
+}
+
+static void run_block(Block* b, dim3 bdim) {
+  const int n = (int)(bdim.x * bdim.y * bdim.z);
+  if (n > kMaxThreads || n <= 0) ptx_unavailable("block size");
+  b->nthreads = n;
+  b->nwarps = (n + 31) / 32;
+  for (int i = 0; i < n; ++i) {
+    Fiber& f = b->fibers[i];
+    f.tid.x = (unsigned)i % bdim.x;
+    f.tid.y = ((unsigned)i / bdim.x) % bdim.y;
+    f.tid.z = (unsigned)i / (bdim.x * bdim.y);
+    f.blk = b;
+    f.warp = &b->warps[i / 32];
+    f.lane = i & 31;
+    f.state = ST_READY;
+    uintptr_t top = ((uintptr_t)(b->stacks + (size_t)(i + 1) * kStack)) & ~(uintptr_t)15;
+    uint64_t* s = (uint64_t*)top;
+    s[-1] = 0;                       // return address of fiber_main (never used)
+    s[-2] = (uint64_t)(uintptr_t)&fiber_main;
+    s[-3] = s[-4] = s[-5] = s[-6] = s[-7] = s[-8] = 0;  // rbp rbx r12 r13 r14 r15
+    s[-9] = 0x1F80ull | (0x037Full << 32);              // mxcsr | x87 control word
+    f.sp = (void*)&s[-9];
+  }
+  for (int w = 0; w < b->nwarps; ++w) {
+    b->warps[w].gen = 0;
+    b->warps[w].n = (w == b->nwarps - 1) ? n - 32 * w : 32;
+  }
+  int live = n;
+  while (live > 0) {
+    bool progressed = false;
+    for (int w = 0; w < b->nwarps; ++w) {
+      Warp& W = b->warps[w];
+      Fiber* lanes = b->fibers + 32 * w;
+      for (;;) {
+        bool ran = false;
+        for (int l = 0; l < W.n; ++l) {
+          Fiber* f = lanes + l;
+          if (f->state != ST_READY) continue;
+          cur = f;
+          cusim_switch(&b->sched_sp, f->sp);
+          ran = true;
+          if (f->state == ST_DONE) --live;
+        }
+        progressed |= ran;
+        unsigned mask = 0;
+        int nblock = 0;
+        for (int l = 0; l < W.n; ++l) {
+          if (lanes[l].state == ST_WARP) mask |= 1u << l;
+          if (lanes[l].state == ST_BLOCK) ++nblock;
+        }
+        if (!mask) break;
+        if (nblock) deadlock(b);  // part of a warp at __syncthreads, part in a warp collective
+        W.active[W.gen & 1u] = mask;
+        W.gen++;
+        for (int l = 0; l < W.n; ++l)
+          if (lanes[l].state == ST_WARP) lanes[l].state = ST_READY;
+        progressed = true;
+      }
+    }
+    if (live > 0) {
+      int waiting = 0, cnt = 0;
+      for (int i = 0; i < n; ++i)
+        if (b->fibers[i].state == ST_BLOCK) {
+          ++waiting;
+          cnt += b->pred[i];
+        }
+      if (waiting == live) {
+        b->count_result = cnt;
+        for (int i = 0; i < n; ++i)
+          if (b->fibers[i].state == ST_BLOCK) {
+            b->fibers[i].state = ST_READY;
+            b->pred[i] = 0;
+          }
+        progressed = true;
+      } else if (!progressed) {
+        deadlock(b);
+      }
+    }
+  }
+  cur = nullptr;
+}
+
+// ---- worker pool -------------------------------------------------------------------------------------------------------
+struct Job {
+  LaunchCfg cfg;
+  const std::function<void()>* body = nullptr;
+  const char* name = "";
+  unsigned nblocks = 0;
+  int active_workers = 0;
+  std::atomic<unsigned> next{0};
+};
+// heap objects that are never destroyed: the detached workers wait on them until the process ends (destroying a condition
+// variable with waiters blocks)
+static std::mutex& g_mu = *new std::mutex();
+static std::mutex& g_launch_mu = *new std::mutex();
+static std::condition_variable& g_cv_start = *new std::condition_variable();
+static std::condition_variable& g_cv_done = *new std::condition_variable();
+static Job& g_job = *new Job();
+static uint64_t g_job_gen = 0;
+static int g_running = 0;
+static bool g_started = false;
+
+static int hw_threads() {
+  const char* e = getenv("CUSIM_THREADS");
+  int n = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+  if (n < 1) n = 1;
+  if (n > kWorkers) n = kWorkers;
+  return n;
+}
+
+static void worker(int id) {
+  Block* b = new Block();
+  b->stacks = (char*)mmap(nullptr, kStack * kMaxThreads, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+  if (b->stacks == (char*)MAP_FAILED) abort();
+  tblk = b;
+  BlockIdx bi;
+  blkid = &bi;
+  uint64_t seen = 0;
+  for (;;) {
+    {
+      std::unique_lock<std::mutex> lk(g_mu);
+      g_cv_start.wait(lk, [&] { return g_job_gen != seen; });
+      seen = g_job_gen;
+    }
+    if (id < g_job.active_workers) {
+      const LaunchCfg& c = g_job.cfg;
+      bi.bdim = c.block;
+      bi.gdim = c.grid;
+      b->body = g_job.body;
+      b->kernel = g_job.name;
+      for (;;) {
+        unsigned i = g_job.next.fetch_add(1);
+        if (i >= g_job.nblocks) break;
+        bi.bid.x = i % c.grid.x;
+        bi.bid.y = (i / c.grid.x) % c.grid.y;
+        bi.bid.z = i / (c.grid.x * c.grid.y);
+        run_block(b, c.block);
+      }
+    }
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      if (--g_running == 0) g_cv_done.notify_all();
+    }
+  }
+}
+
+void launch_impl(const char* name, const LaunchCfg& c, bool cooperative, const std::function<void()>& body) {
+  std::lock_guard<std::mutex> launch_lock(g_launch_mu);
+  const unsigned nblocks = c.grid.x * c.grid.y * c.grid.z;
+  if (nblocks == 0) return;
+  if (!g_started) {
+    g_started = true;
+    for (int i = 0; i < kWorkers; ++i) std::thread(worker, i).detach();
+  }
+  if (cooperative && nblocks > (unsigned)kWorkers) ptx_unavailable("a cooperative grid larger than the worker pool");
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_job.cfg = c;
+    g_job.body = &body;
+    g_job.name = name;
+    g_job.nblocks = nblocks;
+    g_job.next.store(0);
+    // blocks of a cooperative launch wait for each other: every block needs its own OS thread
+    int act = cooperative ? (int)nblocks : hw_threads();
+    if ((unsigned)act > nblocks) act = (int)nblocks;
+    g_job.active_workers = act;
+    g_running = kWorkers;
+    ++g_job_gen;
+  }
+  g_cv_start.notify_all();
+  std::unique_lock<std::mutex> lk(g_mu);
+  g_cv_done.wait(lk, [] { return g_running == 0; });
+}
+
+}  // namespace cusim
+
+// ---- the runtime calls of sb_api.cu ------------------------------------------------------------------------------------
+struct cusimStream { int dummy; };
+struct cusimEvent { double ms; };
+static double now_ms() { return (double)cusim::globaltimer() * 1e-6; }
+
+cudaError_t cudaMalloc(void** p, size_t n) {
+  void* q = nullptr;
+  if (posix_memalign(&q, 512, n ? n : 1)) return cudaErrorMemoryAllocation;
+  *p = q;
+  return cudaSuccess;
+}
+cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
+cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { if (n) memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemset(void* d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { if (n) memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = new cusimStream(); return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new cusimEvent(); (*e)->ms = 0; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->ms = now_ms(); return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->ms - a->ms); return cudaSuccess; }
+cudaError_t cudaGetLastError() { return cudaSuccess; }
+const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "cusim error"; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
+  memset(p, 0, sizeof(*p));
+  snprintf(p->name, sizeof(p->name), "cusim CPU executor (not a GPU)");
+  p->multiProcessorCount = 4;
+  p->totalGlobalMem = (size_t)16 << 30;
+  p->major = 10;
+  p->minor = 0;
+  return cudaSuccess;
+}
+cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) {
+  *v = (a == cudaDevAttrCooperativeLaunch) ? 1 : (a == cudaDevAttrMultiProcessorCount ? 4 : 0);
+  return cudaSuccess;
+}
+int cusim_occupancy_blocks_per_sm() { return 2; }
+cudaError_t cudaGetDriverEntryPoint(const char*, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* qr) {
+  *fn = nullptr;  // no driver, no TMA unit: the library takes its plain-load instantiation
+  if (qr) *qr = cudaDriverEntryPointSymbolNotFound;
+  return cudaErrorNotSupported;
+}
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+  memset(h, 0, sizeof(*h));
+  memcpy(h->reserved, &p, sizeof(p));
+  return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+  memcpy(p, h.reserved, sizeof(*p));  // same process: the loop-back exchange test
+  return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
