@@ -14,8 +14,8 @@ def pytest_addoption(parser):
                           "sources (kernel logic against the oracle without a GPU). The product never does this itself.")
 
 
-CUSIM_SKIP = ("test_gpu_multi.py", "test_gpu_cpp_shim.py")  # need real devices / link the real library
-CUSIM_SKIP_TESTS = ("test_cpp_end_to_end_example_matches_the_python_runner",)  # a C++ program linked against the real library
+CUSIM_SKIP = ("test_gpu_multi.py",)  # two processes with a device each
+CUSIM_SKIP_TESTS = ()
 
 
 def pytest_configure(config):

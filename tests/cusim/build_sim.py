@@ -16,11 +16,17 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "semantic_suma_b200", "csrc")
-GEN = os.path.join(HERE, "_build", "gen")
-OUT = os.path.join(HERE, "_build", "libsuma_b200_sim.so")
+# CUSIM_ASAN=1: AddressSanitizer build -- every "device" buffer is a heap block, so an out-of-bounds kernel access is
+# reported with its source line (a memcheck of the kernels); run python with LD_PRELOAD=$(gcc -print-file-name=libasan.so)
+ASAN = os.environ.get("CUSIM_ASAN") == "1"
+BUILD = os.path.join(HERE, "_build", "asan" if ASAN else "plain")
+GEN = os.path.join(BUILD, "gen")
+OUT = os.path.join(BUILD, "libsuma_b200_sim.so")
 SOURCES = ["sb_preprocess.cu", "sb_icp.cu", "sb_map.cu", "sb_api.cu"]
 CXXFLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-fno-strict-aliasing",
             "-mtls-dialect=gnu2", "-Wno-unknown-pragmas", "-Wno-attributes", "-D__CUDA_ARCH__=1000", "-DCUSIM=1"]
+if ASAN:
+    CXXFLAGS += ["-fsanitize=address", "-fno-omit-frame-pointer", "-O1"]
 
 
 def _match(text, i, open_ch, close_ch):
@@ -150,7 +156,7 @@ def build(force=False, verbose=False):
     objs, procs = [], []
     for src in SOURCES + ["cusim_rt.cpp"]:
         cpp = os.path.join(HERE, src) if src == "cusim_rt.cpp" else os.path.join(GEN, src.replace(".cu", ".cpp"))
-        obj = os.path.join(HERE, "_build", os.path.splitext(src)[0] + ".o")
+        obj = os.path.join(BUILD, os.path.splitext(src)[0] + ".o")
         cmd = ["g++"] + CXXFLAGS + inc + ["-c", "-o", obj, cpp]
         if verbose:
             print(" ".join(cmd))
@@ -162,7 +168,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("g++ failed on %s:\n%s" % (src, out.decode()[-6000:]))
         if verbose and out.strip():
             print(out.decode()[-3000:])
-    subprocess.check_call(["g++", "-shared", "-pthread", "-o", OUT] + objs)
+    subprocess.check_call(["g++", "-shared", "-pthread"] + (["-fsanitize=address"] if ASAN else []) + ["-o", OUT] + objs)
     return OUT
 
 

@@ -116,6 +116,18 @@ void ptx_unavailable(const char* what) {
   abort();
 }
 
+struct Order { int mode; uint64_t seed; };
+static const Order& order() {
+  static const Order o = [] {
+    Order r{0, 0};
+    const char* e = getenv("CUSIM_ORDER");
+    if (e && !strcmp(e, "reverse")) r.mode = 1;
+    if (e && !strncmp(e, "random", 6)) { r.mode = 2; r.seed = e[6] == ':' ? strtoull(e + 7, nullptr, 10) : 1; }
+    return r;
+  }();
+  return o;
+}
+
 static void deadlock(Block* b) {
   int c[4] = {0, 0, 0, 0};
   for (int i = 0; i < b->nthreads; ++i) c[b->fibers[i].state]++;
@@ -150,15 +162,34 @@ static void run_block(Block* b, dim3 bdim) {
     b->warps[w].gen = 0;
     b->warps[w].n = (w == b->nwarps - 1) ? n - 32 * w : 32;
   }
+  // Execution order of the warps of a block and of the lanes of a warp between two rendezvous points. CUDA promises none,
+  // so a correct kernel gives the same bits under every order: CUSIM_ORDER=reverse / random:<seed> look for code that
+  // only works when a warp happens to run in lockstep or the warps in index order.
+  int worder[kMaxThreads / 32], lorder[32];
+  for (int w = 0; w < b->nwarps; ++w) worder[w] = w;
+  for (int l = 0; l < 32; ++l) lorder[l] = l;
+  const Order& ord = order();
+  if (ord.mode == 1) {
+    for (int w = 0; w < b->nwarps; ++w) worder[w] = b->nwarps - 1 - w;
+    for (int l = 0; l < 32; ++l) lorder[l] = 31 - l;
+  } else if (ord.mode == 2) {
+    uint64_t x = ord.seed * 0x9E3779B97F4A7C15ull + ((uint64_t)blkid->bid.x << 20) + blkid->bid.y + 0x1234567ull;
+    auto rnd = [&x]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    for (int w = b->nwarps - 1; w > 0; --w) { int j = (int)(rnd() % (uint64_t)(w + 1)); int t = worder[w]; worder[w] = worder[j]; worder[j] = t; }
+    for (int l = 31; l > 0; --l) { int j = (int)(rnd() % (uint64_t)(l + 1)); int t = lorder[l]; lorder[l] = lorder[j]; lorder[j] = t; }
+  }
   int live = n;
   while (live > 0) {
     bool progressed = false;
-    for (int w = 0; w < b->nwarps; ++w) {
+    for (int wi = 0; wi < b->nwarps; ++wi) {
+      const int w = worder[wi];
       Warp& W = b->warps[w];
       Fiber* lanes = b->fibers + 32 * w;
       for (;;) {
         bool ran = false;
-        for (int l = 0; l < W.n; ++l) {
+        for (int li = 0; li < 32; ++li) {
+          const int l = lorder[li];
+          if (l >= W.n) continue;
           Fiber* f = lanes + l;
           if (f->state != ST_READY) continue;
           cur = f;

@@ -1,0 +1,63 @@
+"""The library's CUDA sources, executed on the CPU (tests/cusim: one fiber per CUDA thread, one OS thread per block, warp
+collectives and barriers as rendezvous points), against the oracle -- the `-m gpu` parity tests themselves, run in a child
+pytest with the test-side switch --cusim. This is a check of the kernels' LOGIC in a container without a GPU (every branch
+the parity suite reaches, bit for bit); it is not a GPU run and says nothing about speed. The product never loads the
+executor: the swap is done by tests/conftest.py only."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _child(files, k, env=None, timeout=1500):
+    e = dict(os.environ)
+    e.pop("SUMA_B200_TEST_CUSIM", None)
+    e.update(env or {})
+    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "--cusim", "-p", "no:cacheprovider", "-k", k] + files
+    r = subprocess.run(cmd, cwd=ROOT, env=e, capture_output=True, text=True, timeout=timeout)
+    tail = (r.stdout + r.stderr)[-4000:]
+    assert r.returncode == 0, tail
+    m = re.search(r"(\d+) passed", r.stdout)
+    assert m, tail
+    assert " skipped" not in r.stdout.splitlines()[-1], tail  # every selected test really ran on the executor
+    return int(m.group(1))
+
+
+def test_launch_rewrite_is_mechanical():
+    from cusim import build_sim
+    src = "  {\n    ScopedKernel sk(L, K);\n    k_foo<4><<<grid, kThreads, 0, L.stream>>>(kp, s,\n        n_dev);\n  }\n"
+    out, n = build_sim.rewrite_launches(src, "x")
+    assert n == 1
+    assert 'cusim::launch("k_foo<4>", cusim::cfg(grid, kThreads, 0, L.stream), [&] { k_foo<4>(kp, s,\n        n_dev); });' in out
+    out, n = build_sim.rewrite_asm('  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));\n', "x")
+    assert n == 1 and "t = cusim::globaltimer();" in out
+
+
+def test_cuda_sources_on_the_cpu_executor_equal_the_oracle():
+    """preprocessing, Jacobian sums, Gauss-Newton (persistent kernel), map update / rendering, whole processScan runs at
+    64x900 / 64x2048 (geometric and semantic), track-loss fallback, submap paging, the in-kernel peer exchange in loop-back,
+    the 24 parameter variants, the 6 image geometries and the reference-generated digests"""
+    n = _child(["tests/test_gpu_parity.py", "tests/test_zz_gpu_late.py", "tests/test_golden.py"],
+               "not loop_closure and not ouster")
+    assert n >= 30
+
+
+def test_kernel_results_do_not_depend_on_the_execution_order():
+    """CUDA promises no order between the lanes of a warp or the warps of a block outside its synchronisation primitives:
+    the same bits with the lanes / warps run in reverse and in a shuffled order (this is how the unsynchronised pivot search
+    of the warp-parallel LDLT was found)"""
+    k = "pipeline_bit_exact or icp_minimize or map_update or track_loss or fused_peer"
+    for order in ("reverse", "random:3"):
+        assert _child(["tests/test_gpu_parity.py"], k, env={"CUSIM_ORDER": order}) >= 7
+
+
+@pytest.mark.skipif(os.environ.get("SUMA_B200_CUSIM_FULL") != "1", reason="long: SUMA_B200_CUSIM_FULL=1")
+def test_the_whole_gpu_suite_on_the_cpu_executor():
+    """everything `-m gpu` selects that does not need real devices: also 128x4096 / 15 iterations and the two 120-scan
+    loop-closure runs (about four minutes on 8 cores)"""
+    assert _child(["tests/"], "not cusim", timeout=3000) >= 38

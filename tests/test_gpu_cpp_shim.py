@@ -15,11 +15,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _compile(tmp_path):
     exe = os.path.join(str(tmp_path), "shim_example")
-    libdir = os.path.join(ROOT, "semantic_suma_b200", "lib")
+    from semantic_suma_b200 import build as product_build
     api.lib()
+    so = product_build.LIB  # libsuma_b200.so; under pytest --cusim the CPU executor's build of the same sources (conftest)
     subprocess.check_call(["g++", "-std=c++14", "-O1", "-I" + os.path.join(ROOT, "include"), "-o", exe,
-                           os.path.join(ROOT, "tests", "cpp", "shim_example.cpp"), "-L" + libdir, "-lsuma_b200",
-                           "-Wl,-rpath," + libdir])
+                           os.path.join(ROOT, "tests", "cpp", "shim_example.cpp"), so, "-Wl,-rpath," + os.path.dirname(so)])
     return exe
 
 

@@ -236,12 +236,13 @@ def test_cpp_end_to_end_example_matches_the_python_runner(tmp_path):
     from semantic_suma_b200 import api, kitti as K, run_kitti
     from helpers import sized
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    libdir = os.path.join(root, "semantic_suma_b200", "lib")
+    from semantic_suma_b200 import build as product_build
     api.lib()
+    so = product_build.LIB  # libsuma_b200.so; under pytest --cusim the CPU executor's build of the same sources (conftest)
     exe = str(tmp_path / "run_sequence_example")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"),
-                           os.path.join(root, "tests", "cpp", "run_sequence_example.cpp"), "-o", exe, "-L" + libdir,
-                           "-lsuma_b200", "-Wl,-rpath," + libdir])
+                           os.path.join(root, "tests", "cpp", "run_sequence_example.cpp"), "-o", exe, so,
+                           "-Wl,-rpath," + os.path.dirname(so)])
     seq = str(tmp_path / "seq")
     run_kitti.make_synthetic_sequence(seq, 6, width=900, semantic=False)
     out_cpp = str(tmp_path / "cpp.txt")
