@@ -46,7 +46,18 @@ namespace cusim {
 enum { ST_READY = 0, ST_WARP = 1, ST_BLOCK = 2, ST_DONE = 3 };
 constexpr size_t kStack = 128 * 1024;
 constexpr int kMaxThreads = 1024;
-constexpr int kWorkers = 16;
+// the executor's "device": CUSIM_SMS multiprocessors (default 4) with two resident blocks each -- a cooperative grid of up
+// to 2 x SMS blocks, every block on its own OS thread. More SMs = the persistent kernel's grid gets closer to a real GPU's
+// (e.g. its shared-memory pixel cache only engages when the image fits blocks x threads x depth).
+static int sim_sms() {
+  static const int n = [] {
+    const char* e = getenv("CUSIM_SMS");
+    int v = e ? atoi(e) : 4;
+    return v < 1 ? 1 : (v > 148 ? 148 : v);
+  }();
+  return n;
+}
+static int n_workers() { return sim_sms() * 2 > 16 ? sim_sms() * 2 : 16; }
 
 struct Warp {
   uint64_t slot[2][32];
@@ -236,7 +247,10 @@ static void run_block(Block* b, dim3 bdim) {
   cur = nullptr;
 }
 
-// ---- worker pool -------------------------------------------------------------------------------------------------------
+// ---- worker pools ------------------------------------------------------------------------------------------------------
+// One pool per HOST thread that launches kernels: two contexts driven by two host threads ("two GPUs") run their kernels
+// at the same time, which the in-kernel peer exchange of the row-striped Gauss-Newton needs (each rank's kernel waits for
+// the words the other ranks' kernels store). Pools and their threads live until the process ends.
 struct Job {
   LaunchCfg cfg;
   const std::function<void()>* body = nullptr;
@@ -245,26 +259,23 @@ struct Job {
   int active_workers = 0;
   std::atomic<unsigned> next{0};
 };
-// heap objects that are never destroyed: the detached workers wait on them until the process ends (destroying a condition
-// variable with waiters blocks)
-static std::mutex& g_mu = *new std::mutex();
-static std::mutex& g_launch_mu = *new std::mutex();
-static std::condition_variable& g_cv_start = *new std::condition_variable();
-static std::condition_variable& g_cv_done = *new std::condition_variable();
-static Job& g_job = *new Job();
-static uint64_t g_job_gen = 0;
-static int g_running = 0;
-static bool g_started = false;
+struct Pool {
+  std::mutex mu;
+  std::condition_variable cv_start, cv_done;
+  Job job;
+  uint64_t gen = 0;
+  int running = 0;
+};
 
 static int hw_threads() {
   const char* e = getenv("CUSIM_THREADS");
   int n = e ? atoi(e) : (int)std::thread::hardware_concurrency();
   if (n < 1) n = 1;
-  if (n > kWorkers) n = kWorkers;
+  if (n > n_workers()) n = n_workers();
   return n;
 }
 
-static void worker(int id) {
+static void worker(Pool* P, int id) {
   Block* b = new Block();
   b->stacks = (char*)mmap(nullptr, kStack * kMaxThreads, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
   if (b->stacks == (char*)MAP_FAILED) abort();
@@ -274,19 +285,20 @@ static void worker(int id) {
   uint64_t seen = 0;
   for (;;) {
     {
-      std::unique_lock<std::mutex> lk(g_mu);
-      g_cv_start.wait(lk, [&] { return g_job_gen != seen; });
-      seen = g_job_gen;
+      std::unique_lock<std::mutex> lk(P->mu);
+      P->cv_start.wait(lk, [&] { return P->gen != seen; });
+      seen = P->gen;
     }
-    if (id < g_job.active_workers) {
-      const LaunchCfg& c = g_job.cfg;
+    Job& J = P->job;
+    if (id < J.active_workers) {
+      const LaunchCfg& c = J.cfg;
       bi.bdim = c.block;
       bi.gdim = c.grid;
-      b->body = g_job.body;
-      b->kernel = g_job.name;
+      b->body = J.body;
+      b->kernel = J.name;
       for (;;) {
-        unsigned i = g_job.next.fetch_add(1);
-        if (i >= g_job.nblocks) break;
+        unsigned i = J.next.fetch_add(1);
+        if (i >= J.nblocks) break;
         bi.bid.x = i % c.grid.x;
         bi.bid.y = (i / c.grid.x) % c.grid.y;
         bi.bid.z = i / (c.grid.x * c.grid.y);
@@ -294,38 +306,39 @@ static void worker(int id) {
       }
     }
     {
-      std::lock_guard<std::mutex> lk(g_mu);
-      if (--g_running == 0) g_cv_done.notify_all();
+      std::lock_guard<std::mutex> lk(P->mu);
+      if (--P->running == 0) P->cv_done.notify_all();
     }
   }
 }
 
 void launch_impl(const char* name, const LaunchCfg& c, bool cooperative, const std::function<void()>& body) {
-  std::lock_guard<std::mutex> launch_lock(g_launch_mu);
+  static thread_local Pool* P = nullptr;
   const unsigned nblocks = c.grid.x * c.grid.y * c.grid.z;
   if (nblocks == 0) return;
-  if (!g_started) {
-    g_started = true;
-    for (int i = 0; i < kWorkers; ++i) std::thread(worker, i).detach();
+  if (!P) {
+    P = new Pool();  // never destroyed: its detached workers wait on it
+    for (int i = 0; i < n_workers(); ++i) std::thread(worker, P, i).detach();
   }
-  if (cooperative && nblocks > (unsigned)kWorkers) ptx_unavailable("a cooperative grid larger than the worker pool");
+  if (cooperative && nblocks > (unsigned)n_workers()) ptx_unavailable("a cooperative grid larger than the worker pool");
   {
-    std::lock_guard<std::mutex> lk(g_mu);
-    g_job.cfg = c;
-    g_job.body = &body;
-    g_job.name = name;
-    g_job.nblocks = nblocks;
-    g_job.next.store(0);
+    std::lock_guard<std::mutex> lk(P->mu);
+    Job& J = P->job;
+    J.cfg = c;
+    J.body = &body;
+    J.name = name;
+    J.nblocks = nblocks;
+    J.next.store(0);
     // blocks of a cooperative launch wait for each other: every block needs its own OS thread
     int act = cooperative ? (int)nblocks : hw_threads();
     if ((unsigned)act > nblocks) act = (int)nblocks;
-    g_job.active_workers = act;
-    g_running = kWorkers;
-    ++g_job_gen;
+    J.active_workers = act;
+    P->running = n_workers();
+    ++P->gen;
   }
-  g_cv_start.notify_all();
-  std::unique_lock<std::mutex> lk(g_mu);
-  g_cv_done.wait(lk, [] { return g_running == 0; });
+  P->cv_start.notify_all();
+  std::unique_lock<std::mutex> lk(P->mu);
+  P->cv_done.wait(lk, [&] { return P->running == 0; });
 }
 
 }  // namespace cusim
@@ -366,14 +379,14 @@ cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
   memset(p, 0, sizeof(*p));
   snprintf(p->name, sizeof(p->name), "cusim CPU executor (not a GPU)");
-  p->multiProcessorCount = 4;
+  p->multiProcessorCount = cusim::sim_sms();
   p->totalGlobalMem = (size_t)16 << 30;
   p->major = 10;
   p->minor = 0;
   return cudaSuccess;
 }
 cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) {
-  *v = (a == cudaDevAttrCooperativeLaunch) ? 1 : (a == cudaDevAttrMultiProcessorCount ? 4 : 0);
+  *v = (a == cudaDevAttrCooperativeLaunch) ? 1 : (a == cudaDevAttrMultiProcessorCount ? cusim::sim_sms() : 0);
   return cudaSuccess;
 }
 int cusim_occupancy_blocks_per_sm() { return 2; }
