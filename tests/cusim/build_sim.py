@@ -19,7 +19,10 @@ CSRC = os.path.join(ROOT, "semantic_suma_b200", "csrc")
 # CUSIM_ASAN=1: AddressSanitizer build -- every "device" buffer is a heap block, so an out-of-bounds kernel access is
 # reported with its source line (a memcheck of the kernels); run python with LD_PRELOAD=$(gcc -print-file-name=libasan.so)
 ASAN = os.environ.get("CUSIM_ASAN") == "1"
-BUILD = os.path.join(HERE, "_build", "asan" if ASAN else "plain")
+# CUSIM_TSAN=1: ThreadSanitizer build = a racecheck of the kernels (CUDA threads are TSan fibers, see cusim_rt.cpp);
+# run python with LD_PRELOAD=$(gcc -print-file-name=libtsan.so)
+TSAN = os.environ.get("CUSIM_TSAN") == "1"
+BUILD = os.path.join(HERE, "_build", "asan" if ASAN else ("tsan" if TSAN else "plain"))
 GEN = os.path.join(BUILD, "gen")
 OUT = os.path.join(BUILD, "libsuma_b200_sim.so")
 SOURCES = ["sb_preprocess.cu", "sb_icp.cu", "sb_map.cu", "sb_api.cu"]
@@ -27,6 +30,8 @@ CXXFLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-pthread", "-ffp-contract=off",
             "-mtls-dialect=gnu2", "-Wno-unknown-pragmas", "-Wno-attributes", "-D__CUDA_ARCH__=1000", "-DCUSIM=1"]
 if ASAN:
     CXXFLAGS += ["-fsanitize=address", "-fno-omit-frame-pointer", "-O1"]
+if TSAN:
+    CXXFLAGS += ["-fsanitize=thread", "--param", "tsan-distinguish-volatile=1", "-fno-omit-frame-pointer", "-O1", "-DCUSIM_TSAN=1"]
 
 
 def _match(text, i, open_ch, close_ch):
@@ -157,7 +162,10 @@ def build(force=False, verbose=False):
     for src in SOURCES + ["cusim_rt.cpp"]:
         cpp = os.path.join(HERE, src) if src == "cusim_rt.cpp" else os.path.join(GEN, src.replace(".cu", ".cpp"))
         obj = os.path.join(BUILD, os.path.splitext(src)[0] + ".o")
-        cmd = ["g++"] + CXXFLAGS + inc + ["-c", "-o", obj, cpp]
+        flags = list(CXXFLAGS)
+        if TSAN and src == "cusim_rt.cpp":  # the executor's own bookkeeping is not what is being checked
+            flags = [f for f in flags if f != "-fsanitize=thread"]
+        cmd = ["g++"] + flags + inc + ["-c", "-o", obj, cpp]
         if verbose:
             print(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
@@ -168,7 +176,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("g++ failed on %s:\n%s" % (src, out.decode()[-6000:]))
         if verbose and out.strip():
             print(out.decode()[-3000:])
-    subprocess.check_call(["g++", "-shared", "-pthread"] + (["-fsanitize=address"] if ASAN else []) + ["-o", OUT] + objs)
+    subprocess.check_call(["g++", "-shared", "-pthread"] + (["-fsanitize=address"] if ASAN else []) + (["-fsanitize=thread", "-Wl,-Bsymbolic-functions"] if TSAN else []) + ["-o", OUT] + objs)
     return OUT
 
 

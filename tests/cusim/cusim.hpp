@@ -249,6 +249,13 @@ template <class T> static inline T __reduce_add_sync(unsigned m, T v) {
   return r;
 }
 
+// CUDA atomics are relaxed; the kernels pair them with __threadfence() for ordering. ThreadSanitizer (CUSIM_TSAN) does not
+// model stand-alone fences, so there the atomics themselves carry acquire-release (see cusim_rt.cpp on volatile accesses).
+#ifdef CUSIM_TSAN
+#define CUSIM_MO __ATOMIC_SEQ_CST
+#else
+#define CUSIM_MO __ATOMIC_RELAXED
+#endif
 // ---- memory and atomics ----------------------------------------------------------------------------------------------
 template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline T __ldcg(const T* p) {
@@ -259,23 +266,23 @@ template <class T> static inline T __ldcg(const T* p) {
 }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-template <class T> static inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
-static inline unsigned atomicAdd(unsigned* p, int v) { return __atomic_fetch_add(p, (unsigned)v, __ATOMIC_RELAXED); }
-template <class T> static inline T atomicExch(T* p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
-template <class T> static inline T atomicOr(T* p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+template <class T> static inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, CUSIM_MO); }
+static inline unsigned atomicAdd(unsigned* p, int v) { return __atomic_fetch_add(p, (unsigned)v, CUSIM_MO); }
+template <class T> static inline T atomicExch(T* p, T v) { return __atomic_exchange_n(p, v, CUSIM_MO); }
+template <class T> static inline T atomicOr(T* p, T v) { return __atomic_fetch_or(p, v, CUSIM_MO); }
 template <class T> static inline T atomicCAS(T* p, T cmp, T v) {
-  __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
+  __atomic_compare_exchange_n(p, &cmp, v, false, CUSIM_MO, CUSIM_MO);
   return cmp;
 }
 template <class T> static inline T atomicMin(T* p, T v) {
-  T old = __atomic_load_n(p, __ATOMIC_RELAXED);
-  while (v < old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+  T old = __atomic_load_n(p, CUSIM_MO);
+  while (v < old && !__atomic_compare_exchange_n(p, &old, v, true, CUSIM_MO, CUSIM_MO)) {
   }
   return old;
 }
 template <class T> static inline T atomicMax(T* p, T v) {
-  T old = __atomic_load_n(p, __ATOMIC_RELAXED);
-  while (v > old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+  T old = __atomic_load_n(p, CUSIM_MO);
+  while (v > old && !__atomic_compare_exchange_n(p, &old, v, true, CUSIM_MO, CUSIM_MO)) {
   }
   return old;
 }

@@ -11,6 +11,29 @@
 #include <thread>
 #include <vector>
 
+// CUSIM_TSAN (build_sim.py, CUSIM_TSAN=1): ThreadSanitizer as a RACECHECK of the kernels. Every CUDA thread is a TSan fiber;
+// a fiber switch establishes NO happens-before (two CUDA threads are unordered unless the kernel synchronises them), the
+// rendezvous points do (__syncthreads: all threads of the block; warp collectives: the lanes of the warp), as do atomics,
+// __threadfence and the launch boundaries. Volatile accesses -- how the kernels poll words another block publishes -- are
+// recorded as relaxed atomics (build flag tsan-distinguish-volatile + the hooks at the end of this file).
+#ifdef CUSIM_TSAN
+extern "C" {
+void* __tsan_get_current_fiber(void);
+void* __tsan_create_fiber(unsigned flags);
+void __tsan_destroy_fiber(void* fiber);
+void __tsan_switch_to_fiber(void* fiber, unsigned flags);
+void __tsan_acquire(void* addr);
+void __tsan_release(void* addr);
+}
+#define TSAN_SWITCH(f) __tsan_switch_to_fiber((f), 1u /* no_sync */)
+#define TSAN_ACQUIRE(a) __tsan_acquire((void*)(a))
+#define TSAN_RELEASE(a) __tsan_release((void*)(a))
+#else
+#define TSAN_SWITCH(f) ((void)0)
+#define TSAN_ACQUIRE(a) ((void)0)
+#define TSAN_RELEASE(a) ((void)0)
+#endif
+
 extern "C" void cusim_switch(void** save_sp, void* load_sp);
 __asm__(R"(
 .text
@@ -75,6 +98,10 @@ struct Block {
   const std::function<void()>* body = nullptr;
   char* stacks = nullptr;
   const char* kernel = "";
+  void* tsan_fiber[kMaxThreads] = {};  // CUSIM_TSAN: one TSan context per CUDA thread slot of this worker (reused)
+  void* tsan_sched = nullptr;
+  char sync_block = 0, sync_start = 0, sync_end = 0;  // addresses the happens-before edges hang on
+  char sync_warp[kMaxThreads / 32] = {};
 };
 
 thread_local Fiber* cur = nullptr;
@@ -83,28 +110,36 @@ static thread_local Block* tblk = nullptr;
 
 static inline void yield_to_scheduler() {
   Fiber* f = cur;
+  TSAN_SWITCH(f->blk->tsan_sched);
   cusim_switch(&f->sp, f->blk->sched_sp);
 }
 
 static void fiber_main() {
   Fiber* f = cur;
+  TSAN_ACQUIRE(&f->blk->sync_start);  // after the launch (arguments, earlier kernels)
   (*f->blk->body)();
   f = cur;
+  TSAN_RELEASE(&f->blk->sync_end);
   f->state = ST_DONE;
   yield_to_scheduler();
   abort();  // a finished fiber is never resumed
 }
 
 void sync_block() {
+  Block* b = cur->blk;
+  TSAN_RELEASE(&b->sync_block);
   cur->state = ST_BLOCK;
   yield_to_scheduler();
+  TSAN_ACQUIRE(&b->sync_block);
 }
 int sync_block_count(int p) {
   Fiber* f = cur;
   Block* b = f->blk;
   b->pred[f - b->fibers] = p ? 1 : 0;
+  TSAN_RELEASE(&b->sync_block);
   f->state = ST_BLOCK;
   yield_to_scheduler();
+  TSAN_ACQUIRE(&b->sync_block);
   return b->count_result;
 }
 unsigned warp_exchange(uint64_t payload, const uint64_t** slots) {
@@ -112,8 +147,11 @@ unsigned warp_exchange(uint64_t payload, const uint64_t** slots) {
   Warp* w = f->warp;
   const unsigned g = w->gen & 1u;
   w->slot[g][f->lane] = payload;
+  char* ws = &f->blk->sync_warp[w - f->blk->warps];
+  TSAN_RELEASE(ws);
   f->state = ST_WARP;
   yield_to_scheduler();
+  TSAN_ACQUIRE(ws);
   *slots = w->slot[g];
   return w->active[g];
 }
@@ -189,6 +227,12 @@ static void run_block(Block* b, dim3 bdim) {
     for (int w = b->nwarps - 1; w > 0; --w) { int j = (int)(rnd() % (uint64_t)(w + 1)); int t = worder[w]; worder[w] = worder[j]; worder[j] = t; }
     for (int l = 31; l > 0; --l) { int j = (int)(rnd() % (uint64_t)(l + 1)); int t = lorder[l]; lorder[l] = lorder[j]; lorder[j] = t; }
   }
+#ifdef CUSIM_TSAN
+  b->tsan_sched = __tsan_get_current_fiber();
+  for (int i = 0; i < n; ++i)
+    if (!b->tsan_fiber[i]) b->tsan_fiber[i] = __tsan_create_fiber(0);
+#endif
+  TSAN_RELEASE(&b->sync_start);
   int live = n;
   while (live > 0) {
     bool progressed = false;
@@ -204,6 +248,7 @@ static void run_block(Block* b, dim3 bdim) {
           Fiber* f = lanes + l;
           if (f->state != ST_READY) continue;
           cur = f;
+          TSAN_SWITCH(b->tsan_fiber[f - b->fibers]);
           cusim_switch(&b->sched_sp, f->sp);
           ran = true;
           if (f->state == ST_DONE) --live;
@@ -245,6 +290,7 @@ static void run_block(Block* b, dim3 bdim) {
     }
   }
   cur = nullptr;
+  TSAN_ACQUIRE(&b->sync_end);
 }
 
 // ---- worker pools ------------------------------------------------------------------------------------------------------
@@ -405,3 +451,39 @@ cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
   return cudaSuccess;
 }
 cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+
+#ifdef CUSIM_TSAN
+// Volatile accesses of the kernels (polling / publishing words between blocks and ranks). TSan does not model stand-alone
+// fences, and the kernels' hand-overs are "__threadfence(); volatile store" on one side and "volatile load; __threadfence()"
+// on the other: a volatile store counts as a store-release and a volatile load as a load-acquire ON THAT ADDRESS (stronger
+// than the GPU's relaxed access where a kernel deliberately goes without the fence -- the self-validating words -- but no
+// ordering is claimed there, and nothing is ordered between threads that do not hand over through the same word).
+extern "C" {
+unsigned char __tsan_atomic8_load(const volatile unsigned char*, int);
+unsigned short __tsan_atomic16_load(const volatile unsigned short*, int);
+unsigned int __tsan_atomic32_load(const volatile unsigned int*, int);
+unsigned long long __tsan_atomic64_load(const volatile unsigned long long*, int);
+unsigned char __tsan_atomic8_fetch_or(volatile unsigned char*, unsigned char, int);
+unsigned short __tsan_atomic16_fetch_or(volatile unsigned short*, unsigned short, int);
+unsigned int __tsan_atomic32_fetch_or(volatile unsigned int*, unsigned int, int);
+unsigned long long __tsan_atomic64_fetch_or(volatile unsigned long long*, unsigned long long, int);
+#define NOTSAN __attribute__((no_sanitize("thread")))
+enum { kAcquire = 2, kRelease = 3 };  // __ATOMIC_ACQUIRE, __ATOMIC_RELEASE
+NOTSAN void __tsan_volatile_read1(void* a) { __tsan_atomic8_load((const volatile unsigned char*)a, kAcquire); }
+NOTSAN void __tsan_volatile_read2(void* a) { __tsan_atomic16_load((const volatile unsigned short*)a, kAcquire); }
+NOTSAN void __tsan_volatile_read4(void* a) { __tsan_atomic32_load((const volatile unsigned int*)a, kAcquire); }
+NOTSAN void __tsan_volatile_read8(void* a) { __tsan_atomic64_load((const volatile unsigned long long*)a, kAcquire); }
+NOTSAN void __tsan_volatile_read16(void* a) {
+  __tsan_atomic64_load((const volatile unsigned long long*)a, kAcquire);
+  __tsan_atomic64_load((const volatile unsigned long long*)a + 1, kAcquire);
+}
+NOTSAN void __tsan_volatile_write1(void* a) { __tsan_atomic8_fetch_or((volatile unsigned char*)a, 0, kRelease); }
+NOTSAN void __tsan_volatile_write2(void* a) { __tsan_atomic16_fetch_or((volatile unsigned short*)a, 0, kRelease); }
+NOTSAN void __tsan_volatile_write4(void* a) { __tsan_atomic32_fetch_or((volatile unsigned int*)a, 0, kRelease); }
+NOTSAN void __tsan_volatile_write8(void* a) { __tsan_atomic64_fetch_or((volatile unsigned long long*)a, 0, kRelease); }
+NOTSAN void __tsan_volatile_write16(void* a) {
+  __tsan_atomic64_fetch_or((volatile unsigned long long*)a, 0, kRelease);
+  __tsan_atomic64_fetch_or((volatile unsigned long long*)a + 1, 0, kRelease);
+}
+}
+#endif
