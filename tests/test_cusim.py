@@ -63,14 +63,26 @@ def test_persistent_kernel_with_a_gpu_sized_grid():
     assert _child(["tests/test_gpu_parity.py"], k, env={"CUSIM_SMS": "64"}) >= 4
 
 
-@pytest.mark.parametrize("ranks,extra", [(2, []), (4, ["900", "64", "5", "jump"]), (8, [])])
+@pytest.mark.parametrize("ranks,extra", [(2, []), (8, ["900", "64", "5", "jump"])])
 def test_in_kernel_peer_exchange_on_n_ranks(ranks, extra):
     """SURVEY.md 8e on 2 / 4 / 8 "GPUs" of the executor (one host thread and one context per rank, mailboxes exchanged through
-    sb_comm_export / sb_comm_init): every rank holds the bits of the un-striped run after every scan; the 4-rank case drives
+    sb_comm_export / sb_comm_init): every rank holds the bits of the un-striped run after every scan; the 8-rank case drives
     a 1.5 m jump through the striped track-loss recovery. (Real GPUs: tests/test_gpu_multi.py, 2 ranks.)"""
     r = subprocess.run([sys.executable, os.path.join(HERE, "cusim", "multirank_check.py"), str(ranks)] + extra, cwd=ROOT,
                        capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0 and "multirank ok: %d ranks" % ranks in r.stdout, (r.stdout + r.stderr)[-3000:]
+
+
+def test_racecheck_of_the_kernels():
+    """the executor built with ThreadSanitizer (CUDA threads = TSan fibers; only barriers, warp collectives, atomics and
+    volatile hand-overs order anything): first the tool on two toy kernels -- a missing __syncthreads / __syncwarp is reported,
+    a present one is not --, then a semantic run with the in-kernel exchange: only the two known by-design report kinds
+    (tests/cusim/racecheck.py; the 24-test run is in profiles/r02_cusim_runs.txt)"""
+    for args in (["--selftest"], []):
+        r = subprocess.run([sys.executable, os.path.join(HERE, "cusim", "racecheck.py")] + args, cwd=ROOT, capture_output=True,
+                           text=True, timeout=1500)
+        assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    assert "racecheck ok" in r.stdout, r.stdout[-2000:]
 
 
 @pytest.mark.skipif(os.environ.get("SUMA_B200_CUSIM_FULL") != "1", reason="long: SUMA_B200_CUSIM_FULL=1")
