@@ -45,6 +45,7 @@ def main():
             (so["iterations"], so["F"], so["inlier"], so["outlier"], so["invalid"]), "scan %d statistics" % t
         assert gsl.getMap().size() == osl.map.size(), "scan %d surfel count" % t
     surfel_fields_equal(gsl.getMap().getAllSurfels(), osl.map.download(), "surfels")
+    n_surfels = gsl.getMap().size()
     # the calls of bench.py's end-to-end pass: reset, host buffers, the next scan staged ahead (sb_prefetch_scan)
     ref_poses = []
     osl2 = O.Slam(O.default_params(**kw))
@@ -66,7 +67,8 @@ def main():
             gsl.process_scan_raw(ptr(p), ptr(l), ptr(q), p.shape[0], on_device)
             assert_bits_equal(gsl.getCurrentPose(), ref_poses[t], "after reset, scan %d (on_device=%r)" % (t, on_device))
     print("bench sequence ok: %s, %d scans, %d surfels at the end, every pose / statistic / surfel record bit-identical "
-          "(executor %.1f s, oracle %.1f s)" % (wl, n, gsl.getMap().size(), t_sim, t_orc))
+          "(executor %.1f s, oracle %.1f s); reset + host buffers + input staging: the first %d scans again, identical"
+          % (wl, n, n_surfels, t_sim, t_orc, m))
     gsl.ctx.close()
 
 
