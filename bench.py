@@ -330,15 +330,17 @@ def run_native(args, w, rank, world, local_rank):
         top = max(prof.items(), key=lambda kv: kv[1][0])[0]
         us = 1e3 * prof[top][0] / prof[top][1]
         ach = algorithmic_bytes(top, P, S_avg, N_avg, sem) / (us * 1e-6) / 1e9
-        traffic, traffic_src = None, None
+        traffic, traffic_src, traffic_S = None, None, None
         try:  # DRAM bytes of this kernel from the committed ncu --set full capture (profiles/ncu_traffic.py)
             tj = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
             traffic = tj["kernels"][top]["dram_bytes_per_launch"]
             traffic_src = tj.get("source")
+            traffic_S = tj.get("surfels_at_capture")
         except Exception:  # noqa: BLE001
             pass
         roofline = {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(ach / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                    "traffic_at_surfels": traffic_S,  # the ncu capture's map size (S of this run: surfels_avg below)
                     "algorithmic_bytes_per_launch": int(algorithmic_bytes(top, P, S_avg, N_avg, sem)),
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                     "avg_launch_us": round(us, 2), "surfels_avg": int(S_avg),
