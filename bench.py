@@ -293,58 +293,61 @@ def run_native(args, w, rank, world, local_rank):
     roofline = None
     kernel_table = {}
     if rank == 0 and not args.no_profile:
-        preroll(dev, True)
-        ctx.profile(True)
-        s_sum = 0
-        per_step_prof = []
-        for i in range(args.steps):
-            with torch.cuda.stream(stream):
-                flush.zero_()
-            s_sum += slam.getMap().size()
-            feed(dev, pre + i, True)
-            per_step_prof.append(ctx.profile_collect())
-        ctx.profile(False)
-        # per kernel class: median over the steps of the step's mean launch time (one disturbed launch -- another
-        # process initialising on the box, a clock sample -- must not move a 15 us kernel's figure), times its launches
-        prof = {}
-        for k in {k for st in per_step_prof for k in st}:
-            per = [st[k][0] / st[k][1] for st in per_step_prof if k in st and st[k][1] > 0]
-            cnt = sum(st[k][1] for st in per_step_prof if k in st)
-            if per and cnt:
-                prof[k] = (statistics.median(per) * cnt, cnt)
-        tot = sum(v[0] for v in prof.values())
-        P = w["width"] * w["height"]
-        S_avg = s_sum / max(1, args.steps)
-        N_avg = float(np.mean([p.shape[0] for p, _, _ in scans[pre:]]))
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:  # noqa: BLE001
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        for k, (ms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-            b = algorithmic_bytes(k, P, S_avg, N_avg, sem)
-            us = 1e3 * ms / cnt
-            kernel_table[k] = {"launches_per_step": round(cnt / args.steps, 2), "avg_us": round(us, 2),
-                               "share": round(ms / tot, 4), "gbps": round(b / (us * 1e-6) / 1e9, 1) if us > 0 else None}
-        top = max(prof.items(), key=lambda kv: kv[1][0])[0]
-        us = 1e3 * prof[top][0] / prof[top][1]
-        ach = algorithmic_bytes(top, P, S_avg, N_avg, sem) / (us * 1e-6) / 1e9
-        traffic, traffic_src, traffic_S = None, None, None
-        try:  # DRAM bytes of this kernel from the committed ncu --set full capture (profiles/ncu_traffic.py)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
-            traffic = tj["kernels"][top]["dram_bytes_per_launch"]
-            traffic_src = tj.get("source")
-            traffic_S = tj.get("surfels_at_capture")
-        except Exception:  # noqa: BLE001
-            pass
-        roofline = {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(ach / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
-                    "traffic_at_surfels": traffic_S,  # the ncu capture's map size (S of this run: surfels_avg below)
-                    "algorithmic_bytes_per_launch": int(algorithmic_bytes(top, P, S_avg, N_avg, sem)),
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                    "avg_launch_us": round(us, 2), "surfels_avg": int(S_avg),
-                    "step_share": kernel_table[top]["share"]}
+        try:  # the per-kernel table explains the headline; a failure in it must not cost the line
+            preroll(dev, True)
+            ctx.profile(True)
+            s_sum = 0
+            per_step_prof = []
+            for i in range(args.steps):
+                with torch.cuda.stream(stream):
+                    flush.zero_()
+                s_sum += slam.getMap().size()
+                feed(dev, pre + i, True)
+                per_step_prof.append(ctx.profile_collect())
+            ctx.profile(False)
+            # per kernel class: median over the steps of the step's mean launch time (one disturbed launch -- another
+            # process initialising on the box, a clock sample -- must not move a 15 us kernel's figure), times its launches
+            prof = {}
+            for k in {k for st in per_step_prof for k in st}:
+                per = [st[k][0] / st[k][1] for st in per_step_prof if k in st and st[k][1] > 0]
+                cnt = sum(st[k][1] for st in per_step_prof if k in st)
+                if per and cnt:
+                    prof[k] = (statistics.median(per) * cnt, cnt)
+            tot = sum(v[0] for v in prof.values())
+            P = w["width"] * w["height"]
+            S_avg = s_sum / max(1, args.steps)
+            N_avg = float(np.mean([p.shape[0] for p, _, _ in scans[pre:]]))
+            peaks = {}
+            try:
+                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except Exception:  # noqa: BLE001
+                pass
+            peak = float(peaks.get("hbm_gbs", 6650.0))
+            for k, (ms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+                b = algorithmic_bytes(k, P, S_avg, N_avg, sem)
+                us = 1e3 * ms / cnt
+                kernel_table[k] = {"launches_per_step": round(cnt / args.steps, 2), "avg_us": round(us, 2),
+                                   "share": round(ms / tot, 4), "gbps": round(b / (us * 1e-6) / 1e9, 1) if us > 0 else None}
+            top = max(prof.items(), key=lambda kv: kv[1][0])[0]
+            us = 1e3 * prof[top][0] / prof[top][1]
+            ach = algorithmic_bytes(top, P, S_avg, N_avg, sem) / (us * 1e-6) / 1e9
+            traffic, traffic_src, traffic_S = None, None, None
+            try:  # DRAM bytes of this kernel from the committed ncu --set full capture (profiles/ncu_traffic.py)
+                tj = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+                traffic = tj["kernels"][top]["dram_bytes_per_launch"]
+                traffic_src = tj.get("source")
+                traffic_S = tj.get("surfels_at_capture")
+            except Exception:  # noqa: BLE001
+                pass
+            roofline = {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                        "frac": round(ach / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                        "traffic_at_surfels": traffic_S,  # the ncu capture's map size (S of this run: surfels_avg below)
+                        "algorithmic_bytes_per_launch": int(algorithmic_bytes(top, P, S_avg, N_avg, sem)),
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                        "avg_launch_us": round(us, 2), "surfels_avg": int(S_avg),
+                        "step_share": kernel_table[top]["share"]}
+        except Exception as e:  # noqa: BLE001
+            roofline = {"error": "per-kernel pass failed: %s: %s" % (type(e).__name__, str(e)[:200])}
     if dist is not None:
         dist.barrier()  # the other ranks stay quiet while rank 0 takes the per-kernel times
     slam.ctx.close()
@@ -354,7 +357,12 @@ def run_native(args, w, rank, world, local_rank):
     out = None
     if rank == 0:
         # the CPU baseline is timed at N = 1 only (rank 0); the N > 1 lines carry null
-        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(w, scans, budget_s=args.cpu_budget)
+        cpu = None
+        if not (args.no_cpu_baseline or world > 1):
+            try:
+                cpu = cpu_baseline(w, scans, budget_s=args.cpu_budget)
+            except Exception as e:  # noqa: BLE001 -- the GPU figures above are complete; report why the CPU arm is missing
+                cpu = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
         value = world * args.steps / (ms_dev * 1e-3)
         e2e_value = world * args.steps / (ms_e2e * 1e-3)
         out = {
