@@ -85,6 +85,15 @@ def test_racecheck_of_the_kernels():
     assert "racecheck ok" in r.stdout, r.stdout[-2000:]
 
 
+def test_bench_native_arm_dry_run():
+    """bench.py's own Python path at N = 1 (pre-roll, device-resident pass, end-to-end pass with input staging, per-kernel pass,
+    CPU baseline, the JSON line with every key of the contract) with the CUDA sources on the executor and torch's CUDA calls
+    stubbed: the line is complete. Its numbers mean nothing."""
+    r = subprocess.run([sys.executable, os.path.join(HERE, "cusim", "bench_dryrun.py"), "--steps", "3", "--warmup", "3", "--preroll", "2",
+                        "--cpu-budget", "1"], cwd=ROOT, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0 and "bench dry run ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
+
+
 @pytest.mark.skipif(os.environ.get("SUMA_B200_CUSIM_FULL") != "1", reason="long: SUMA_B200_CUSIM_FULL=1")
 def test_the_whole_gpu_suite_on_the_cpu_executor():
     """everything `-m gpu` selects that does not need real devices: also 128x4096 / 15 iterations and the two 120-scan
