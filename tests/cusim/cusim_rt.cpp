@@ -421,7 +421,11 @@ cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms 
 cudaError_t cudaGetLastError() { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "cusim error"; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int* n) {  // CUSIM_DEVICES "GPUs" (default 1); every host thread that launches is its own
+  const char* e = getenv("CUSIM_DEVICES");
+  *n = e && atoi(e) > 0 ? atoi(e) : 1;
+  return cudaSuccess;
+}
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
   memset(p, 0, sizeof(*p));
   snprintf(p->name, sizeof(p->name), "cusim CPU executor (not a GPU)");
