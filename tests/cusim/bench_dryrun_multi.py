@@ -15,7 +15,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 N = int(sys.argv[1])
-ARGS = sys.argv[2:] or ["--steps", "3", "--warmup", "3", "--preroll", "2"]
+ARGS = sys.argv[2:] or ["--steps", "3", "--warmup", "3", "--preroll", "2", "--striped-deadline", "3000"]  # one process: a guard that fires would end every rank
 sys.argv = sys.argv[:1]
 os.environ["CUSIM_DEVICES"] = str(N)
 import bench_dryrun  # noqa: E402,F401  (installs the executor build and the torch.cuda stubs)

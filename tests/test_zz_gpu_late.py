@@ -1,9 +1,10 @@
-"""GPU tests written AFTER the round's GPU minutes were spent: they have not run on a GPU yet. The file name sorts last on
+"""GPU tests written AFTER the round's GPU minutes were spent: no B200 has run them yet. The file name sorts last on
 purpose, so that `pytest -x` reaches them only after the suite that was verified on B200s (tests/test_gpu_*.py,
 tests/test_golden.py). Everything they compare against is CPU-verified: the digests were computed by the reference itself
 (tests/golden/make_reference_golden.py), the loop-closure integration by the oracle twin, which tests/test_ref_full.py
-holds to the reference's own SurfelMapping::integrateLoopClosures bit for bit. The test LOGIC itself (keys, call order, counts,
-digests) was dry-run on the CPU with oracle-backed stand-ins for the api classes (scratch/dry_run_late_gpu_tests.py)."""
+holds to the reference's own SurfelMapping::integrateLoopClosures bit for bit. What they exercise of the CUDA path has run,
+and passes, on the CPU executor for the library's CUDA sources (`pytest -m gpu --cusim`, tests/cusim; log in
+profiles/r02_cusim_runs.txt) -- kernel logic, not a GPU run."""
 import json
 import os
 
