@@ -1062,10 +1062,17 @@ __global__ void __launch_bounds__(kThreads) k_gen_compact(KParams kp, FrameDev f
   if (t < kp.W * kp.H) {
     int x = t / kp.H, y = t - x * kp.H;
     size_t pix = (size_t)y * kp.W + x;
-    float4 V = __ldg(f.vertex + pix), N = __ldg(f.normal + pix), R = __ldg(radius_map + pix);
+    // the flag first: in the steady state most measurements were integrated into an existing surfel, and for those pixels
+    // the three images below are never needed (1 byte instead of 49 per pixel)
+    const bool integ = integrated[pix] != 0;
+    float4 V = make_float4(0.f, 0.f, 0.f, 0.f), N = V, R = V;
+    if (!integ) {
+      V = __ldg(f.vertex + pix);
+      N = __ldg(f.normal + pix);
+      R = __ldg(radius_map + pix);
+    }
     bool invalid = (V.w < 1.0f) || (N.w < 1.0f);
     invalid = invalid || (R.w < 0.5f);
-    bool integ = integrated[pix] != 0;
     V3 v = mk3(V.x, V.y, V.z), n = mk3(N.x, N.y, N.z);
     V3 view_dir = divs3(neg3(v), len3(v));
     bool valid = !invalid && !integ && (dot3(n, view_dir) > 0.01f);
