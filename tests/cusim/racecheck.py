@@ -63,6 +63,9 @@ def selftest():
         for which in (0, 1, 2):
             r = subprocess.run([exe, str(which)], capture_output=True, text=True, timeout=300,
                                env=dict(os.environ, TSAN_OPTIONS="exitcode=0:halt_on_error=0:report_signal_unsafe=0:history_size=7"))
+            if "FATAL: ThreadSanitizer" in r.stderr:  # e.g. an address-space layout this libtsan cannot map
+                print("ThreadSanitizer does not start here: " + r.stderr.strip().splitlines()[0])
+                sys.exit(77)
             assert "selftest ran" in r.stdout, r.stdout + r.stderr
             res[which] |= set(re.findall(r"SUMMARY: ThreadSanitizer: data race \S+ in (\w+)", r.stderr))
         if res[1] == {"k_block"} and res[2] == {"k_warp"}:
@@ -86,6 +89,9 @@ def main():
                    % (d, os.path.join(HERE, "tsan.supp")))
         r = subprocess.run([sys.executable, os.path.abspath(__file__), str(n_scans), str(width)], env=env, capture_output=True,
                            text=True, timeout=1500)
+        if "FATAL: ThreadSanitizer" in r.stderr:
+            print("ThreadSanitizer does not start here: " + r.stderr.strip().splitlines()[0])
+            sys.exit(77)
         assert r.returncode == 0 and "racecheck run:" in r.stdout, (r.stdout + r.stderr)[-3000:]
         sites = {}
         for f in glob.glob(os.path.join(d, "tsan.*")):

@@ -81,6 +81,8 @@ def test_racecheck_of_the_kernels():
     for args in (["--selftest"], []):
         r = subprocess.run([sys.executable, os.path.join(HERE, "cusim", "racecheck.py")] + args, cwd=ROOT, capture_output=True,
                            text=True, timeout=1500)
+        if r.returncode == 77:
+            pytest.skip(r.stdout.strip()[-200:])
         assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     assert "racecheck ok" in r.stdout, r.stdout[-2000:]
 
