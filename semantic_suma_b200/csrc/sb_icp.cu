@@ -496,7 +496,7 @@ __device__ void gn_step_warp(GnShared& sh, long long raw, int lane, double last_
         piv = i;
       }
     }
-    __syncwarp();  // every lane has read the diagonal before lanes k / piv swap it below (found by tests/cusim)
+    __syncwarp();  // every lane has read the diagonal before lanes k / piv swap it below (without it: correct in lockstep only)
     if (piv != k) {  // warp-uniform
       if (lane < 6) {
         double t = A[k * 6 + lane];

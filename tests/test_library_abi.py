@@ -74,6 +74,7 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in txt.replace("CPU oracle", "").replace("the oracle", "").lower() or f == "build.py", f
+                assert "cusim" not in txt.lower(), f  # nor the CPU executor of tests/cusim: only tests/conftest.py swaps it in
 
 
 def test_cpp_mirror_has_the_reference_class_surface():
