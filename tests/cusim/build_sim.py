@@ -22,7 +22,9 @@ ASAN = os.environ.get("CUSIM_ASAN") == "1"
 # CUSIM_TSAN=1: ThreadSanitizer build = a racecheck of the kernels (CUDA threads are TSan fibers, see cusim_rt.cpp);
 # run python with LD_PRELOAD=$(gcc -print-file-name=libtsan.so)
 TSAN = os.environ.get("CUSIM_TSAN") == "1"
-BUILD = os.path.join(HERE, "_build", "asan" if ASAN else ("tsan" if TSAN else "plain"))
+# CUSIM_COV=1: gcov instrumentation -- which lines of csrc/*.cu the tests reach (scratch/cusim_coverage.sh)
+COV = os.environ.get("CUSIM_COV") == "1"
+BUILD = os.path.join(HERE, "_build", "asan" if ASAN else ("tsan" if TSAN else ("cov" if COV else "plain")))
 GEN = os.path.join(BUILD, "gen")
 OUT = os.path.join(BUILD, "libsuma_b200_sim.so")
 SOURCES = ["sb_preprocess.cu", "sb_icp.cu", "sb_map.cu", "sb_api.cu"]
@@ -30,6 +32,8 @@ CXXFLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-pthread", "-ffp-contract=off",
             "-mtls-dialect=gnu2", "-Wno-unknown-pragmas", "-Wno-attributes", "-D__CUDA_ARCH__=1000", "-DCUSIM=1"]
 if ASAN:
     CXXFLAGS += ["-fsanitize=address", "-fno-omit-frame-pointer", "-O1"]
+if COV:
+    CXXFLAGS += ["--coverage", "-O1"]
 if TSAN:
     CXXFLAGS += ["-fsanitize=thread", "--param", "tsan-distinguish-volatile=1", "-fno-omit-frame-pointer", "-O1", "-DCUSIM_TSAN=1"]
 
@@ -176,7 +180,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("g++ failed on %s:\n%s" % (src, out.decode()[-6000:]))
         if verbose and out.strip():
             print(out.decode()[-3000:])
-    subprocess.check_call(["g++", "-shared", "-pthread"] + (["-fsanitize=address"] if ASAN else []) + (["-fsanitize=thread", "-Wl,-Bsymbolic-functions"] if TSAN else []) + ["-o", OUT] + objs)
+    subprocess.check_call(["g++", "-shared", "-pthread"] + (["-fsanitize=address"] if ASAN else []) + (["-fsanitize=thread", "-Wl,-Bsymbolic-functions"] if TSAN else []) + (["--coverage"] if COV else []) + ["-o", OUT] + objs)
     return OUT
 
 

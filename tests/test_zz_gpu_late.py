@@ -144,3 +144,58 @@ def test_image_geometries_bit_exact():
                             fov_down=kw.get("data_fov_down", -25.0), semantic=True)
         poses = synth.trajectory(3)
         _pipeline_equal(po, pp, [scene.scan(t, poses[t]) for t in range(3)], repr(kw))
+
+
+@pytest.mark.parametrize("t_now,compose,seed", [(150, 1, 1), (40, 1, 2), (150, 0, 3), (150, 1, 4)])
+def test_adversarial_random_clouds_bit_exact(t_now, compose, seed):
+    """the adversarial inputs tests/test_ref_full.py feeds the reference's own SurfelMap class with (random surfels of any
+    orientation, huge and tiny discs across the azimuth seam -- the warp-cooperative large-quad rasteriser --, negative
+    confidences, old and new creation times, movable labels; points outside the field of view, duplicates, zeros), through the
+    CUDA operators: preprocessing, render / render_active / render_inactive / render_composed, map update -- against the oracle"""
+    from oracle import oracle as O
+    from semantic_suma_b200 import api
+    from test_ref_shaders import _random_cloud, _random_surfels
+    rng = np.random.default_rng(1000 * seed + t_now + compose)
+    kw = dict(sized(360, 32), compose_rendering=compose)
+    po, pp = both_params(**kw)
+    pts, lab, prob = _random_cloud(rng, 30000, po)
+    lab[:] = rng.choice(np.array((0, 10, 30, 40, 50), np.float32), lab.shape[0])
+    ctx = api.Context(pp)
+    om, gm = O.Map(po), api.SurfelMap(ctx)
+    S = _random_surfels(rng, 20000, t_now)
+    pose = np.eye(4)
+    pose[:3, 3] = (0.3, -0.2, 0.1)
+    a = np.deg2rad(3.0)
+    pose[:2, :2] = [[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]
+    om.upload(S, t_now)
+    gm.upload(S, t_now)
+    for t in range(0, t_now + 1, 7):
+        T = np.eye(4); T[:3, 3] = (0.01 * t, 0.002 * t, 0.0)
+        om.set_pose(t, T)
+        gm.set_pose(t, T)
+    try:
+        data = O.preprocess(po, pts, lab, prob, timestamp=t_now)
+        f = api.Frame(ctx, 360, 32)
+        api.Preprocessing(ctx).process(pts, f, lab, prob, t_now)
+        for g, o, name in zip(f.maps(), data, "vns"):
+            assert_bits_equal(g, o, "preprocess " + name)
+        out = api.Frame(ctx, 360, 32)
+        gm.render(np.eye(4), pose, out, 0.5)
+        for g, o, name in zip(out.maps(), om.render(np.eye(4), pose, 0.5), "vns"):
+            assert_bits_equal(g, o, "render " + name)
+        frames = (gm.oldMapFrame, gm.newMapFrame, gm.composedFrame)
+        for w in range(3 if compose else 2):
+            for g, o, name in zip(frames[w]().maps(), om.frame(w), "vns"):
+                assert_bits_equal(g, o, "frame %d %s" % (w, name))
+        om.render_active(pose, 0.2); gm.render_active(pose, 0.2)
+        om.render_inactive(pose, 0.2); gm.render_inactive(pose, 0.2)
+        om.render_composed(np.eye(4), pose, 0.2); gm.render_composed(np.eye(4), pose, 0.2)
+        for w in range(3):
+            for g, o, name in zip(frames[w]().maps()[:2], om.frame(w)[:2], "vn"):
+                assert_bits_equal(g, o, "single-view frame %d %s" % (w, name))
+        om.update(pose, data)
+        gm.update(pose, f)
+        assert gm.size() == om.size() > 0
+        surfel_fields_equal(gm.getAllSurfels(), om.download(), "surfels after the update")
+    finally:
+        ctx.close()
