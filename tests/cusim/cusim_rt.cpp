@@ -155,10 +155,18 @@ unsigned warp_exchange(uint64_t payload, const uint64_t** slots) {
   *slots = w->slot[g];
   return w->active[g];
 }
+// %globaltimer. The kernels only use it to bound their spins (10 s). The lanes of a warp are fibers that run one after the
+// other between rendezvous points, so 32 lanes that all time out wait 32 x 10 s here where a GPU waits 10 s:
+// CUSIM_CLOCK_SCALE=<n> lets the executor's clock run n times faster (tests of the time-out paths).
 unsigned long long globaltimer() {
+  static const unsigned long long scale = [] {
+    const char* e = getenv("CUSIM_CLOCK_SCALE");
+    long v = e ? atol(e) : 1;
+    return (unsigned long long)(v < 1 ? 1 : v);
+  }();
   timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
-  return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+  return ((unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec) * scale;
 }
 void ptx_unavailable(const char* what) {
   fprintf(stderr, "cusim: %s is not available in the CPU executor\n", what);
@@ -367,6 +375,8 @@ void launch_impl(const char* name, const LaunchCfg& c, bool cooperative, const s
     for (int i = 0; i < n_workers(); ++i) std::thread(worker, P, i).detach();
   }
   if (cooperative && nblocks > (unsigned)n_workers()) ptx_unavailable("a cooperative grid larger than the worker pool");
+  static const bool trace = getenv("CUSIM_TRACE") != nullptr;  // kernel names as they start and end (finding a hang)
+  if (trace) fprintf(stderr, "cusim: launch %s grid %u block %u\n", name, nblocks, c.block.x * c.block.y * c.block.z);
   {
     std::lock_guard<std::mutex> lk(P->mu);
     Job& J = P->job;
@@ -385,6 +395,7 @@ void launch_impl(const char* name, const LaunchCfg& c, bool cooperative, const s
   P->cv_start.notify_all();
   std::unique_lock<std::mutex> lk(P->mu);
   P->cv_done.wait(lk, [&] { return P->running == 0; });
+  if (trace) fprintf(stderr, "cusim: done   %s\n", name);
 }
 
 }  // namespace cusim

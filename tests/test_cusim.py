@@ -87,6 +87,14 @@ def test_racecheck_of_the_kernels():
     assert "racecheck ok" in r.stdout, r.stdout[-2000:]
 
 
+def test_a_missing_peer_ends_in_an_error_not_a_hang():
+    """two ranks set up for the in-kernel exchange, only one runs: its persistent kernel gives up after the bounded spin, the
+    scan returns SB_ERR_STATE, the contexts close (tests/cusim/peer_timeout_check.py)"""
+    r = subprocess.run([sys.executable, os.path.join(HERE, "cusim", "peer_timeout_check.py")], cwd=ROOT, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "peer timeout ok" in r.stdout and "contexts closed" in r.stdout, (r.stdout + r.stderr)[-3000:]
+
+
 def test_bench_native_arm_dry_run():
     """bench.py's own Python path at N = 1 (pre-roll, device-resident pass, end-to-end pass with input staging, per-kernel pass,
     CPU baseline, the JSON line with every key of the contract) with the CUDA sources on the executor and torch's CUDA calls
