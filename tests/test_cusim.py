@@ -10,6 +10,9 @@ import sys
 
 import pytest
 
+FULL = os.environ.get("SUMA_B200_CUSIM_FULL") == "1"
+long_run = pytest.mark.skipif(not FULL, reason="kept out of the default CPU tier for its run time: SUMA_B200_CUSIM_FULL=1 "
+                                                "(log of a full run: profiles/r02_cusim_runs.txt)")
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
@@ -47,6 +50,7 @@ def test_cuda_sources_on_the_cpu_executor_equal_the_oracle():
     assert n >= 30
 
 
+@long_run
 def test_kernel_results_do_not_depend_on_the_execution_order():
     """CUDA promises no order between the lanes of a warp or the warps of a block outside its synchronisation primitives:
     the same bits with the lanes / warps run in reverse and in a shuffled order (this is how the unsynchronised pivot search
@@ -56,6 +60,7 @@ def test_kernel_results_do_not_depend_on_the_execution_order():
     assert _child(["tests/test_gpu_parity.py"], k, env={"CUSIM_ORDER": order}) >= 6
 
 
+@long_run
 def test_persistent_kernel_with_a_gpu_sized_grid():
     """the executor's default device has 4 SMs (8 cooperative blocks); with 64 SMs the persistent Gauss-Newton kernel runs 128
     co-resident blocks and its shared-memory pixel cache engages at 64x900, as on a B200"""
@@ -63,10 +68,11 @@ def test_persistent_kernel_with_a_gpu_sized_grid():
     assert _child(["tests/test_gpu_parity.py"], k, env={"CUSIM_SMS": "64"}) >= 4
 
 
-@pytest.mark.parametrize("ranks,extra", [(2, []), (8, ["900", "64", "5", "jump"])])
+@pytest.mark.parametrize("ranks,extra", [(2, []), pytest.param(4, ["900", "64", "5", "jump"]),
+                                         pytest.param(8, ["900", "64", "5", "jump"], marks=long_run)])
 def test_in_kernel_peer_exchange_on_n_ranks(ranks, extra):
     """SURVEY.md 8e on 2 / 4 / 8 "GPUs" of the executor (one host thread and one context per rank, mailboxes exchanged through
-    sb_comm_export / sb_comm_init): every rank holds the bits of the un-striped run after every scan; the 8-rank case drives
+    sb_comm_export / sb_comm_init): every rank holds the bits of the un-striped run after every scan; the 4- and 8-rank cases drive
     a 1.5 m jump through the striped track-loss recovery. (Real GPUs: tests/test_gpu_multi.py, 2 ranks.)"""
     r = subprocess.run([sys.executable, os.path.join(HERE, "cusim", "multirank_check.py"), str(ranks)] + extra, cwd=ROOT,
                        capture_output=True, text=True, timeout=1200)
@@ -104,7 +110,7 @@ def test_bench_native_arm_dry_run():
     assert r.returncode == 0 and "bench dry run ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
 
 
-@pytest.mark.skipif(os.environ.get("SUMA_B200_CUSIM_FULL") != "1", reason="long: SUMA_B200_CUSIM_FULL=1")
+@long_run
 def test_the_whole_gpu_suite_on_the_cpu_executor():
     """everything `-m gpu` selects that does not need real devices: also 128x4096 / 15 iterations and the two 120-scan
     loop-closure runs (about four minutes on 8 cores)"""
