@@ -3,7 +3,11 @@
      seeds and over image sizes incl. odd ones (361x33, 128x16, 513x48, 900x64, 2048x64);
  (b) random COMBINATIONS of the parameter variants (tests/test_ref_full.py::VARIANTS, 2-5 at a time), geometric / semantic,
      three widths, three speeds, with and without a jump that triggers the track-loss fallback: five scans of the whole
-     pipeline each.
+     pipeline each;
+ (c) the Jacobian operator (raw 32 int64 sums) on pairs of random clouds: 2 sampling modes x 4 robust weightings x geometric /
+     semantic x three image sizes, three poses each;
+ (d) whole Gauss-Newton minimisations (persistent kernel): real scene pairs and random clouds (degenerate systems, early
+     stops), 3 weightings x 2 sampling modes x max iterations 1 / 7 / 30 x stop thresholds 0 / 1e-4 x three image sizes.
 usage: python tests/cusim/fuzz.py [n_cloud_seeds=40] [n_param_combos=40]"""
 import os
 import random
@@ -70,14 +74,78 @@ def params(n_combos):
     return n_combos, bad
 
 
+def operators():
+    import itertools
+
+    import numpy as np
+    from helpers import assert_bits_equal
+    from oracle import oracle as O
+    from test_gpu_parity import _prep_both
+    from test_ref_shaders import _random_cloud
+    rng = np.random.default_rng(11)
+    n_j = bad_j = n_g = bad_g = 0
+    for (W, H) in ((360, 32), (361, 33), (900, 64)):
+        for bil, wt, sem in itertools.product((0, 1), (0, 1, 2, 3), (False, True)):
+            po, pp = both_params(**sized(W, H, bilinear_sampling=bil, weighting=wt))
+            ctx = api.Context(pp)
+            for rep in range(3):
+                o0, f0 = _prep_both(po, ctx, _random_cloud(rng, 25000, po, labels=sem), 100)
+                o1, f1 = _prep_both(po, ctx, _random_cloud(rng, 25000, po, labels=sem), 100)
+                obj = api.Frame2Model(ctx)
+                obj.setData(f1, f0)
+                T0 = np.eye(4); T0[:3, 3] = rng.normal(0, 0.3, 3)
+                a = rng.normal(0, 0.05)
+                T0[:2, :2] = [[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]
+                for it, pose in enumerate([np.eye(4), T0, T0]):
+                    n_j += 1
+                    obj.initialize(pose); obj.iteration_ = it; obj.jacobianProducts()
+                    _, raw = O.icp_jacobian(po, o1, o0, pose, iteration=it)
+                    if not np.array_equal(obj.raw32, raw):
+                        bad_j += 1
+                        print("FAIL jacobian %dx%d bilinear %d weighting %d semantic %r" % (H, W, bil, wt, sem))
+            ctx.close()
+    for (W, H) in ((360, 32), (450, 64), (361, 33)):
+        for wt, bil, mi, eps in itertools.product((0, 1, 2), (0, 1), (1, 7, 30), (0.0, 1e-4)):
+            po, pp = both_params(**sized(W, H, bilinear_sampling=bil, weighting=wt, max_iterations=mi, stopping_threshold=eps,
+                                         delta=eps))
+            ctx = api.Context(pp)
+            for rep in range(2):
+                if rep == 0:
+                    scene = synth.Scene(width=W, height=H, seed=int(rng.integers(1, 1000)))
+                    poses = synth.trajectory(2, step=float(rng.uniform(0.05, 0.8)), yaw_deg=float(rng.uniform(0, 3)))
+                    c0, c1 = scene.scan(0, poses[0]), scene.scan(1, poses[1])
+                else:
+                    c0, c1 = _random_cloud(rng, 20000, po, labels=False), _random_cloud(rng, 20000, po, labels=False)
+                o0, f0 = _prep_both(po, ctx, c0, 100)
+                o1, f1 = _prep_both(po, ctx, c1, 100)
+                obj = api.Frame2Model(ctx)
+                obj.setData(f1, f0)
+                gn = api.LieGaussNewton(ctx)
+                T0 = np.eye(4); T0[:3, 3] = rng.normal(0, 0.05, 3)
+                gn.minimize(obj, T0)
+                pose_o, o48, k, hist = O.icp_minimize(po, o1, o0, T0)
+                n_g += 1
+                try:
+                    assert gn.iterationCount() == k and len(gn.history()) == len(hist)
+                    assert_bits_equal(gn.pose(), pose_o, "pose")
+                    assert_bits_equal(gn.out48, o48, "out48")
+                except AssertionError as e:
+                    bad_g += 1
+                    print("FAIL minimise %dx%d weighting %d bilinear %d max_iter %d eps %g: %s" % (H, W, wt, bil, mi, eps, str(e)[:200]))
+            ctx.close()
+    return n_j, bad_j, n_g, bad_g
+
+
 def main():
     a = int(sys.argv[1]) if len(sys.argv) > 1 else 40
     b = int(sys.argv[2]) if len(sys.argv) > 2 else 40
     n1, bad1 = clouds(a)
     n2, bad2 = params(b)
-    print("fuzz: %d adversarial cloud cases (6 image sizes), %d failures; %d parameter combinations x 5 scans, %d failures"
-          % (n1, bad1, n2, bad2))
-    assert bad1 == 0 and bad2 == 0
+    n_j, bad_j, n_g, bad_g = operators()
+    print("fuzz: %d adversarial cloud cases (6 image sizes), %d failures; %d parameter combinations x 5 scans, %d failures; "
+          "%d Jacobian evaluations on random clouds, %d failures; %d Gauss-Newton minimisations, %d failures"
+          % (n1, bad1, n2, bad2, n_j, bad_j, n_g, bad_g))
+    assert bad1 == 0 and bad2 == 0 and bad_j == 0 and bad_g == 0
 
 
 if __name__ == "__main__":
