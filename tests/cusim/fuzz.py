@@ -8,7 +8,9 @@
      semantic x three image sizes, three poses each;
  (d) whole Gauss-Newton minimisations (persistent kernel): real scene pairs and random clouds (degenerate systems, early
      stops), 3 weightings x 2 sampling modes x max iterations 1 / 7 / 30 x stop thresholds 0 / 1e-4 x three image sizes.
-usage: python tests/cusim/fuzz.py [n_cloud_seeds=40] [n_param_combos=40]"""
+ (e) submap paging: random walks (28 scans, random steps and turns, U-turns back over extracted tiles) with small submap
+     windows (extent 2 / 3 / 5 m, dimension 1 / 2, partial extraction on / off): the whole pipeline against the oracle.
+usage: python tests/cusim/fuzz.py [n_cloud_seeds=40] [n_param_combos=40] [n_walks=12]"""
 import os
 import random
 import sys
@@ -72,6 +74,35 @@ def params(n_combos):
             bad += 1
             print("FAIL params W=%d semantic=%r %r: %s" % (W, sem, kw, str(e)[:300]))
     return n_combos, bad
+
+
+def paging(n_walks):
+    import numpy as np
+    rnd = random.Random(3)
+    bad = 0
+    for i in range(n_walks):
+        kw = dict(submap_extent=rnd.choice((2.0, 3.0, 5.0)), submap_dimension=rnd.choice((1, 2)), partial_extraction=rnd.choice((0, 1)))
+        W = rnd.choice((360, 450))
+        poses, yaw = [np.eye(4)], 0.0
+        for t in range(1, 28):
+            yaw += np.deg2rad(rnd.uniform(-6, 6))
+            step = rnd.uniform(0.2, 0.7)
+            P = poses[-1].copy()
+            P[:2, :2] = [[np.cos(yaw), -np.sin(yaw)], [np.sin(yaw), np.cos(yaw)]]
+            P[0, 3] += step * np.cos(yaw)
+            P[1, 3] += step * np.sin(yaw)
+            if rnd.random() < 0.1:
+                yaw += np.pi * rnd.choice((0.5, 1.0))
+            poses.append(P)
+        scene = synth.Scene(width=W, height=64, semantic=rnd.random() < 0.5, seed=300 + i)
+        sc = [scene.scan(t, poses[t]) for t in range(28)]
+        po, pp = both_params(**sized(W), **kw)
+        try:
+            T._pipeline_equal(po, pp, sc, repr(kw))
+        except AssertionError as e:
+            bad += 1
+            print("FAIL paging walk %d %r: %s" % (i, kw, str(e)[:300]))
+    return n_walks, bad
 
 
 def operators():
@@ -142,10 +173,11 @@ def main():
     n1, bad1 = clouds(a)
     n2, bad2 = params(b)
     n_j, bad_j, n_g, bad_g = operators()
+    n_w, bad_w = paging(int(sys.argv[3]) if len(sys.argv) > 3 else 12)
     print("fuzz: %d adversarial cloud cases (6 image sizes), %d failures; %d parameter combinations x 5 scans, %d failures; "
-          "%d Jacobian evaluations on random clouds, %d failures; %d Gauss-Newton minimisations, %d failures"
-          % (n1, bad1, n2, bad2, n_j, bad_j, n_g, bad_g))
-    assert bad1 == 0 and bad2 == 0 and bad_j == 0 and bad_g == 0
+          "%d Jacobian evaluations on random clouds, %d failures; %d Gauss-Newton minimisations, %d failures; "
+          "%d paging random walks x 28 scans, %d failures" % (n1, bad1, n2, bad2, n_j, bad_j, n_g, bad_g, n_w, bad_w))
+    assert bad1 == 0 and bad2 == 0 and bad_j == 0 and bad_g == 0 and bad_w == 0
 
 
 if __name__ == "__main__":
