@@ -935,10 +935,14 @@ __global__ void __launch_bounds__(kThreads) k_update_surfels(KParams kp, SurfelP
     float x, y, z;
     project01(vertex, kp.fov_up, kp.fov, kp.min_depth, kp.max_depth, x, y, z);
     float ix = floorf(x * (float)W) + 0.5f, iy = floorf(y * (float)H) + 0.5f;
-    float4 Vt = data_tex(f.vertex, W, H, ix, iy);
-    float4 Nt = data_tex(f.normal, W, H, ix, iy);
-    bool valid = (Vt.w > 0.5f) && (Nt.w > 0.5f);
     bool inside = (ix < (float)W && iy < (float)H && z < 1.0f) && !(ix < 0.0f && iy < 0.0f && z < 0.0f);
+    // the measurement is only ever used under (valid && inside && visible): back-facing surfels skip the two gathers
+    float4 Vt = make_float4(0.f, 0.f, 0.f, 0.f), Nt = Vt;
+    if (visible && inside) {
+      Vt = data_tex(f.vertex, W, H, ix, iy);
+      Nt = data_tex(f.normal, W, H, ix, iy);
+    }
+    bool valid = (Vt.w > 0.5f) && (Nt.w > 0.5f);
     float penalty = 0.0f;
     float update_conf = kp.log_prior;
     size_t dpix = 0;
