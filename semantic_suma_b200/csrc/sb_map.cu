@@ -615,7 +615,7 @@ struct Px {
 };
 
 __device__ __forceinline__ Px resolve_px(const SurfelPlanes& s, unsigned long long key, const float* __restrict__ M_old,
-                                         const float* __restrict__ M_new, int fixed_pass, int lequal) {
+                                         const float* __restrict__ M_new, int fixed_pass, int lequal, bool need_semantic) {
   Px o;
   o.v = o.n = o.s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (key == ~0ull) return o;
@@ -634,7 +634,7 @@ __device__ __forceinline__ Px resolve_px(const SurfelPlanes& s, unsigned long lo
   V3 nn = xform_dir(M, mk3(p1.x, p1.y, p1.z));
   o.v = make_float4(pp.x, pp.y, pp.z, 1.0f);  // render_surfels.frag:30, .geom:95-97 (flat: surfel centre)
   o.n = make_float4(nn.x, nn.y, nn.z, 1.0f);
-  o.s = __ldg(s.p3 + k);
+  if (need_semantic) o.s = __ldg(s.p3 + k);  // Q4: the single-view renderings keep the previous semantic image
   return o;
 }
 
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(kThreads) k_render_resolve(KParams kp, SurfelP
   if (t.key_old) {
     ko_raw = t.key_old[pix];
     t.key_old[pix] = ~0ull;
-    po = resolve_px(s, ko_raw, M_old, M_new, 0, 0);
+    po = resolve_px(s, ko_raw, M_old, M_new, 0, 0, !keep_semantic);
     f_old.vertex[pix] = po.v;
     f_old.normal[pix] = po.n;
     if (!keep_semantic) f_old.semantic[pix] = po.s;
@@ -659,7 +659,7 @@ __global__ void __launch_bounds__(kThreads) k_render_resolve(KParams kp, SurfelP
   if (t.key_new) {
     kn_raw = t.key_new[pix];
     t.key_new[pix] = ~0ull;
-    pn = resolve_px(s, kn_raw, M_old, M_new, 1, 0);
+    pn = resolve_px(s, kn_raw, M_old, M_new, 1, 0, !keep_semantic);
     f_new.vertex[pix] = pn.v;
     f_new.normal[pix] = pn.n;
     if (!keep_semantic) f_new.semantic[pix] = pn.s;
@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(kThreads) k_render_resolve(KParams kp, SurfelP
     // union of both passes is the smaller of the two per-pass winners, depth first, then pass, then surfel index
     unsigned long long ko = ko_raw, kn = kn_raw;
     if (kn != ~0ull) kn |= (1ull << 32);
-    Px pc = resolve_px(s, ko < kn ? ko : kn, M_old, M_new, -1, 0);
+    Px pc = resolve_px(s, ko < kn ? ko : kn, M_old, M_new, -1, 0, !keep_semantic);
     f_comp.vertex[pix] = pc.v;
     f_comp.normal[pix] = pc.n;
     if (!keep_semantic) f_comp.semantic[pix] = pc.s;
@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(kThreads) k_render_resolve(KParams kp, SurfelP
   if (t.key_comp) {
     unsigned long long kc = t.key_comp[pix];
     t.key_comp[pix] = ~0ull;
-    Px pc = resolve_px(s, kc, M_old, M_new, -1, lequal);
+    Px pc = resolve_px(s, kc, M_old, M_new, -1, lequal, !keep_semantic);
     f_comp.vertex[pix] = pc.v;
     f_comp.normal[pix] = pc.n;
     if (!keep_semantic) f_comp.semantic[pix] = pc.s;
