@@ -59,7 +59,7 @@ def build(force=False, verbose=False):
         out, _ = pr.communicate()
         if pr.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, out.decode()))
-    cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB] + objs
+    cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
     subprocess.check_call(cmd)
     return LIB
 
