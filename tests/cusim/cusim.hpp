@@ -292,8 +292,20 @@ static inline unsigned __float_as_uint(float f) { return cusim::pack(f) & 0xffff
 static inline float __uint_as_float(unsigned u) { return cusim::unpack<float>(u); }
 static inline int __float_as_int(float f) { return (int)__float_as_uint(f); }
 static inline float __int_as_float(int i) { return __uint_as_float((unsigned)i); }
-static inline long long __float2ll_rn(float f) { return llrintf(f); }
-static inline long long __double2ll_rn(double d) { return llrint(d); }
+// PTX cvt semantics, not x86's: NaN converts to 0 and out-of-range values saturate (x86 returns 0x8000... for both), so a
+// NaN or an overflow that reaches a conversion shows on the executor the way it would on the GPU
+static inline long long __float2ll_rn(float f) {
+  if (f != f) return 0;
+  if (f >= 9223372036854775808.0f) return 0x7fffffffffffffffll;
+  if (f <= -9223372036854775808.0f) return (long long)0x8000000000000000ull;
+  return llrintf(f);
+}
+static inline long long __double2ll_rn(double d) {
+  if (d != d) return 0;
+  if (d >= 9223372036854775808.0) return 0x7fffffffffffffffll;
+  if (d <= -9223372036854775808.0) return (long long)0x8000000000000000ull;
+  return llrint(d);
+}
 static inline double __hiloint2double(int hi, int lo) {
   return cusim::unpack<double>(((uint64_t)(uint32_t)hi << 32) | (uint64_t)(uint32_t)lo);
 }

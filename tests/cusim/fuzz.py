@@ -10,6 +10,9 @@
      stops), 3 weightings x 2 sampling modes x max iterations 1 / 7 / 30 x stop thresholds 0 / 1e-4 x three image sizes.
  (e) submap paging: random walks (28 scans, random steps and turns, U-turns back over extracted tiles) with small submap
      windows (extent 2 / 3 / 5 m, dimension 1 / 2, partial extraction on / off): the whole pipeline against the oracle.
+ (f) pathological scans: 2 % of the points carry NaN / +-inf / +-1e30 / denormal coordinates, NaN probabilities, NaN / huge /
+     negative labels -- whole pipeline, four scans, three widths (the executor converts float -> integer the PTX way: NaN -> 0,
+     saturation, where x86 returns 0x8000...; run it with CUSIM_ASAN=1 for the memcheck of these inputs).
 usage: python tests/cusim/fuzz.py [n_cloud_seeds=40] [n_param_combos=40] [n_walks=12]"""
 import os
 import random
@@ -105,6 +108,36 @@ def paging(n_walks):
     return n_walks, bad
 
 
+def pathological():
+    import numpy as np
+    from helpers import bits
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    n = bad = 0
+    for rep in range(6):
+        W = (360, 450, 361)[rep % 3]
+        po, pp = both_params(**sized(W))
+        scene = synth.Scene(width=W, height=64, semantic=True, seed=50 + rep)
+        poses = synth.trajectory(4)
+        g, o = api.SurfelMapping(pp), O.Slam(po)
+        for t in range(4):
+            pts, lab, prb = (a.copy() for a in scene.scan(t, poses[t]))
+            m = pts.shape[0]
+            idx = rng.integers(0, m, m // 50)
+            vals = np.array([np.nan, np.inf, -np.inf, 1e30, -1e30, 1e-40, 0.0], np.float32)
+            pts[idx, rng.integers(0, 3, idx.shape[0])] = rng.choice(vals, idx.shape[0])
+            prb[rng.integers(0, m, 50)] = np.nan
+            lab[rng.integers(0, m, 50)] = rng.choice(np.array([np.nan, 1e9, -5.0], np.float32), 50)
+            g.processScan(pts, lab, prb)
+            o.process_scan(pts, lab, prb)
+            n += 1
+            if not (np.array_equal(bits(g.getCurrentPose()), bits(o.pose())) and g.getMap().size() == o.map.size()):
+                bad += 1
+                print("FAIL pathological scan: width %d scan %d" % (W, t))
+        g.ctx.close()
+    return n, bad
+
+
 def operators():
     import itertools
 
@@ -174,10 +207,12 @@ def main():
     n2, bad2 = params(b)
     n_j, bad_j, n_g, bad_g = operators()
     n_w, bad_w = paging(int(sys.argv[3]) if len(sys.argv) > 3 else 12)
+    n_p, bad_p = pathological()
     print("fuzz: %d adversarial cloud cases (6 image sizes), %d failures; %d parameter combinations x 5 scans, %d failures; "
           "%d Jacobian evaluations on random clouds, %d failures; %d Gauss-Newton minimisations, %d failures; "
-          "%d paging random walks x 28 scans, %d failures" % (n1, bad1, n2, bad2, n_j, bad_j, n_g, bad_g, n_w, bad_w))
-    assert bad1 == 0 and bad2 == 0 and bad_j == 0 and bad_g == 0 and bad_w == 0
+          "%d paging random walks x 28 scans, %d failures; %d scans with NaN / inf / 1e30 points, %d failures"
+          % (n1, bad1, n2, bad2, n_j, bad_j, n_g, bad_g, n_w, bad_w, n_p, bad_p))
+    assert bad1 == 0 and bad2 == 0 and bad_j == 0 and bad_g == 0 and bad_w == 0 and bad_p == 0
 
 
 if __name__ == "__main__":
