@@ -75,7 +75,7 @@ def main():
     assert out["metric"] == "scans_per_sec" and out["n_gpus"] == 1 and out["gpu_launches"] > 0
     for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
         assert k in out["e2e"], k
-    assert out["e2e"]["h2d_bytes_per_step"] > 1_000_000
+    assert out["e2e"]["h2d_bytes_per_step"] > 500_000
     assert "error" not in (out["roofline"] or {}), out["roofline"]
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert k in out["roofline"], k

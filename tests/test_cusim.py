@@ -84,7 +84,7 @@ def test_racecheck_of_the_kernels():
     volatile hand-overs order anything): first the tool on two toy kernels -- a missing __syncthreads / __syncwarp is reported,
     a present one is not --, then a semantic run with the in-kernel exchange: only the two known by-design report kinds
     (tests/cusim/racecheck.py; the 24-test run is in profiles/r02_cusim_runs.txt)"""
-    for args in (["--selftest"], []):
+    for args in (["--selftest"], ["2"]):
         r = subprocess.run([sys.executable, os.path.join(HERE, "cusim", "racecheck.py")] + args, cwd=ROOT, capture_output=True,
                            text=True, timeout=1500)
         if r.returncode == 77:
@@ -106,7 +106,7 @@ def test_bench_native_arm_dry_run():
     CPU baseline, the JSON line with every key of the contract) with the CUDA sources on the executor and torch's CUDA calls
     stubbed: the line is complete. Its numbers mean nothing."""
     r = subprocess.run([sys.executable, os.path.join(HERE, "cusim", "bench_dryrun.py"), "--steps", "3", "--warmup", "3", "--preroll", "2",
-                        "--cpu-budget", "1"], cwd=ROOT, capture_output=True, text=True, timeout=1200)
+                        "--cpu-budget", "1", "--workload", "hdl64_900_geometric"], cwd=ROOT, capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0 and "bench dry run ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
 
 
